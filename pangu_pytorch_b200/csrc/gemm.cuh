@@ -1,0 +1,370 @@
+// Persistent, warp-specialised tcgen05 GEMM engine for sm_100a.
+//
+//   C[M, N] = A[M, K] * B[N, K]^T     A, B: 16-bit (bf16 or fp16), K contiguous; fp32 accumulate
+//
+// * operands arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B, 64-element K slabs) into a
+//   multi-stage shared-memory ring guarded by full/empty mbarriers;
+// * one elected thread issues tcgen05.mma (M=128, N<=256 per instruction, K=16) with the
+//   accumulator in tensor memory; tcgen05.commit releases ring slots / publishes the tile;
+// * eight epilogue warps (two warpgroups, alternating 32-column chunks) read the accumulator
+//   with tcgen05.ld (one thread == one output row, so LayerNorm statistics are thread-local),
+//   apply the fused epilogue (bias / q-scale / GELU / LayerNorm / residual), stage the chunk
+//   in shared memory and write it out with coalesced, row-remapped 16-byte stores.  The row
+//   remaps implement window-partition / roll / crop without ever
+//   materialising a permuted tensor.
+//
+// Epilogue variants are selected by a compile-time config struct (see gemm_kernels.cu).
+#pragma once
+#include "common.cuh"
+#include "geometry.cuh"
+
+namespace pg {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 x 16-bit = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+
+enum RowMapKind { RM_IDENT = 0, RM_WIN2TOK = 1, RM_UPSAMPLE = 2 };
+enum DstMapKind { DM_IDENT = 0, DM_TOK2WIN = 1 };
+enum RecoverKind { RC_NONE = 0, RC_UPPER = 1, RC_SURFACE = 2 };
+
+struct GemmShape {
+  int M;             // valid rows of A
+  int num_m_blocks;  // ceil(M / 128)
+  int num_n_blocks;  // N / BN
+  int num_k_blocks;  // K / 64 (A and A2 together)
+  int k_split;       // k-blocks taken from A; the rest come from A2 (== num_k_blocks if unused)
+};
+
+struct EpiArgs {
+  const float* bias;    // [N] or nullptr
+  const float* gamma;   // LayerNorm weight [BN] (LN configs)
+  const float* beta;    // LayerNorm bias   [BN]
+  const float* resid;   // fp32 residual stream, natural token rows
+  float* out32;         // fp32 output
+  void* out16;          // 16-bit output
+  float* out32b;        // second fp32 field (unused except RECOVER: nothing) -- reserved
+  int ld32, ld16;       // row pitches in elements
+  int Z, H, W;          // token grid of the row maps
+  int roll_in;          // RM_WIN2TOK: roll state of the window-ordered A rows
+  int roll_out;         // DM_TOK2WIN: roll state of the window-ordered 16-bit output
+  int q_cols;           // columns [0, q_cols) are multiplied by q_scale (QKV: q *= 32^-0.5)
+  float q_scale;
+  float res_scale;      // DropPath factor on the normalised branch (1 in eval)
+  float eps;
+  int lat, lon;         // RECOVER: output field extents (721, 1440)
+};
+
+// ---------------------------------------------------------------------------------------
+template <class Cfg>
+struct GemmTraits {
+  static constexpr int BN = Cfg::BN;
+  static constexpr int UN = Cfg::UN;                 // N per tcgen05.mma (<= 256, % 16 == 0)
+  static constexpr int NUM_B = BN / UN;
+  static constexpr int CH = Cfg::CH;                 // epilogue chunk (columns)
+  static constexpr int STAGES = Cfg::STAGES;
+  static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS_RAW = ACC_STAGES * BN;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
+                                   : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_PITCH = CH * 4 + 16;      // bytes; == 16 (mod 128) -> conflict-free 16 B rows
+  static constexpr int STG_BYTES = BLOCK_M * STG_PITCH;
+  static constexpr int PAR_BYTES = 3 * BN * 4;       // bias / gamma / beta per warpgroup
+  static constexpr int TAB_BYTES = 2 * BLOCK_M * 4;  // row -> token, row -> 16-bit destination row
+  static constexpr int WG_BYTES = STG_BYTES + PAR_BYTES + TAB_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * WG_BYTES + BAR_BYTES;
+  static_assert(BN % UN == 0 && UN % 16 == 0 && UN <= 256, "bad N tiling");
+  static_assert(BN % CH == 0 && (CH == 16 || CH == 32), "bad epilogue chunk");
+  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024 B alignment");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+constexpr int kNumThreads = 320;      // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int kEpiThreads = 256;
+
+template <class Cfg, bool kFp16>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+            const __grid_constant__ CUtensorMap tmB, const GemmShape shape, const EpiArgs ep) {
+  using T = GemmTraits<Cfg>;
+  constexpr int BN = T::BN, UN = T::UN, CH = T::CH;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* wg_area = smem + T::STAGES * T::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wg_area + 2 * T::WG_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + T::STAGES;          // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * T::STAGES;      // [ACC_STAGES]
+  uint64_t* tempty_bar = tfull_bar + T::ACC_STAGES;  // [ACC_STAGES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + T::ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = shape.num_m_blocks * shape.num_n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < T::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < T::ACC_STAGES; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], kEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<T::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / shape.num_n_blocks, n_blk = tile % shape.num_n_blocks;
+        for (int kb = 0; kb < shape.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = ring + stage * T::STAGE_BYTES;
+          uint8_t* sb = sa + T::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], T::STAGE_BYTES);
+          if (kb < shape.k_split)
+            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
+          else
+            tma_load_2d(&tmA2, &full_bar[stage], sa, (kb - shape.k_split) * BLOCK_K, m_blk * BLOCK_M);
+#pragma unroll
+          for (int j = 0; j < T::NUM_B; ++j)
+            tma_load_2d_hint(&tmB, &full_bar[stage], sb + j * UN * 128, kb * BLOCK_K, n_blk * BN + j * UN, kEvictLast);
+          if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, UN, kFp16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < shape.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + stage * T::STAGE_BYTES);
+          const uint64_t da = make_sdesc_sw128(sa);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+#pragma unroll
+            for (int j = 0; j < T::NUM_B; ++j) {
+              const uint64_t db = make_sdesc_sw128(sa + T::A_BYTES + j * UN * 128);
+              // advancing K by 16 elements = 32 B inside the swizzle row: +2 in the (addr>>4) field
+              umma_f16_ss(tmem_base + acc * BN + j * UN, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the ring slot once these MMAs have read it
+          if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int wg = (warp - 2) >> 2;            // 0 / 1: alternates column chunks
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;          // tile row owned by this thread (phase A)
+    const int tid = ((warp - 2) & 3) * 32 + lane;  // 0..127 inside the warpgroup (phase B)
+    uint8_t* my = wg_area + wg * T::WG_BYTES;
+    uint8_t* stg = my;
+    float* s_bias = reinterpret_cast<float*>(my + T::STG_BYTES);
+    float* s_gamma = s_bias + BN;
+    float* s_beta = s_gamma + BN;
+    int* s_tok = reinterpret_cast<int*>(my + T::STG_BYTES + T::PAR_BYTES);
+    int* s_dst = s_tok + BLOCK_M;
+    const int bar_id = 1 + wg;
+    const Geo geo = make_geo(ep.Z, ep.H, ep.W);
+
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int loaded_n_blk = -1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / shape.num_n_blocks, n_blk = tile % shape.num_n_blocks;
+      // ---- per-tile tables (overlaps the mainloop of this tile)
+      named_bar_sync(bar_id, 128);  // previous tile's phase B done with tables/params
+      {
+        const int g = m_blk * BLOCK_M + tid;  // logical A row
+        int tok = -1;
+        if (g < shape.M) {
+          if constexpr (Cfg::ROWMAP == RM_IDENT) tok = g;
+          else if constexpr (Cfg::ROWMAP == RM_WIN2TOK) tok = win_row_to_token(geo, g, ep.roll_in);
+          else tok = upsample_row_to_token(geo, g, n_blk);
+        }
+        int dst = tok;
+        if constexpr (Cfg::DSTMAP == DM_TOK2WIN) { if (tok >= 0) dst = token_to_win_row(geo, tok, ep.roll_out); }
+        s_tok[tid] = tok;
+        s_dst[tid] = dst;
+        if (loaded_n_blk != n_blk) {
+          for (int c = tid; c < BN; c += 128) {
+            s_bias[c] = ep.bias ? ep.bias[n_blk * BN + c] : 0.f;
+            if constexpr (Cfg::LN) { s_gamma[c] = ep.gamma[c]; s_beta[c] = ep.beta[c]; }
+          }
+          loaded_n_blk = n_blk;
+        }
+      }
+      named_bar_sync(bar_id, 128);
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+
+      float mean = 0.f, rstd = 1.f;
+      if constexpr (Cfg::LN) {
+        // thread-local LayerNorm statistics over the whole row (shifted sums)
+        float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tacc + c0, r);
+          tmem_ld_wait();
+          if (c0 == 0) shift = __uint_as_float(r[0]) + s_bias[0];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(r[j]) + s_bias[c0 + j] - shift;
+            s1 += v;
+            s2 = fmaf(v, v, s2);
+          }
+        }
+        const float inv_n = 1.0f / float(BN);
+        const float m = s1 * inv_n;
+        const float var = fmaxf(s2 * inv_n - m * m, 0.f);
+        mean = shift + m;
+        rstd = rsqrtf(var + ep.eps);
+      }
+
+#pragma unroll 1
+      for (int c0 = wg * CH; c0 < BN; c0 += 2 * CH) {
+        // ---------------- phase A: TMEM -> registers -> math -> staging (row per thread)
+        {
+          uint32_t r[CH];
+          if constexpr (CH == 32) tmem_ld32(tacc + c0, r); else tmem_ld16(tacc + c0, r);
+          tmem_ld_wait();
+          const int ncol0 = n_blk * BN + c0;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            float v = __uint_as_float(r[j]) + s_bias[c0 + j];
+            if constexpr (Cfg::LN) v = (v - mean) * rstd * s_gamma[c0 + j] + s_beta[c0 + j];
+            if constexpr (Cfg::SCALEQ) { if (ncol0 + j < ep.q_cols) v *= ep.q_scale; }
+            if constexpr (Cfg::GELU) v = gelu_erf(v);
+            r[j] = __float_as_uint(v);
+          }
+          uint4* dstp = reinterpret_cast<uint4*>(stg + row * T::STG_PITCH);
+#pragma unroll
+          for (int j = 0; j < CH / 4; ++j) dstp[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+        named_bar_sync(bar_id, 128);
+        // ---------------- phase B: staging -> global, coalesced, row-remapped
+        if constexpr (Cfg::RECOVER != RC_NONE) {
+          constexpr int PPR = CH / 4;  // 16 B fp32 pieces per row
+#pragma unroll
+          for (int it = 0; it < PPR; ++it) {
+            const int id = it * 128 + tid;
+            const int rr = id / PPR, pc = id % PPR;
+            const int tok = s_tok[rr];
+            if (tok < 0) continue;
+            const int grp = (c0 >> 2) + pc;        // (c, dz, dh) for upper, (c, dh) for surface
+            const int wt = tok % geo.W, ht = (tok / geo.W) % geo.H, zt = tok / (geo.W * geo.H);
+            const int dh = grp & 3;
+            const int la = 4 * ht + dh;
+            if (la >= ep.lat) continue;
+            size_t off;
+            if constexpr (Cfg::RECOVER == RC_UPPER) {
+              const int dz = (grp >> 2) & 1, c = grp >> 3;
+              const int lev = 2 * zt + dz;
+              if (lev >= 13) continue;
+              off = ((size_t(c) * 13 + lev) * ep.lat + la) * ep.lon + 4 * wt;
+            } else {
+              const int c = grp >> 2;
+              off = (size_t(c) * ep.lat + la) * ep.lon + 4 * wt;
+            }
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * T::STG_PITCH + pc * 16);
+            stg16(ep.out32 + off, v);
+          }
+        } else if constexpr (Cfg::OUT32) {
+          constexpr int PPR = CH / 4;
+#pragma unroll
+          for (int it = 0; it < PPR; ++it) {
+            const int id = it * 128 + tid;
+            const int rr = id / PPR, pc = id % PPR;
+            const int tok = s_tok[rr];
+            if (tok < 0) continue;
+            const int col = (Cfg::GROUPCOL ? 0 : n_blk * BN) + c0 + pc * 4;
+            uint4 v = *reinterpret_cast<const uint4*>(stg + rr * T::STG_PITCH + pc * 16);
+            float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y), f2 = __uint_as_float(v.z),
+                  f3 = __uint_as_float(v.w);
+            if constexpr (Cfg::RESID) {
+              const uint4 q = ldg_nc16(ep.resid + size_t(tok) * ep.ld32 + col);
+              f0 = fmaf(ep.res_scale, f0, __uint_as_float(q.x));
+              f1 = fmaf(ep.res_scale, f1, __uint_as_float(q.y));
+              f2 = fmaf(ep.res_scale, f2, __uint_as_float(q.z));
+              f3 = fmaf(ep.res_scale, f3, __uint_as_float(q.w));
+            }
+            stg16(ep.out32 + size_t(tok) * ep.ld32 + col,
+                  make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)));
+            if constexpr (Cfg::OUT16) {
+              uint2 h = make_uint2(pack16<kFp16>(f0, f1), pack16<kFp16>(f2, f3));
+              *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out16) + size_t(s_dst[rr]) * ep.ld16 + col) = h;
+            }
+          }
+        } else {
+          // 16-bit only: 8 columns (32 B of staging) -> one 16 B store
+          constexpr int PPR = CH / 8;
+#pragma unroll
+          for (int it = 0; it < PPR; ++it) {
+            const int id = it * 128 + tid;
+            const int rr = id / PPR, pc = id % PPR;
+            const int tok = s_tok[rr];
+            if (tok < 0) continue;
+            const int col = (Cfg::GROUPCOL ? 0 : n_blk * BN) + c0 + pc * 8;
+            const uint4 a = *reinterpret_cast<const uint4*>(stg + rr * T::STG_PITCH + pc * 32);
+            const uint4 b = *reinterpret_cast<const uint4*>(stg + rr * T::STG_PITCH + pc * 32 + 16);
+            uint4 h;
+            h.x = pack16<kFp16>(__uint_as_float(a.x), __uint_as_float(a.y));
+            h.y = pack16<kFp16>(__uint_as_float(a.z), __uint_as_float(a.w));
+            h.z = pack16<kFp16>(__uint_as_float(b.x), __uint_as_float(b.y));
+            h.w = pack16<kFp16>(__uint_as_float(b.z), __uint_as_float(b.w));
+            stg16(reinterpret_cast<uint16_t*>(ep.out16) + size_t(s_dst[rr]) * ep.ld16 + col, h);
+          }
+        }
+        named_bar_sync(bar_id, 128);  // staging free again
+      }
+      // accumulator drained by this thread
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<T::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace pg
