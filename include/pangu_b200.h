@@ -1,0 +1,128 @@
+/* pangu_b200 -- C ABI of the B200 (sm_100a) Pangu-Weather hot path.
+ *
+ * The reference (zhaoshan2/pangu-pytorch) has no FFI layer: its hot path is the nn.Module
+ * code in models/layers.py and models/pangu_model.py.  This library replaces the ATen op
+ * chains of those modules with hand-written kernels; the Python host
+ * (pangu_pytorch_b200/models/*.py) binds these entry points with ctypes and keeps the
+ * reference's module API and state_dict layout.  Each entry point cites the reference
+ * code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never allocates,
+ *     frees or retains memory.  Workspaces are caller-provided.
+ *   - all work is enqueued on `stream` (a cudaStream_t); no host synchronisation inside.
+ *   - `fp16` selects the 16-bit operand format of activations/weights: 0 = bf16, 1 = fp16.
+ *     Accumulation, LayerNorm, softmax and the residual stream are always fp32.
+ *   - return 0 on success, negative on error (bad shape / alignment / CUDA error);
+ *     pangu_last_error() returns a thread-local message.  No fallbacks: unsupported shapes
+ *     are rejected.
+ *   - token grids: (Z, H, W) is the un-padded grid (8,181,360 / 8,91,180 at 0.25 deg; W may be
+ *     any multiple of 12).  "window order" means row = (lon_window*types + type)*144 + k with
+ *     the +5 zero-pad latitude rows included; "natural order" means
+ *     row = (z*H + h)*W + w.
+ */
+#ifndef PANGU_B200_H
+#define PANGU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* pangu_last_error(void);
+int pangu_version(void);
+/* 0 when the current device is sm_100 and the kernels are loadable, negative otherwise. */
+int pangu_check_device(void);
+
+/* fp32 -> 16-bit cast of a [rows, k_src] matrix into [rows, k_dst] (zero padded columns).
+ * Weight preparation for the nn.Linear / nn.Conv1d(k=1) weights (layout (out, in), as stored
+ * in the reference state_dict; models/onnx2torch.py:41-44). */
+int pangu_cast16(const float* src, void* dst, int rows, int k_src, int k_dst, int fp16, void* stream);
+
+/* F.pad + torch.roll + window partition of EarthSpecificBlock.forward (models/layers.py:188-221)
+ * applied to a plain fp32 residual stream: x32 [T,C] natural -> x16w [Tp,C] window order for
+ * roll state `roll` (pad rows zero); roll < 0 = plain cast in natural order.  Only needed when a
+ * block is entered from an fp32 tensor; inside the model the producing GEMM writes this layout. */
+int pangu_to_window16(const float* x32, void* x16w, int Z, int H, int W, int C, int roll, int fp16, void* stream);
+
+/* PatchEmbedding_pretrain.forward (models/layers.py:40-93).
+ * Normalise + zero-pad + concat constants + 2x4x4 / 4x4 im2col into `ws_a_upper`
+ * [7*Hh*Ww,192] and `ws_a_surface` [Hh*Ww,128], then two GEMMs (+bias).
+ * Outputs: x32 [8*Hh*Ww,192] fp32 natural order; x16w: 16-bit copy in window order (roll 0)
+ * for the first block's QKV GEMM (pad rows must have been zeroed once by the caller). */
+int pangu_patch_embed(const float* upper, const float* surface,
+                      const float* surface_mean, const float* surface_std,
+                      const float* upper_mean, const float* upper_std,
+                      const float* maps, const float* const_h,
+                      const void* w_upper16 /*[192,192]*/, const float* b_upper,
+                      const void* w_surface16 /*[192,128] K zero-padded*/, const float* b_surface,
+                      void* ws_a_upper, void* ws_a_surface,
+                      float* x32, void* x16w,
+                      int lat, int lon, int fp16, void* stream);
+
+/* EarthAttention3D.linear1 + head split + q*scale (models/layers.py:365-374).
+ * x16w [Tp, C] window order -> qkv16 [Tp, 3C] window order, q pre-scaled by 32^-0.5. */
+int pangu_qkv(const void* x16w, const void* w16 /*[3C,C]*/, const float* bias /*[3C]*/,
+              void* qkv16, int Z, int H, int W, int C, int fp16, void* stream);
+
+/* q k^T + earth_specific_bias (+ shift mask, gen_mask models/layers.py:153-181) -> softmax ->
+ * P v, heads merged (models/layers.py:378-415).  bias: the fp32 parameter
+ * [1, types, heads, 144, 144] as stored in the state_dict. */
+int pangu_window_attention(const void* qkv16, const float* earth_bias, void* att16,
+                           int Z, int H, int W, int C, int heads, int roll, int fp16, void* stream);
+
+/* EarthAttention3D.linear2 + window reverse + un-roll + crop + norm1 + residual
+ * (models/layers.py:418, 227-250):  x32[tok] += res_scale * LN1(att W2^T + b2).
+ * Also writes x16 (natural order) = cast(x32) for the MLP. In-place on x32. */
+int pangu_proj_ln_residual(const void* att16, const void* w16 /*[C,C]*/, const float* bias,
+                           const float* gamma, const float* beta,
+                           float* x32, void* x16, int Z, int H, int W, int C, int roll,
+                           float res_scale, int fp16, void* stream);
+
+/* Mlp.forward + norm2 + residual (models/layers.py:264-270, 251):
+ *   x32 += res_scale * LN2(GELU(x W1^T + b1) W2^T + b2)      (exact erf GELU)
+ * x16_in natural order; ws_hidden [T, 4C] 16-bit workspace.  x16_out: 16-bit copy of the new
+ * residual stream, in natural order when roll_out < 0, else in window order for a following
+ * block with roll state roll_out (pad rows never written). */
+int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16 /*[4C,C]*/, const float* b1,
+                          const void* w2_16 /*[C,4C]*/, const float* b2,
+                          const float* gamma, const float* beta,
+                          void* ws_hidden, float* x32, void* x16_out,
+                          int Z, int H, int W, int C, int roll_out,
+                          float res_scale, int fp16, void* stream);
+
+/* DownSample.forward (models/layers.py:432-459): pad + 2x2 merge + LN(4C) -> ws_a [T2,4C];
+ * GEMM (no bias) -> x32_out [T2, 2C] natural, x16w_out window order (roll 0) on the low grid. */
+int pangu_downsample(const float* x32_in, const float* gamma, const float* beta,
+                     const void* w16 /*[2C,4C]*/, void* ws_a, float* x32_out, void* x16w_out,
+                     int Z, int H, int W, int C, int fp16, void* stream);
+
+/* UpSample.forward (models/layers.py:474-499): GEMM1 (no bias) with pixel-shuffle + crop +
+ * LN(C_out) fused in the epilogue -> ws_a [T, C_out]; GEMM2 (no bias) -> x32_out natural,
+ * x16w_out window order (roll 0) on the high grid (Z, H, W). x16_in: low grid, natural. */
+int pangu_upsample(const void* x16_in, const void* w1_16 /*[4Co,Ci]*/, const float* gamma, const float* beta,
+                   const void* w2_16 /*[Co,Co]*/, void* ws_a, float* x32_out, void* x16w_out,
+                   int Z, int H, int W, int C_in, int C_out, int fp16, void* stream);
+
+/* torch.cat((skip, x), -1) + PatchRecovery_pretrain.forward (models/pangu_model.py:81,
+ * models/layers.py:511-545): the concat is folded into the GEMM K loop (two A sources);
+ * un-patchify + crop (14->13 levels, 4*H->lat) in the epilogue.  Outputs normalised fields
+ * out_upper [5,13,lat,lon], out_surface [4,lat,lon]. */
+int pangu_patch_recover(const void* skip16, const void* x16, const void* w_upper16 /*[160,384]*/,
+                        const float* b_upper, const void* w_surface16 /*[64,384]*/, const float* b_surface,
+                        float* out_upper, float* out_surface,
+                        int Z, int H, int W, int C, int lat, int lon, int fp16, void* stream);
+
+/* Generic nn.Linear forward used by the stand-alone module API (EarthAttention3D.linear2,
+ * Mlp.linear1/2 outside the fused block path) and by the unit tests of the tcgen05 GEMM engine:
+ * out = a16 [M,K] * w16 [N,K]^T + bias.  gelu == 0: fp32 out32 and 16-bit out16 (both required),
+ * N % 192 == 0.  gelu != 0: exact-erf GELU applied, 16-bit out16 only, N % 256 == 0.  K % 64 == 0. */
+int pangu_linear(const void* a16, const void* w16, const float* bias, float* out32, void* out16,
+                 int M, int N, int K, int gelu, int fp16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANGU_B200_H */

@@ -101,6 +101,21 @@ def gen_maps():
     print("maps: ok (oracle == reference, exact)")
 
 
+def gen_keys():
+    """state_dict contract: the reference's 223 keys, shapes and dtypes in registration order."""
+    import json
+    _, RM = import_reference()
+    model = RM.PanguModel(device="cpu")
+    sd = model.state_dict()
+    rows = [[k, list(v.shape), str(v.dtype)] for k, v in sd.items()]
+    assert [r[0] for r in rows] == [n for n, _ in O.param_shapes()]
+    assert [tuple(r[1]) for r in rows] == [tuple(s) for _, s in O.param_shapes()]
+    assert len(list(model.buffers())) == 0
+    with open(os.path.join(GOLD, "state_dict_keys.json"), "w") as fh:
+        json.dump(rows, fh, indent=0)
+    print(f"keys: {len(rows)} entries, {sum(v.numel() for v in sd.values())} parameters")
+
+
 def gen_blocks():
     """One EarthSpecificBlock per resolution, stress weights, W=24 strip, both roll states;
     also DownSample at W=24 (the only other W-generic module)."""
@@ -195,12 +210,12 @@ def gen_full(kind: str):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="maps,blocks,full,stress")
+    ap.add_argument("--what", default="maps,keys,blocks,full,stress")
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
     for w in args.what.split(","):
         t0 = time.time()
-        {"maps": gen_maps, "blocks": gen_blocks, "full": lambda: gen_full("full"),
+        {"maps": gen_maps, "keys": gen_keys, "blocks": gen_blocks, "full": lambda: gen_full("full"),
          "stress": lambda: gen_full("stress")}[w]()
         print(f"[{w}] done in {time.time() - t0:.1f}s")

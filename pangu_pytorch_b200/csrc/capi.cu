@@ -1,0 +1,450 @@
+// Host side of the C ABI declared in include/pangu_b200.h: argument validation, TMA
+// tensor-map encoding, kernel configuration and launches.  No allocation, no syncs.
+#include "../../include/pangu_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+using namespace pg;
+
+// ---------------------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define PG_REQUIRE(cond, ...) do { if (!(cond)) return fail(-1, __VA_ARGS__); } while (0)
+#define PG_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) \
+  return fail(-2, "%s failed: %s", #expr, cudaGetErrorString(e__)); } while (0)
+#define PG_TRY(expr) do { int r__ = (expr); if (r__ != 0) return r__; } while (0)
+
+extern "C" const char* pangu_last_error(void) { return g_err; }
+extern "C" int pangu_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------------------
+// device / driver entry points
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 0;
+static int g_cc_major = 0;
+static std::once_flag g_once;
+static int g_init_status = 0;
+
+static void init_once() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { g_init_status = -3; return; }
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&g_cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+    g_init_status = -4;
+    return;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+static int ensure_init() {
+  std::call_once(g_once, init_once);
+  if (g_init_status != 0) return fail(g_init_status, "pangu_b200: CUDA device / driver entry point unavailable");
+  if (g_cc_major != 10) return fail(-5, "pangu_b200: requires an sm_100 (B200) device, found sm_%d*", g_cc_major);
+  return 0;
+}
+
+extern "C" int pangu_check_device(void) { return ensure_init(); }
+
+// 2-D K-major operand map: dim0 = K (contiguous), dim1 = rows; box = 64 x box_rows, 128 B swizzle,
+// out-of-bounds rows read as zero (this is what pads ragged M tails).
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t k, uint64_t pitch_elems,
+                    uint32_t box_rows) {
+  PG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "operand base %p not 16 B aligned", base);
+  PG_REQUIRE((pitch_elems * 2) % 16 == 0, "operand pitch %llu not a multiple of 16 B", (unsigned long long)pitch_elems * 2);
+  PG_REQUIRE(box_rows <= 256 && k % 64 == 0, "bad box (%u rows, K=%llu)", box_rows, (unsigned long long)k);
+  cuuint64_t dims[2] = {k, rows};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled failed (%d)", int(r));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// GEMM configurations (epilogue variants)
+// ---------------------------------------------------------------------------------------
+struct CfgBase {
+  static constexpr bool LN = false, GELU = false, SCALEQ = false, RESID = false, OUT32 = false, OUT16 = false,
+                        GROUPCOL = false;
+  static constexpr int RECOVER = RC_NONE;
+  static constexpr int CH = 32;
+};
+struct CfgQKV : CfgBase {      // linear1 of attention: bias, q-scale, 16-bit out
+  static constexpr int BN = 192, UN = 192, STAGES = 4;
+  static constexpr bool SCALEQ = true, OUT16 = true;
+};
+struct CfgMLP1 : CfgBase {     // Mlp.linear1: bias + exact GELU, 16-bit out
+  static constexpr int BN = 256, UN = 256, STAGES = 3;
+  static constexpr bool GELU = true, OUT16 = true;
+};
+struct CfgLNRes192 : CfgBase { // bias + LayerNorm(192) + residual, fp32 + 16-bit out
+  static constexpr int BN = 192, UN = 192, STAGES = 4;
+  static constexpr bool LN = true, RESID = true, OUT32 = true, OUT16 = true;
+};
+struct CfgLNRes384 : CfgBase { // bias + LayerNorm(384) + residual
+  static constexpr int BN = 384, UN = 192, STAGES = 3, CH = 16;
+  static constexpr bool LN = true, RESID = true, OUT32 = true, OUT16 = true;
+};
+struct CfgPlain192 : CfgBase { // (bias) -> fp32 + 16-bit (embed, downsample.linear, upsample.linear2, tests)
+  static constexpr int BN = 192, UN = 192, STAGES = 4;
+  static constexpr bool OUT32 = true, OUT16 = true;
+};
+struct CfgUpLN : CfgBase {     // upsample.linear1: pixel shuffle + crop + LayerNorm(192) -> 16-bit
+  static constexpr int BN = 192, UN = 192, STAGES = 4;
+  static constexpr bool LN = true, OUT16 = true, GROUPCOL = true;
+};
+struct CfgRecU : CfgBase {     // _output_layer.conv: bias + un-patchify + crop (upper-air)
+  static constexpr int BN = 160, UN = 160, STAGES = 4;
+  static constexpr int RECOVER = RC_UPPER;
+};
+struct CfgRecS : CfgBase {     // _output_layer.conv_surface
+  static constexpr int BN = 64, UN = 64, STAGES = 4;
+  static constexpr int RECOVER = RC_SURFACE;
+};
+
+struct GemmOperands {
+  const void* a; uint64_t a_pitch;     // rows = M
+  const void* a2; uint64_t a2_pitch;   // optional second K range
+  int k1, k2;                          // K taken from a / a2 (multiples of 64)
+  const void* b; uint64_t b_pitch;     // [N, K]
+  int M, N;
+};
+
+template <class Cfg, bool kFp16>
+static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t stream) {
+  using T = GemmTraits<Cfg>;
+  PG_REQUIRE(o.N % Cfg::BN == 0, "N=%d not a multiple of the %d-column tile", o.N, Cfg::BN);
+  PG_REQUIRE(o.k1 % 64 == 0 && o.k2 % 64 == 0 && o.k1 > 0, "K (%d + %d) must be multiples of 64", o.k1, o.k2);
+  PG_REQUIRE(o.M > 0, "empty M");
+  CUtensorMap ma, ma2, mb;
+  PG_TRY(make_map(&ma, o.a, o.M, o.k1, o.a_pitch, BLOCK_M));
+  if (o.k2 > 0) PG_TRY(make_map(&ma2, o.a2, o.M, o.k2, o.a2_pitch, BLOCK_M)); else ma2 = ma;
+  PG_TRY(make_map(&mb, o.b, o.N, o.k1 + o.k2, o.b_pitch, Cfg::UN));
+  GemmShape sh;
+  sh.M = o.M;
+  sh.num_m_blocks = (o.M + BLOCK_M - 1) / BLOCK_M;
+  sh.num_n_blocks = o.N / Cfg::BN;
+  sh.num_k_blocks = (o.k1 + o.k2) / 64;
+  sh.k_split = o.k1 / 64;
+  auto kern = gemm_kernel<Cfg, kFp16>;
+  static bool attr_done = false;   // per instantiation
+  if (!attr_done) {
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles = sh.num_m_blocks * sh.num_n_blocks;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  kern<<<grid, kNumThreads, T::SMEM_BYTES, stream>>>(ma, ma2, mb, sh, ep);
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+template <class Cfg>
+static int launch_gemm(const GemmOperands& o, const EpiArgs& ep, int fp16, cudaStream_t s) {
+  return fp16 ? launch_gemm_t<Cfg, true>(o, ep, s) : launch_gemm_t<Cfg, false>(o, ep, s);
+}
+
+static EpiArgs epi_defaults() {
+  EpiArgs e;
+  memset(&e, 0, sizeof(e));
+  e.Z = 8; e.H = 1; e.W = 12;
+  e.res_scale = 1.f; e.q_scale = 1.f; e.eps = 1e-5f;
+  e.rowmap = RM_IDENT; e.dstmap = DM_IDENT;
+  return e;
+}
+
+static int check_grid(int Z, int H, int W, int C, int heads) {
+  PG_REQUIRE(Z == 8, "Z must be 8 (got %d)", Z);
+  PG_REQUIRE((H + 5) % 6 == 0, "H+5 must be a multiple of 6 (got H=%d)", H);
+  PG_REQUIRE(W % 12 == 0 && W > 0, "W must be a positive multiple of 12 (got %d)", W);
+  PG_REQUIRE(C == 192 || C == 384, "C must be 192 or 384 (got %d)", C);
+  PG_REQUIRE(heads == 0 || heads * 32 == C, "heads*32 must equal C");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// entry points
+// ---------------------------------------------------------------------------------------
+extern "C" int pangu_cast16(const float* src, void* dst, int rows, int k_src, int k_dst, int fp16, void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(rows > 0 && k_src > 0 && k_dst >= k_src, "bad cast16 shape");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = size_t(rows) * k_dst;
+  const int grid = int((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  if (fp16) cast16_kernel<true><<<grid, 256, 0, s>>>(src, static_cast<uint16_t*>(dst), rows, k_src, k_dst);
+  else cast16_kernel<false><<<grid, 256, 0, s>>>(src, static_cast<uint16_t*>(dst), rows, k_src, k_dst);
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pangu_to_window16(const float* x32, void* x16w, int Z, int H, int W, int C, int roll, int fp16,
+                                 void* stream) {
+  PG_TRY(ensure_init());
+  PG_TRY(check_grid(Z, H, W, C, 0));
+  const Geo g = make_geo(Z, H, W);
+  const int rows = roll < 0 ? Z * H * W : g.nLon * g.types * 144;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int blocks = (rows * 32 + 255) / 256;
+  if (fp16) to_window16_kernel<true><<<blocks, 256, 0, s>>>(x32, static_cast<uint16_t*>(x16w), g, C, roll, rows);
+  else to_window16_kernel<false><<<blocks, 256, 0, s>>>(x32, static_cast<uint16_t*>(x16w), g, C, roll, rows);
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pangu_patch_embed(const float* upper, const float* surface, const float* surface_mean,
+                                 const float* surface_std, const float* upper_mean, const float* upper_std,
+                                 const float* maps, const float* const_h, const void* w_upper16,
+                                 const float* b_upper, const void* w_surface16, const float* b_surface,
+                                 void* ws_a_upper, void* ws_a_surface, float* x32, void* x16w, int lat, int lon,
+                                 int fp16, void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(lon % 48 == 0 && lon > 0, "lon must be a positive multiple of 48 (got %d)", lon);
+  const int Hh = (lat + 3) / 4, Ww = lon / 4;
+  PG_TRY(check_grid(8, Hh, Ww, 192, 0));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  EmbedArgs ea{upper, surface, surface_mean, surface_std, upper_mean, upper_std, maps, const_h,
+               ws_a_upper, ws_a_surface, lat, lon, Hh, Ww};
+  dim3 grid((Ww + EMB_TT - 1) / EMB_TT, Hh, 8);
+  if (fp16) embed_im2col_kernel<true><<<grid, EMB_THREADS, 0, s>>>(ea);
+  else embed_im2col_kernel<false><<<grid, EMB_THREADS, 0, s>>>(ea);
+  PG_CUDA(cudaGetLastError());
+  const int plane = Hh * Ww;
+  EpiArgs ep = epi_defaults();
+  ep.Z = 8; ep.H = Hh; ep.W = Ww;
+  ep.ld32 = 192; ep.ld16 = 192;
+  ep.dstmap = DM_TOK2WIN; ep.roll_out = 0;
+  // surface plane: tokens [0, plane)
+  {
+    GemmOperands o{ws_a_surface, 128, nullptr, 0, 128, 0, w_surface16, 128, plane, 192};
+    ep.bias = b_surface; ep.out32 = x32; ep.out16 = x16w; ep.row_base = 0;
+    PG_TRY(launch_gemm<CfgPlain192>(o, ep, fp16, s));
+  }
+  // upper-air planes: tokens [plane, 8*plane)
+  {
+    GemmOperands o{ws_a_upper, 192, nullptr, 0, 192, 0, w_upper16, 192, 7 * plane, 192};
+    ep.bias = b_upper; ep.row_base = plane;
+    PG_TRY(launch_gemm<CfgPlain192>(o, ep, fp16, s));
+  }
+  return 0;
+}
+
+extern "C" int pangu_qkv(const void* x16w, const void* w16, const float* bias, void* qkv16, int Z, int H, int W,
+                         int C, int fp16, void* stream) {
+  PG_TRY(ensure_init());
+  PG_TRY(check_grid(Z, H, W, C, 0));
+  const Geo g = make_geo(Z, H, W);
+  const int Tp = g.nLon * g.types * 144;
+  GemmOperands o{x16w, uint64_t(C), nullptr, 0, C, 0, w16, uint64_t(C), Tp, 3 * C};
+  EpiArgs ep = epi_defaults();
+  ep.bias = bias; ep.out16 = qkv16; ep.ld16 = 3 * C;
+  ep.q_cols = C; ep.q_scale = 0.17677669529663687f;   // 32^-0.5, models/layers.py:289
+  return launch_gemm<CfgQKV>(o, ep, fp16, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pangu_window_attention(const void* qkv16, const float* earth_bias, void* att16, int Z, int H, int W,
+                                      int C, int heads, int roll, int fp16, void* stream) {
+  PG_TRY(ensure_init());
+  PG_TRY(check_grid(Z, H, W, C, heads));
+  const Geo g = make_geo(Z, H, W);
+  AttnArgs a;
+  a.qkv = qkv16; a.bias = earth_bias; a.out = att16;
+  a.C = C; a.heads = heads; a.types = g.types; a.nLon = g.nLon; a.nH = g.nH; a.roll = roll ? 1 : 0;
+  // split the longitude walk so that the grid is a few waves of the SM count
+  const int base = g.types * heads;
+  int best_split = 1;
+  double best_eff = 0.0;
+  for (int sp = 1; sp <= g.nLon && sp <= 6; ++sp) {
+    const int per = (g.nLon + sp - 1) / sp;
+    const int nsp = (g.nLon + per - 1) / per;
+    const double ctas = double(base) * nsp;
+    const double waves = ctas / g_num_sms;
+    const double full = double(long(waves + 0.999999));
+    // cost model: waves * (per windows + ~1.5 windows of fixed bias-load cost)
+    const double cost = full * (per + 1.5);
+    const double eff = 1.0 / cost;
+    if (eff > best_eff) { best_eff = eff; best_split = nsp; a.lon_per_cta = per; }
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid(base, best_split);
+  static bool attr_done[2] = {false, false};
+  if (fp16) {
+    if (!attr_done[1]) {
+      PG_CUDA(cudaFuncSetAttribute(window_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+      attr_done[1] = true;
+    }
+    window_attention_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(a);
+  } else {
+    if (!attr_done[0]) {
+      PG_CUDA(cudaFuncSetAttribute(window_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+      attr_done[0] = true;
+    }
+    window_attention_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(a);
+  }
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pangu_proj_ln_residual(const void* att16, const void* w16, const float* bias, const float* gamma,
+                                      const float* beta, float* x32, void* x16, int Z, int H, int W, int C, int roll,
+                                      float res_scale, int fp16, void* stream) {
+  PG_TRY(ensure_init());
+  PG_TRY(check_grid(Z, H, W, C, 0));
+  const Geo g = make_geo(Z, H, W);
+  const int Tp = g.nLon * g.types * 144;
+  GemmOperands o{att16, uint64_t(C), nullptr, 0, C, 0, w16, uint64_t(C), Tp, C};
+  EpiArgs ep = epi_defaults();
+  ep.Z = Z; ep.H = H; ep.W = W;
+  ep.bias = bias; ep.gamma = gamma; ep.beta = beta;
+  ep.resid = x32; ep.out32 = x32; ep.out16 = x16; ep.ld32 = C; ep.ld16 = C;
+  ep.rowmap = RM_WIN2TOK; ep.roll_in = roll ? 1 : 0; ep.dstmap = DM_IDENT;
+  ep.res_scale = res_scale;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return C == 192 ? launch_gemm<CfgLNRes192>(o, ep, fp16, s) : launch_gemm<CfgLNRes384>(o, ep, fp16, s);
+}
+
+extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, const float* b1, const void* w2_16,
+                                     const float* b2, const float* gamma, const float* beta, void* ws_hidden,
+                                     float* x32, void* x16_out, int Z, int H, int W, int C, int roll_out,
+                                     float res_scale, int fp16, void* stream) {
+  PG_TRY(ensure_init());
+  PG_TRY(check_grid(Z, H, W, C, 0));
+  const int T = Z * H * W;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    GemmOperands o{x16_in, uint64_t(C), nullptr, 0, C, 0, w1_16, uint64_t(C), T, 4 * C};
+    EpiArgs ep = epi_defaults();
+    ep.bias = b1; ep.out16 = ws_hidden; ep.ld16 = 4 * C;
+    PG_TRY(launch_gemm<CfgMLP1>(o, ep, fp16, s));
+  }
+  {
+    GemmOperands o{ws_hidden, uint64_t(4 * C), nullptr, 0, 4 * C, 0, w2_16, uint64_t(4 * C), T, C};
+    EpiArgs ep = epi_defaults();
+    ep.Z = Z; ep.H = H; ep.W = W;
+    ep.bias = b2; ep.gamma = gamma; ep.beta = beta;
+    ep.resid = x32; ep.out32 = x32; ep.out16 = x16_out; ep.ld32 = C; ep.ld16 = C;
+    ep.rowmap = RM_IDENT;
+    ep.dstmap = roll_out < 0 ? DM_IDENT : DM_TOK2WIN;
+    ep.roll_out = roll_out > 0 ? 1 : 0;
+    ep.res_scale = res_scale;
+    PG_TRY(C == 192 ? launch_gemm<CfgLNRes192>(o, ep, fp16, s) : launch_gemm<CfgLNRes384>(o, ep, fp16, s));
+  }
+  return 0;
+}
+
+extern "C" int pangu_downsample(const float* x32_in, const float* gamma, const float* beta, const void* w16,
+                                void* ws_a, float* x32_out, void* x16w_out, int Z, int H, int W, int C, int fp16,
+                                void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(C == 192 && Z == 8 && W % 24 == 0, "downsample: C must be 192, Z 8, W a multiple of 24");
+  const int H2 = (H + 1) / 2, W2 = W / 2;
+  PG_TRY(check_grid(Z, H2, W2, 384, 0));
+  const int T2 = Z * H2 * W2;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DownArgs da{x32_in, gamma, beta, ws_a, Z, H, W, C, 1e-5f};
+  const int blocks = (T2 * 32 + 255) / 256;
+  if (fp16) downsample_gather_ln_kernel<true><<<blocks, 256, 0, s>>>(da);
+  else downsample_gather_ln_kernel<false><<<blocks, 256, 0, s>>>(da);
+  PG_CUDA(cudaGetLastError());
+  GemmOperands o{ws_a, 768, nullptr, 0, 768, 0, w16, 768, T2, 384};
+  EpiArgs ep = epi_defaults();
+  ep.Z = Z; ep.H = H2; ep.W = W2;
+  ep.out32 = x32_out; ep.out16 = x16w_out; ep.ld32 = 384; ep.ld16 = 384;
+  ep.dstmap = DM_TOK2WIN; ep.roll_out = 0;
+  return launch_gemm<CfgPlain192>(o, ep, fp16, s);
+}
+
+extern "C" int pangu_upsample(const void* x16_in, const void* w1_16, const float* gamma, const float* beta,
+                              const void* w2_16, void* ws_a, float* x32_out, void* x16w_out, int Z, int H, int W,
+                              int C_in, int C_out, int fp16, void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(C_in == 384 && C_out == 192 && Z == 8 && W % 24 == 0, "upsample: expects 384 -> 192 on a W%%24 grid");
+  PG_TRY(check_grid(Z, H, W, C_out, 0));
+  const int H2 = (H + 1) / 2, W2 = W / 2;
+  const int T2 = Z * H2 * W2, T = Z * H * W;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    GemmOperands o{x16_in, 384, nullptr, 0, 384, 0, w1_16, 384, T2, 768};
+    EpiArgs ep = epi_defaults();
+    ep.Z = Z; ep.H = H; ep.W = W;             // HIGH-res grid for the pixel-shuffle map
+    ep.gamma = gamma; ep.beta = beta;
+    ep.out16 = ws_a; ep.ld16 = 192;
+    ep.rowmap = RM_UPSAMPLE;
+    PG_TRY(launch_gemm<CfgUpLN>(o, ep, fp16, s));
+  }
+  {
+    GemmOperands o{ws_a, 192, nullptr, 0, 192, 0, w2_16, 192, T, 192};
+    EpiArgs ep = epi_defaults();
+    ep.Z = Z; ep.H = H; ep.W = W;
+    ep.out32 = x32_out; ep.out16 = x16w_out; ep.ld32 = 192; ep.ld16 = 192;
+    ep.dstmap = DM_TOK2WIN; ep.roll_out = 0;
+    PG_TRY(launch_gemm<CfgPlain192>(o, ep, fp16, s));
+  }
+  return 0;
+}
+
+extern "C" int pangu_patch_recover(const void* skip16, const void* x16, const void* w_upper16, const float* b_upper,
+                                   const void* w_surface16, const float* b_surface, float* out_upper,
+                                   float* out_surface, int Z, int H, int W, int C, int lat, int lon, int fp16,
+                                   void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(C == 192 && Z == 8, "recover: C must be 192 per source (384 concatenated), Z 8");
+  PG_REQUIRE(lon == 4 * W && (lat + 3) / 4 == H, "recover: field extents do not match the token grid");
+  const int plane = H * W;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint16_t* sk = static_cast<const uint16_t*>(skip16);
+  const uint16_t* xx = static_cast<const uint16_t*>(x16);
+  EpiArgs ep = epi_defaults();
+  ep.Z = Z - 1; ep.H = H; ep.W = W; ep.lat = lat; ep.lon = lon;
+  {
+    GemmOperands o{sk + size_t(plane) * C, uint64_t(C), xx + size_t(plane) * C, uint64_t(C), C, C,
+                   w_upper16, uint64_t(2 * C), 7 * plane, 160};
+    ep.bias = b_upper; ep.out32 = out_upper;
+    PG_TRY(launch_gemm<CfgRecU>(o, ep, fp16, s));
+  }
+  {
+    GemmOperands o{sk, uint64_t(C), xx, uint64_t(C), C, C, w_surface16, uint64_t(2 * C), plane, 64};
+    ep.bias = b_surface; ep.out32 = out_surface;
+    PG_TRY(launch_gemm<CfgRecS>(o, ep, fp16, s));
+  }
+  return 0;
+}
+
+extern "C" int pangu_linear(const void* a16, const void* w16, const float* bias, float* out32, void* out16, int M,
+                            int N, int K, int gelu, int fp16, void* stream) {
+  PG_TRY(ensure_init());
+  GemmOperands o{a16, uint64_t(K), nullptr, 0, K, 0, w16, uint64_t(K), M, N};
+  EpiArgs ep = epi_defaults();
+  ep.bias = bias; ep.out32 = out32; ep.out16 = out16; ep.ld32 = N; ep.ld16 = N;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (gelu) {
+    PG_REQUIRE(out16 != nullptr && N % 256 == 0, "pangu_linear(gelu): needs a 16-bit output and N %% 256 == 0");
+    return launch_gemm<CfgMLP1>(o, ep, fp16, s);
+  }
+  PG_REQUIRE(out32 != nullptr && out16 != nullptr && N % 192 == 0, "pangu_linear: needs both outputs and N %% 192 == 0");
+  return launch_gemm<CfgPlain192>(o, ep, fp16, s);
+}

@@ -1,0 +1,179 @@
+// Memory-bound gather kernels that build GEMM A-operands without materialising the
+// reference's permute/pad/cat chains:
+//   * embed_im2col_kernel      (models/layers.py:48-85)
+//   * downsample_gather_ln_kernel (models/layers.py:436-454)
+//   * cast16_kernel            fp32 -> bf16/fp16 (weight preparation, zero padded K)
+#pragma once
+#include "common.cuh"
+#include "geometry.cuh"
+
+namespace pg {
+
+constexpr int EMB_TT = 120;                // tokens per CTA tile (480 longitudes)
+constexpr int EMB_PITCH = 192 * 2 + 8;     // bytes per staged token row (+8: conflict-free 8 B column writes)
+constexpr int EMB_THREADS = 256;
+
+struct EmbedArgs {
+  const float* upper;     // [5][13][lat][lon]
+  const float* surface;   // [4][lat][lon]
+  const float* s_mean; const float* s_std;   // [4]
+  const float* u_mean; const float* u_std;   // [13][5]  (level axis reversed w.r.t. data, layers.py:73-76)
+  const float* maps;      // [3][4*Hh][lon]
+  const float* const_h;   // [13][lat][lon]
+  void* a_upper;          // [7*Hh*Ww][192] 16-bit, feature ((c*2+dz)*4+dh)*4+dw
+  void* a_surface;        // [Hh*Ww][128]   16-bit, feature (c*4+dh)*4+dw, zero for f >= 112
+  int lat, lon, Hh, Ww;
+};
+
+template <bool kFp16>
+__global__ void __launch_bounds__(EMB_THREADS) embed_im2col_kernel(const EmbedArgs a) {
+  __shared__ __align__(16) uint8_t tile[EMB_TT * EMB_PITCH];
+  const int zp = blockIdx.z;                 // 0 = surface plane, 1..7 = upper patch level zt + 1
+  const int ht = blockIdx.y;
+  const int wt0 = blockIdx.x * EMB_TT;
+  const int ntok = min(EMB_TT, a.Ww - wt0);
+  const int nfeat = zp == 0 ? 128 : 192;
+  const int ngrp = zp == 0 ? 28 : 48;        // (c, [dz,] dh) groups of 4 dw
+  const size_t plane = size_t(a.lat) * a.lon;
+
+  // zero fill for the surface K padding (features 112..127)
+  if (zp == 0) {
+    for (int i = threadIdx.x; i < ntok * 4; i += EMB_THREADS)
+      *reinterpret_cast<uint2*>(tile + (i >> 2) * EMB_PITCH + 224 + (i & 3) * 8) = make_uint2(0u, 0u);
+  }
+  for (int idx = threadIdx.x; idx < ngrp * ntok; idx += EMB_THREADS) {
+    const int grp = idx / ntok, tk = idx % ntok;     // consecutive threads -> consecutive longitudes
+    const int dh = grp & 3;
+    const int la = 4 * ht + dh;
+    const int lo = 4 * (wt0 + tk);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (zp == 0) {
+      const int c = grp >> 2;                        // 0..6
+      if (c < 4) {
+        if (la < a.lat) {
+          v = *reinterpret_cast<const float4*>(a.surface + c * plane + size_t(la) * a.lon + lo);
+          const float m = a.s_mean[c], s = a.s_std[c];
+          v.x = (v.x - m) / s; v.y = (v.y - m) / s; v.z = (v.z - m) / s; v.w = (v.w - m) / s;
+        }
+      } else {
+        v = *reinterpret_cast<const float4*>(a.maps + (size_t(c - 4) * (4 * a.Hh) + la) * a.lon + lo);
+      }
+    } else {
+      const int dz = (grp >> 2) & 1, c = grp >> 3;   // 0..5
+      const int lev = 2 * (zp - 1) + dz;
+      if (lev < 13 && la < a.lat) {
+        if (c < 5) {
+          v = *reinterpret_cast<const float4*>(a.upper + (size_t(c) * 13 + lev) * plane + size_t(la) * a.lon + lo);
+          const float m = a.u_mean[(12 - lev) * 5 + c], s = a.u_std[(12 - lev) * 5 + c];
+          v.x = (v.x - m) / s; v.y = (v.y - m) / s; v.z = (v.z - m) / s; v.w = (v.w - m) / s;
+        } else {
+          v = *reinterpret_cast<const float4*>(a.const_h + size_t(lev) * plane + size_t(la) * a.lon + lo);
+        }
+      }
+    }
+    *reinterpret_cast<uint2*>(tile + tk * EMB_PITCH + grp * 8) =
+        make_uint2(pack16<kFp16>(v.x, v.y), pack16<kFp16>(v.z, v.w));
+  }
+  __syncthreads();
+  // the tile's token rows are contiguous in the output: flat 8-byte copy
+  const int p8 = nfeat / 4;                          // 8 B pieces per token
+  uint2* dst;
+  if (zp == 0) dst = reinterpret_cast<uint2*>(a.a_surface) + (size_t(ht) * a.Ww + wt0) * p8;
+  else dst = reinterpret_cast<uint2*>(a.a_upper) + ((size_t(zp - 1) * a.Hh + ht) * a.Ww + wt0) * p8;
+  for (int i = threadIdx.x; i < ntok * p8; i += EMB_THREADS)
+    dst[i] = *reinterpret_cast<const uint2*>(tile + (i / p8) * EMB_PITCH + (i % p8) * 8);
+}
+
+// ---------------------------------------------------------------------------------------
+struct DownArgs {
+  const float* x;       // [Z*H*W][C] fp32
+  const float* gamma;   // [4C]
+  const float* beta;    // [4C]
+  void* out;            // [Z*H2*W2][4C] 16-bit
+  int Z, H, W, C;       // C == 192
+  float eps;
+};
+
+// one warp per output token: 2x2 merge (zero row when 2*h2+dh == H) + LayerNorm(4C)
+template <bool kFp16>
+__global__ void __launch_bounds__(256) downsample_gather_ln_kernel(const DownArgs a) {
+  const int H2 = (a.H + 1) / 2, W2 = a.W / 2;
+  const int ntok = a.Z * H2 * W2;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= ntok) return;
+  const int w2 = warp % W2, h2 = (warp / W2) % H2, z = warp / (W2 * H2);
+  // 4C = 768 values = 192 float4; lane handles float4 index lane + 32*i (i < 6):
+  //   index q -> dh = q / 96, within-row offset (q % 96) covers the two adjacent tokens (dw, c)
+  float4 v[6];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int q = lane + 32 * i;
+    const int dh = q / 96, r = q % 96;
+    const int h = 2 * h2 + dh;
+    if (h < a.H) {
+      v[i] = *reinterpret_cast<const float4*>(a.x + (size_t(z * a.H + h) * a.W + 2 * w2) * a.C + r * 4);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / 768.0f);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    ss += dx * dx + dy * dy + dz * dz + dw * dw;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss * (1.0f / 768.0f) + a.eps);
+  uint2* dst = reinterpret_cast<uint2*>(a.out) + size_t(warp) * 192;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int q = lane + 32 * i;
+    const float4 g = *reinterpret_cast<const float4*>(a.gamma + q * 4);
+    const float4 b = *reinterpret_cast<const float4*>(a.beta + q * 4);
+    const float y0 = (v[i].x - mean) * rstd * g.x + b.x, y1 = (v[i].y - mean) * rstd * g.y + b.y;
+    const float y2 = (v[i].z - mean) * rstd * g.z + b.z, y3 = (v[i].w - mean) * rstd * g.w + b.w;
+    dst[q] = make_uint2(pack16<kFp16>(y0, y1), pack16<kFp16>(y2, y3));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// x32 [T][C] natural order -> x16w [Tp][C] window order for roll state `roll` (pad rows = 0).
+// Only used when a block is entered from a plain fp32 tensor (module-level API); inside the
+// model the producing GEMM epilogue writes this layout directly.
+template <bool kFp16>
+__global__ void __launch_bounds__(256) to_window16_kernel(const float* __restrict__ x, uint16_t* __restrict__ out,
+                                                          Geo g, int C, int roll, int rows) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int tok = roll < 0 ? row : win_row_to_token(g, row, roll);
+  uint2* dst = reinterpret_cast<uint2*>(out + size_t(row) * C);
+  for (int q = lane; q < C / 4; q += 32) {
+    uint2 h = make_uint2(0u, 0u);
+    if (tok >= 0) {
+      const float4 v = *reinterpret_cast<const float4*>(x + size_t(tok) * C + q * 4);
+      h = make_uint2(pack16<kFp16>(v.x, v.y), pack16<kFp16>(v.z, v.w));
+    }
+    dst[q] = h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// dst[r][0..kd) = cast(src[r][0..ks)), zero for columns ks..kd (K padding of conv_surface)
+template <bool kFp16>
+__global__ void cast16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int rows, int ks, int kd) {
+  const size_t n = size_t(rows) * kd;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const int r = int(i / kd), c = int(i % kd);
+    dst[i] = c < ks ? cvt16<kFp16>(src[size_t(r) * ks + c]) : uint16_t(0);
+  }
+}
+
+}  // namespace pg

@@ -43,8 +43,10 @@ struct EpiArgs {
   const float* resid;   // fp32 residual stream, natural token rows
   float* out32;         // fp32 output
   void* out16;          // 16-bit output
-  float* out32b;        // second fp32 field (unused except RECOVER: nothing) -- reserved
   int ld32, ld16;       // row pitches in elements
+  int rowmap;           // RowMapKind: A row -> output token
+  int dstmap;           // DstMapKind: output token -> row of the 16-bit output
+  int row_base;         // RM_IDENT: token = A row + row_base
   int Z, H, W;          // token grid of the row maps
   int roll_in;          // RM_WIN2TOK: roll state of the window-ordered A rows
   int roll_out;         // DM_TOK2WIN: roll state of the window-ordered 16-bit output
@@ -210,12 +212,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int g = m_blk * BLOCK_M + tid;  // logical A row
         int tok = -1;
         if (g < shape.M) {
-          if constexpr (Cfg::ROWMAP == RM_IDENT) tok = g;
-          else if constexpr (Cfg::ROWMAP == RM_WIN2TOK) tok = win_row_to_token(geo, g, ep.roll_in);
+          if (ep.rowmap == RM_IDENT) tok = g + ep.row_base;
+          else if (ep.rowmap == RM_WIN2TOK) tok = win_row_to_token(geo, g, ep.roll_in);
           else tok = upsample_row_to_token(geo, g, n_blk);
         }
         int dst = tok;
-        if constexpr (Cfg::DSTMAP == DM_TOK2WIN) { if (tok >= 0) dst = token_to_win_row(geo, tok, ep.roll_out); }
+        if (ep.dstmap == DM_TOK2WIN && tok >= 0) dst = token_to_win_row(geo, tok, ep.roll_out);
         s_tok[tid] = tok;
         s_dst[tid] = dst;
         if (loaded_n_blk != n_blk) {

@@ -1,0 +1,107 @@
+"""Device-side plumbing shared by the modules: operand precision, 16-bit weight caches and
+the per-resolution activation workspaces (memory laid out once, reused every step).
+
+HBM layout of one resolution (``GridWorkspace``), T = Z*H*W real tokens, Tp = window-padded:
+
+    x32      [T , C ] fp32   residual stream, natural token order (updated in place)
+    x16      [T , C ] 16-bit shadow of x32, natural order   (A operand of Mlp.linear1, ...)
+    x16w[r]  [Tp, C ] 16-bit shadow in WINDOW order for roll state r in {0,1}; the +5 latitude
+                             pad rows are zeroed once here and never written again
+    qkv      [Tp, 3C] 16-bit window order, q pre-scaled
+    att      [Tp, C ] 16-bit window order, heads merged
+    hidden   [T , 4C] 16-bit GELU(linear1) activations
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Tuple
+
+import torch
+
+from . import ops
+
+_OPERANDS = os.environ.get("PANGU_B200_OPERANDS", "bf16").lower()
+if _OPERANDS not in ("bf16", "fp16"):
+    raise ValueError("PANGU_B200_OPERANDS must be 'bf16' or 'fp16'")
+
+
+def set_operand_dtype(name: str) -> None:
+    """'bf16' (default; range-safe) or 'fp16' (3 more mantissa bits: ~8x lower error, see
+    DESIGN.md 'Numerics').  Tensor-core rate is identical (tcgen05 kind::f16)."""
+    global _OPERANDS
+    name = name.lower()
+    if name not in ("bf16", "fp16"):
+        raise ValueError("operand dtype must be 'bf16' or 'fp16'")
+    _OPERANDS = name
+
+
+def operand_dtype() -> str:
+    return _OPERANDS
+
+
+def use_fp16() -> bool:
+    return _OPERANDS == "fp16"
+
+
+def geometry(Z: int, H: int, W: int) -> Tuple[int, int, int, int]:
+    """(T, Tp, types, nLon) of the window partition (models/layers.py:145-151, 216-221)."""
+    Hp = H + 5
+    if Z != 8 or Hp % 6 or W % 12:
+        raise ValueError(f"unsupported token grid ({Z},{H},{W})")
+    types, nlon = (Z // 2) * (Hp // 6), W // 12
+    return Z * H * W, nlon * types * 144, types, nlon
+
+
+class GridWorkspace:
+    def __init__(self, device, Z: int, H: int, W: int, C: int, fp16: bool):
+        self.Z, self.H, self.W, self.C, self.fp16 = Z, H, W, C, fp16
+        self.T, self.Tp, self.types, self.nlon = geometry(Z, H, W)
+        h = ops.dtype16(fp16)
+        T, Tp = self.T, self.Tp
+        self.x32 = torch.empty(T, C, dtype=torch.float32, device=device)
+        self.x16 = torch.empty(T, C, dtype=h, device=device)
+        self.x16w = [torch.zeros(Tp, C, dtype=h, device=device) for _ in range(2)]
+        self.qkv = torch.empty(Tp, 3 * C, dtype=h, device=device)
+        self.att = torch.empty(Tp, C, dtype=h, device=device)
+        self.hidden = torch.empty(T, 4 * C, dtype=h, device=device)
+
+
+_WORKSPACES: Dict[tuple, GridWorkspace] = {}
+
+
+def workspace(device, Z: int, H: int, W: int, C: int) -> GridWorkspace:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("pangu_pytorch_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, Z, H, W, C, use_fp16())
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        ops.check_device()
+        ws = _WORKSPACES[key] = GridWorkspace(torch.device("cuda", idx), Z, H, W, C, use_fp16())
+    return ws
+
+
+def free_workspaces() -> None:
+    _WORKSPACES.clear()
+
+
+class Weight16:
+    """Lazily maintained 16-bit copy of an fp32 parameter (re-cast when the parameter changes)."""
+
+    def __init__(self, k_pad=None):
+        self.k_pad = k_pad
+        self._key = None
+        self._val = None
+
+    def get(self, param: torch.Tensor) -> torch.Tensor:
+        key = (param.data_ptr(), param._version, use_fp16(), str(param.device))
+        if key != self._key:
+            self._val = ops.cast16(param, use_fp16(), self.k_pad)
+            self._key = key
+        return self._val
+
+
+def f32(t: torch.Tensor, device) -> torch.Tensor:
+    """Contiguous fp32 view/copy of a small tensor on ``device`` (statistics, biases)."""
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()

@@ -1,0 +1,144 @@
+"""Tensor-level wrappers over the C ABI (``include/pangu_b200.h``).
+
+Every function takes CUDA tensors that the caller owns, validates device / dtype /
+contiguity, and enqueues the kernels on torch's current stream.  Nothing here computes
+with PyTorch ops: torch is used for memory and streams only.
+"""
+from __future__ import annotations
+
+from ctypes import c_void_p
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+Tensor = torch.Tensor
+_LAUNCHES = [0]          # kernels launched through this module (bench.py reports it)
+
+# kernels per entry point (for the gpu_launches bookkeeping)
+_KERNELS_PER_CALL = {
+    "pangu_cast16": 1, "pangu_to_window16": 1, "pangu_patch_embed": 3, "pangu_qkv": 1,
+    "pangu_window_attention": 1, "pangu_proj_ln_residual": 1, "pangu_mlp_ln_residual": 2,
+    "pangu_downsample": 2, "pangu_upsample": 2, "pangu_patch_recover": 2, "pangu_linear": 1,
+}
+
+
+def launches() -> int:
+    return _LAUNCHES[0]
+
+
+def dtype16(fp16: bool) -> torch.dtype:
+    return torch.float16 if fp16 else torch.bfloat16
+
+
+def _p(t: Optional[Tensor], dtype=None, name: str = "tensor"):
+    if t is None:
+        return c_void_p(0)
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (the B200 path has no CPU fallback)")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    return c_void_p(t.data_ptr())
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _call(name, *args):
+    _lib.call(name, *args)
+    _LAUNCHES[0] += _KERNELS_PER_CALL[name]
+
+
+def check_device() -> None:
+    _lib.call("pangu_check_device")
+
+
+def cast16(src: Tensor, fp16: bool, k_pad: Optional[int] = None) -> Tensor:
+    """fp32 [rows, k] -> 16-bit [rows, k_pad] (zero padded)."""
+    src = src.detach().reshape(src.shape[0], -1).contiguous()
+    rows, k = src.shape
+    kd = k if k_pad is None else k_pad
+    out = torch.empty(rows, kd, dtype=dtype16(fp16), device=src.device)
+    _call("pangu_cast16", _p(src, torch.float32, "src"), _p(out), rows, k, kd, int(fp16), _stream())
+    return out
+
+
+def cast_rows(src32: Tensor, out16: Tensor, fp16: bool) -> None:
+    """fp32 [M, C] -> existing 16-bit [M, C] buffer."""
+    M, C = src32.shape
+    _call("pangu_cast16", _p(src32, torch.float32, "src"), _p(out16, dtype16(fp16), "dst"), M, C, C, int(fp16),
+          _stream())
+
+
+def to_window16(x32: Tensor, out: Tensor, Z, H, W, C, roll: int, fp16: bool) -> None:
+    _call("pangu_to_window16", _p(x32, torch.float32, "x32"), _p(out, dtype16(fp16), "x16w"), Z, H, W, C, roll,
+          int(fp16), _stream())
+
+
+def patch_embed(upper, surface, s_mean, s_std, u_mean, u_std, maps, const_h, w_u16, b_u, w_s16, b_s,
+                ws_a_upper, ws_a_surface, x32, x16w, lat, lon, fp16: bool) -> None:
+    f = torch.float32
+    h = dtype16(fp16)
+    _call("pangu_patch_embed", _p(upper, f, "input"), _p(surface, f, "input_surface"), _p(s_mean, f), _p(s_std, f),
+          _p(u_mean, f), _p(u_std, f), _p(maps, f, "maps"), _p(const_h, f, "const_h"), _p(w_u16, h), _p(b_u, f),
+          _p(w_s16, h), _p(b_s, f), _p(ws_a_upper, h), _p(ws_a_surface, h), _p(x32, f), _p(x16w, h), lat, lon,
+          int(fp16), _stream())
+
+
+def qkv(x16w, w16, bias, out, Z, H, W, C, fp16: bool) -> None:
+    h = dtype16(fp16)
+    _call("pangu_qkv", _p(x16w, h, "x16w"), _p(w16, h), _p(bias, torch.float32), _p(out, h), Z, H, W, C, int(fp16),
+          _stream())
+
+
+def window_attention(qkv16, earth_bias, out, Z, H, W, C, heads, roll: bool, fp16: bool) -> None:
+    h = dtype16(fp16)
+    _call("pangu_window_attention", _p(qkv16, h, "qkv"), _p(earth_bias, torch.float32, "earth_specific_bias"),
+          _p(out, h), Z, H, W, C, heads, int(bool(roll)), int(fp16), _stream())
+
+
+def proj_ln_residual(att16, w16, bias, gamma, beta, x32, x16, Z, H, W, C, roll: bool, res_scale: float,
+                     fp16: bool) -> None:
+    h, f = dtype16(fp16), torch.float32
+    _call("pangu_proj_ln_residual", _p(att16, h), _p(w16, h), _p(bias, f), _p(gamma, f), _p(beta, f), _p(x32, f),
+          _p(x16, h), Z, H, W, C, int(bool(roll)), float(res_scale), int(fp16), _stream())
+
+
+def mlp_ln_residual(x16_in, w1, b1, w2, b2, gamma, beta, ws_hidden, x32, x16_out, Z, H, W, C, roll_out: int,
+                    res_scale: float, fp16: bool) -> None:
+    h, f = dtype16(fp16), torch.float32
+    _call("pangu_mlp_ln_residual", _p(x16_in, h), _p(w1, h), _p(b1, f), _p(w2, h), _p(b2, f), _p(gamma, f),
+          _p(beta, f), _p(ws_hidden, h), _p(x32, f), _p(x16_out, h), Z, H, W, C, int(roll_out), float(res_scale),
+          int(fp16), _stream())
+
+
+def downsample(x32_in, gamma, beta, w16, ws_a, x32_out, x16w_out, Z, H, W, C, fp16: bool) -> None:
+    h, f = dtype16(fp16), torch.float32
+    _call("pangu_downsample", _p(x32_in, f), _p(gamma, f), _p(beta, f), _p(w16, h), _p(ws_a, h), _p(x32_out, f),
+          _p(x16w_out, h), Z, H, W, C, int(fp16), _stream())
+
+
+def upsample(x16_in, w1, gamma, beta, w2, ws_a, x32_out, x16w_out, Z, H, W, C_in, C_out, fp16: bool) -> None:
+    h, f = dtype16(fp16), torch.float32
+    _call("pangu_upsample", _p(x16_in, h), _p(w1, h), _p(gamma, f), _p(beta, f), _p(w2, h), _p(ws_a, h),
+          _p(x32_out, f), _p(x16w_out, h), Z, H, W, C_in, C_out, int(fp16), _stream())
+
+
+def patch_recover(skip16, x16, w_u16, b_u, w_s16, b_s, out_upper, out_surface, Z, H, W, C, lat, lon,
+                  fp16: bool) -> None:
+    h, f = dtype16(fp16), torch.float32
+    _call("pangu_patch_recover", _p(skip16, h), _p(x16, h), _p(w_u16, h), _p(b_u, f), _p(w_s16, h), _p(b_s, f),
+          _p(out_upper, f), _p(out_surface, f), Z, H, W, C, lat, lon, int(fp16), _stream())
+
+
+def linear(a16, w16, bias, out32, out16, gelu: bool, fp16: bool) -> None:
+    """out = a16 @ w16.T + bias (tcgen05 GEMM engine); see ``pangu_linear`` in the header."""
+    h = dtype16(fp16)
+    M, K = a16.shape
+    N = w16.shape[0]
+    _call("pangu_linear", _p(a16, h), _p(w16, h), _p(bias, torch.float32), _p(out32, torch.float32),
+          _p(out16, h), M, N, K, int(bool(gelu)), int(fp16), _stream())

@@ -1,0 +1,217 @@
+"""Parity of the sm_100a kernels (through the C ABI) against the CPU oracle and the committed
+golden fixtures.  Run on the B200 box:  python -m pytest tests -m gpu -x -q
+
+Floating-point tolerances are relative L2 against the fp32 oracle and are stated in
+tests/util.py (TOL_BLOCK / TOL_MODEL) per operand format; index maps are compared exactly.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pangu_oracle as O
+from tests.util import TOL_BLOCK, TOL_MODEL, golden, rel_l2, sampled_rel_l2, to_device
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FORMATS = ["bf16", "fp16"]
+
+
+@pytest.fixture(autouse=True)
+def _fresh():
+    import pangu_pytorch_b200 as pb
+    yield
+    pb.free_workspaces()
+    torch.cuda.empty_cache()
+
+
+def _fmt(fmt):
+    import pangu_pytorch_b200 as pb
+    pb.set_operand_dtype(fmt)
+    pb.free_workspaces()
+    return fmt == "fp16"
+
+
+def _round16(t, fp16):
+    return t.to(torch.float16 if fp16 else torch.bfloat16)
+
+
+# ------------------------------------------------------------------ GEMM engine
+@pytest.mark.parametrize("fmt", FORMATS)
+@pytest.mark.parametrize("M,N,K", [(128, 192, 64), (1000, 192, 192), (4133, 384, 768), (20000, 768, 384)])
+def test_linear_matches_fp64_matmul(fmt, M, N, K):
+    from pangu_pytorch_b200 import ops
+    fp16 = _fmt(fmt)
+    g = torch.Generator().manual_seed(M + N + K)
+    a = _round16(torch.randn(M, K, generator=g), fp16).to(DEV)
+    w = _round16(torch.randn(N, K, generator=g) * 0.05, fp16).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    out32 = torch.full((M, N), float("nan"), device=DEV)
+    out16 = torch.empty(M, N, dtype=a.dtype, device=DEV)
+    ops.linear(a, w, b, out32, out16, False, fp16)
+    torch.cuda.synchronize()
+    ref = (a.double() @ w.double().t() + b.double())
+    assert torch.isfinite(out32).all()
+    assert rel_l2(out32, ref) < 2e-6                    # fp32 accumulation of exact 16-bit products
+    assert rel_l2(out16.float(), ref) < (1e-3 if fp16 else 6e-3)
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_linear_gelu(fmt):
+    from pangu_pytorch_b200 import ops
+    fp16 = _fmt(fmt)
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 777, 768, 192
+    a = _round16(torch.randn(M, K, generator=g), fp16).to(DEV)
+    w = _round16(torch.randn(N, K, generator=g) * 0.1, fp16).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    out16 = torch.empty(M, N, dtype=a.dtype, device=DEV)
+    ops.linear(a, w, b, None, out16, True, fp16)
+    ref = torch.nn.functional.gelu(a.double() @ w.double().t() + b.double())
+    assert rel_l2(out16.float(), ref) < (1e-3 if fp16 else 6e-3)
+
+
+# ------------------------------------------------------------------ integer contracts
+@pytest.mark.parametrize("H,C", [(181, 192), (91, 384)])
+@pytest.mark.parametrize("roll", [0, 1])
+def test_window_partition_bit_exact(H, C, roll):
+    """Index-valued input through the gather kernel == oracle map == reference map (golden)."""
+    from pangu_pytorch_b200 import ops
+    Z, W = 8, 24
+    T = Z * H * W
+    x = torch.zeros(T, C)
+    x[:, 0] = torch.arange(1, T + 1).float() % 251.0      # exactly representable in bf16/fp16
+    x[:, 1] = (torch.arange(1, T + 1) // 251).float()
+    src = O.window_source_index(Z, H, W, bool(roll)).reshape(-1)
+    g = golden("index_maps.npz")
+    assert np.array_equal(src.numpy().astype(np.int32).reshape(g[f"{'hi' if C == 192 else 'lo'}.src.roll{roll}"].shape),
+                          g[f"{'hi' if C == 192 else 'lo'}.src.roll{roll}"])
+    for fp16 in (False, True):
+        out = torch.full((src.numel(), C), 7.0, dtype=torch.float16 if fp16 else torch.bfloat16, device=DEV)
+        ops.to_window16(x.to(DEV), out, Z, H, W, C, roll, fp16)
+        got = out.float().cpu()
+        tok = (got[:, 0] + 251.0 * got[:, 1]).long() - 1
+        want = src.clone()
+        assert torch.equal(tok, want)                     # pad rows: 0 + 0 - 1 == -1
+        assert (got[src < 0] == 0).all()
+
+
+# ------------------------------------------------------------------ modules vs oracle
+def _load_block(dim, heads, pre, p):
+    import pangu_pytorch_b200 as pb
+    blk = pb.EarthSpecificBlock(dim, 0.0, heads, device=DEV)
+    blk.load_state_dict({k[len(pre):]: v for k, v in p.items() if k.startswith(pre)}, strict=True)
+    return blk.to(DEV).eval()
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+@pytest.mark.parametrize("tag", ["hi", "lo"])
+def test_attention_module(fmt, tag):
+    fp16 = _fmt(fmt)
+    dim, heads, H = (192, 6, 181) if tag == "hi" else (384, 12, 91)
+    pre = f"layers.EarthSpecificLayer{0 if tag == 'hi' else 1}.blocks.EarthSpecificBlock1."
+    p = O.stress_weights(seed=7)
+    blk = _load_block(dim, heads, pre, p)
+    nlon, types = 2, (124 if tag == "hi" else 64)
+    x = torch.randn(nlon, types, 144, dim, generator=torch.Generator().manual_seed(2))
+    for roll in (False, True):
+        mask = O.shift_mask(8, H) if roll else None
+        ref = O.window_attention(x, p, pre + "attention.", heads, mask)
+        got = blk.attention(x.to(DEV), None if mask is None else mask.to(DEV))
+        err = rel_l2(got, ref)
+        print(f"attention {tag} {fmt} roll={roll}: rel-L2 {err:.3e}")
+        assert err < TOL_BLOCK[fmt]
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+@pytest.mark.parametrize("tag", ["hi", "lo"])
+def test_block_against_oracle_and_golden(fmt, tag):
+    _fmt(fmt)
+    dim, heads, H = (192, 6, 181) if tag == "hi" else (384, 12, 91)
+    pre = f"layers.EarthSpecificLayer{0 if tag == 'hi' else 1}.blocks.EarthSpecificBlock1."
+    p = O.stress_weights(seed=7)
+    blk = _load_block(dim, heads, pre, p)
+    g = golden("blocks.npz")
+    x = torch.randn(1, 8 * H * 24, dim, generator=torch.Generator().manual_seed(11))
+    for roll in (0, 1):
+        ref = O.earth_block(x, p, pre, 8, H, 24, heads, bool(roll))
+        got = blk(x.to(DEV), 8, H, 24, bool(roll))
+        e1, e2 = rel_l2(got - x.to(DEV), ref - x), sampled_rel_l2(got, g, f"{tag}.roll{roll}")
+        print(f"block {tag} {fmt} roll={roll}: branch rel-L2 {e1:.3e}, vs golden (whole stream) {e2:.3e}")
+        assert e1 < TOL_BLOCK[fmt] and e2 < TOL_BLOCK[fmt]
+
+
+def _strip_model(p):
+    import pangu_pytorch_b200 as pb
+    m = pb.PanguModel(device=DEV)
+    m.load_state_dict(p, strict=True)
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_embed_down_up_recover_modules(fmt):
+    _fmt(fmt)
+    p = O.stress_weights(seed=3)
+    m = _strip_model(p)
+    up, sf, stats, maps, ch = O.synthetic_inputs(seed=1, lat=721, lon=96)
+    d = lambda t: t.to(DEV)
+    ref = O.patch_embed(up, sf, stats, maps, ch, p)
+    got = m._input_layer(d(up), d(sf), [d(s) for s in stats], d(maps), d(ch))
+    e = rel_l2(got, ref); print(f"embed {fmt}: {e:.3e}"); assert e < TOL_BLOCK[fmt]
+    x = torch.randn(1, 8 * 181 * 24, 192, generator=torch.Generator().manual_seed(4))
+    ref = O.down_sample(x, p, 8, 181, 24)
+    got = m.downsample(d(x), 8, 181, 24)
+    e = rel_l2(got, ref); print(f"down {fmt}: {e:.3e}"); assert e < TOL_BLOCK[fmt]
+    x2 = torch.randn(1, 8 * 91 * 12, 384, generator=torch.Generator().manual_seed(5))
+    ref = O.up_sample(x2, p, 8, 91, 12, 181)
+    got = m.upsample(d(x2))
+    e = rel_l2(got, ref); print(f"up {fmt}: {e:.3e}"); assert e < TOL_BLOCK[fmt]
+    x3 = torch.randn(1, 8 * 181 * 24, 384, generator=torch.Generator().manual_seed(6))
+    ru, rs = O.patch_recover(x3, p, 8, 181, 24, 721)
+    gu, gs = m._output_layer(d(x3), 8, 181, 24)
+    eu, es = rel_l2(gu, ru), rel_l2(gs, rs)
+    print(f"recover {fmt}: {eu:.3e} {es:.3e}")
+    assert gu.shape == ru.shape and gs.shape == rs.shape and eu < TOL_BLOCK[fmt] and es < TOL_BLOCK[fmt]
+
+
+def _per_var_err(got, ref):
+    got, ref = got.detach().double().cpu(), ref.double()
+    return ((got - ref).flatten(2).norm(dim=2) / ref.flatten(2).norm(dim=2)).reshape(-1)
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+@pytest.mark.parametrize("init", ["reference_like", "stress"])
+def test_full_depth_forward_on_strip(fmt, init):
+    """All 16 blocks + embed/down/up/recover on a 96-column longitude strip vs the oracle."""
+    _fmt(fmt)
+    p = O.reference_like_weights(seed=0) if init == "reference_like" else O.stress_weights(seed=3)
+    m = _strip_model(p)
+    up, sf, stats, maps, ch = O.synthetic_inputs(seed=1, lat=721, lon=96)
+    ru, rs = O.forward(p, up, sf, stats, maps, ch)
+    d = lambda t: t.to(DEV)
+    with torch.no_grad():
+        gu, gs = m(d(up), d(sf), [d(s) for s in stats], d(maps), d(ch))
+    eu, es = _per_var_err(gu, ru), _per_var_err(gs, rs)
+    print(f"strip forward {fmt} {init}: upper {eu.tolist()} surface {es.tolist()}")
+    assert float(eu.max()) < TOL_MODEL[fmt] and float(es.max()) < TOL_MODEL[fmt]
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+@pytest.mark.parametrize("kind", ["full", "stress"])
+def test_full_025_forward_against_reference_golden(fmt, kind):
+    """BASELINE.json config 1/2: one 24 h step at 0.25 degrees against sampled outputs of the
+    reference's own fp32 CPU forward (tests/golden/*_forward.npz)."""
+    _fmt(fmt)
+    g = golden(f"{kind}_forward.npz")
+    p = O.reference_like_weights(seed=0) if kind == "full" else O.stress_weights(seed=3, bias_std=1.0)
+    m = _strip_model(p)
+    up, sf, stats, maps, ch = O.synthetic_inputs(seed=1, nontrivial_stats=True)
+    d = lambda t: t.to(DEV)
+    with torch.no_grad():
+        gu, gs = m(d(up), d(sf), [d(s) for s in stats], d(maps), d(ch))
+    torch.cuda.synchronize()
+    eu, es = sampled_rel_l2(gu, g, "out_upper"), sampled_rel_l2(gs, g, "out_surface")
+    vu = gu[0].double().flatten(1).norm(dim=1).cpu().numpy() / g["out_upper.var_l2"]
+    vs = gs[0].double().flatten(1).norm(dim=1).cpu().numpy() / g["out_surface.var_l2"]
+    print(f"0.25deg forward {fmt} {kind}: sampled rel-L2 upper {eu:.3e} surface {es:.3e}; norm ratios {vu} {vs}")
+    assert eu < TOL_MODEL[fmt] and es < TOL_MODEL[fmt]
+    assert np.all(np.abs(vu - 1) < TOL_MODEL[fmt]) and np.all(np.abs(vs - 1) < TOL_MODEL[fmt])

@@ -1,0 +1,135 @@
+"""Host-side logic that needs no GPU: the C ABI exports what include/pangu_b200.h declares,
+the module tree reproduces the reference's state_dict layout, the device index maps (compiled
+for the host) are bit-exact against the oracle, and the product refuses to run without CUDA."""
+import ctypes
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pangu_oracle as O
+from tests.util import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from pangu_pytorch_b200 import build
+    return build.build()
+
+
+def test_cabi_exports_every_declared_symbol(lib_path):
+    from pangu_pytorch_b200 import _lib
+    names = _lib.header_symbols()
+    assert len(names) >= 14
+    lib = ctypes.CDLL(lib_path)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pangu_b200.h but not exported"
+    assert sorted(set(names) - {"pangu_last_error"}) == sorted(_lib.SIGNATURES)
+    lib.pangu_version.restype = ctypes.c_int
+    assert lib.pangu_version() >= 100
+
+
+def test_cabi_has_no_torch_or_python_dependency(lib_path):
+    out = subprocess.run(["ldd", lib_path], capture_output=True, text=True).stdout
+    assert "torch" not in out and "python" not in out and "c10" not in out
+
+
+def test_sass_contains_blackwell_instructions(lib_path):
+    """tcgen05.mma -> UTC*MMA, tcgen05.ld -> LDTM, TMA -> UTMALDG (B200_PROFILING.md)."""
+    sass = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "LDTM" in sass and "UTMALDG" in sass
+
+
+@pytest.fixture(scope="module")
+def model():
+    import pangu_pytorch_b200 as pb
+    return pb.PanguModel(device="cpu")
+
+
+def test_state_dict_layout_matches_reference(model):
+    with open(os.path.join(GOLDEN, "state_dict_keys.json")) as fh:
+        ref = json.load(fh)
+    sd = model.state_dict()
+    assert [k for k, _, _ in ref] == list(sd.keys())
+    for k, shape, dtype in ref:
+        assert list(sd[k].shape) == shape and str(sd[k].dtype) == dtype, k
+    assert len(list(model.buffers())) == 0
+    assert sum(v.numel() for v in sd.values()) == 276_659_936
+
+
+def test_state_dict_roundtrip_strict(model):
+    p = O.reference_like_weights(seed=0)
+    model.load_state_dict(p, strict=True)
+    back = model.state_dict()
+    assert all(torch.equal(back[k], p[k]) for k in p)
+
+
+def test_module_api_surface(model):
+    import pangu_pytorch_b200 as pb
+    blk = model.layers[0].blocks[1]
+    assert isinstance(blk, pb.EarthSpecificBlock) and blk.type_of_windows == 124
+    assert model.layers[1].blocks[0].type_of_windows == 64
+    assert isinstance(blk.attention.linear1, torch.nn.Linear) and blk.attention.scale == 32 ** -0.5
+    assert torch.equal(blk.attention.position_index, O.position_index())
+    assert [type(b.drop_path).__name__ for b in model.layers[0].blocks] == ["_Identity", "DropPath"]
+    assert abs(model.layers[3].blocks[1].drop_path.drop_prob - 0.2) < 1e-6       # linspace(0, .2, 16)
+    x = torch.zeros(1, 8, 186, 24, 1)
+    assert torch.equal(blk.gen_mask(x)[0], O.shift_mask(8, 181))
+    nlinear = sum(isinstance(m, torch.nn.Linear) for m in model.modules())
+    assert nlinear == 67                                                         # LoRA targets, SURVEY a17
+
+
+def test_reference_pickle_aliases():
+    import pangu_pytorch_b200 as pb
+    pb.install_reference_aliases()
+    import models.layers as ML
+    import models.pangu_model as MP
+    assert MP.PanguModel is pb.PanguModel and ML.EarthSpecificBlock is pb.EarthSpecificBlock
+    for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+        del sys.modules[k]
+
+
+def test_no_cpu_fallback(model):
+    up, sf, stats, maps, ch = O.synthetic_inputs(seed=1, lat=721, lon=96)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        with torch.no_grad():
+            model.eval()(up, sf, stats, maps, ch)
+    with pytest.raises(RuntimeError):
+        model.layers[0].blocks[0](torch.zeros(1, 8 * 181 * 24, 192), 8, 181, 24, False)
+
+
+def test_product_does_not_import_oracle():
+    import pathlib
+    for f in pathlib.Path(ROOT, "pangu_pytorch_b200").rglob("*.py"):
+        assert "oracle" not in f.read_text(), f"{f} references the oracle"
+
+
+@pytest.mark.parametrize("H,W", [(181, 24), (91, 36)])
+@pytest.mark.parametrize("roll", [0, 1])
+def test_device_index_maps_bit_exact_on_host(tmp_path, H, W, roll):
+    exe = tmp_path / "geom"
+    subprocess.run(["nvcc", "-O1", "-o", str(exe), os.path.join(ROOT, "tests", "geometry_host.cu")], check=True)
+    out = tmp_path / "maps.bin"
+    subprocess.run([str(exe), "8", str(H), str(W), str(roll), str(out)], check=True)
+    raw = np.fromfile(out, dtype=np.int32)
+    src = O.window_source_index(8, H, W, bool(roll)).reshape(-1).numpy()
+    Tp, T = src.size, 8 * H * W
+    w2t, t2w, up = raw[:Tp], raw[Tp:Tp + T], raw[Tp + T:]
+    assert np.array_equal(w2t, src)
+    assert np.array_equal(w2t[t2w], np.arange(T))                 # inverse on real tokens
+    # up-sample pixel shuffle + crop; here (H, W) is the HIGH-res grid
+    if W % 24 == 0:
+        H2, W2 = (H + 1) // 2, W // 2
+        T2 = 8 * H2 * W2
+        r = np.arange(T2)
+        w2, h2, z = r % W2, (r // W2) % H2, r // (W2 * H2)
+        for grp in range(4):
+            h, w = 2 * h2 + grp // 2, 2 * w2 + grp % 2
+            want = np.where(h >= H, -1, (z * H + h) * W + w)
+            assert np.array_equal(up[grp * T2:(grp + 1) * T2], want)
