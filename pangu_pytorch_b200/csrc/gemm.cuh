@@ -95,7 +95,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   using T = GemmTraits<Cfg>;
   constexpr int BN = T::BN, UN = T::UN, CH = T::CH;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024 B alignment for SWIZZLE_128B; offset arithmetic (not an int->pointer cast) so that the
+  // compiler keeps the shared address space and emits LDS/STS instead of generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;
   uint8_t* wg_area = smem + T::STAGES * T::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wg_area + 2 * T::WG_BYTES);
@@ -230,6 +232,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       named_bar_sync(bar_id, 128);
 
+      auto load_resid = [&](int cc, uint4 (&dst)[CH / 4]) {
+#pragma unroll
+        for (int it = 0; it < CH / 4; ++it) {
+          const int id = it * 128 + tid;
+          const int rr = id / (CH / 4), pc = id % (CH / 4);
+          const int tok = s_tok[rr];
+          dst[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (tok >= 0) dst[it] = ldg16(ep.resid + size_t(tok) * ep.ld32 + (n_blk * BN + cc + pc * 4));
+        }
+      };
+      [[maybe_unused]] uint4 resq[CH / 4];
+      if constexpr (Cfg::RESID) load_resid(wg * CH, resq);   // first chunk: latency hidden by the mainloop wait
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
@@ -244,11 +258,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld32(tacc + c0, r);
           tmem_ld_wait();
           if (c0 == 0) shift = __uint_as_float(r[0]) + s_bias[0];
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = __uint_as_float(r[j]) + s_bias[c0 + j] - shift;
-            s1 += v;
-            s2 = fmaf(v, v, s2);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = b4[j4];
+            const float v0 = __uint_as_float(r[4 * j4]) + bb.x - shift, v1 = __uint_as_float(r[4 * j4 + 1]) + bb.y - shift;
+            const float v2 = __uint_as_float(r[4 * j4 + 2]) + bb.z - shift, v3 = __uint_as_float(r[4 * j4 + 3]) + bb.w - shift;
+            s1 += (v0 + v1) + (v2 + v3);
+            s2 = fmaf(v0, v0, s2); s2 = fmaf(v1, v1, s2); s2 = fmaf(v2, v2, s2); s2 = fmaf(v3, v3, s2);
           }
         }
         const float inv_n = 1.0f / float(BN);
@@ -260,23 +277,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 #pragma unroll 1
       for (int c0 = wg * CH; c0 < BN; c0 += 2 * CH) {
+        // ---------------- residual prefetch for the NEXT chunk's phase-B items (consumed two barriers later)
+        [[maybe_unused]] uint4 resn[CH / 4];
+        if constexpr (Cfg::RESID) {
+          if (c0 + 2 * CH < BN) load_resid(c0 + 2 * CH, resn);
+        }
         // ---------------- phase A: TMEM -> registers -> math -> staging (row per thread)
         {
           uint32_t r[CH];
           if constexpr (CH == 32) tmem_ld32(tacc + c0, r); else tmem_ld16(tacc + c0, r);
           tmem_ld_wait();
           const int ncol0 = n_blk * BN + c0;
-#pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            float v = __uint_as_float(r[j]) + s_bias[c0 + j];
-            if constexpr (Cfg::LN) v = (v - mean) * rstd * s_gamma[c0 + j] + s_beta[c0 + j];
-            if constexpr (Cfg::SCALEQ) { if (ncol0 + j < ep.q_cols) v *= ep.q_scale; }
-            if constexpr (Cfg::GELU) v = gelu_erf(v);
-            r[j] = __float_as_uint(v);
-          }
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+          const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
+          const float4* e4 = reinterpret_cast<const float4*>(s_beta + c0);
           uint4* dstp = reinterpret_cast<uint4*>(stg + row * T::STG_PITCH);
 #pragma unroll
-          for (int j = 0; j < CH / 4; ++j) dstp[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          for (int j4 = 0; j4 < CH / 4; ++j4) {
+            const float4 bb = b4[j4];
+            float v[4] = {__uint_as_float(r[4 * j4]) + bb.x, __uint_as_float(r[4 * j4 + 1]) + bb.y,
+                          __uint_as_float(r[4 * j4 + 2]) + bb.z, __uint_as_float(r[4 * j4 + 3]) + bb.w};
+            if constexpr (Cfg::LN) {
+              const float4 gg = g4[j4], ee = e4[j4];
+              v[0] = fmaf((v[0] - mean) * rstd, gg.x, ee.x);
+              v[1] = fmaf((v[1] - mean) * rstd, gg.y, ee.y);
+              v[2] = fmaf((v[2] - mean) * rstd, gg.z, ee.z);
+              v[3] = fmaf((v[3] - mean) * rstd, gg.w, ee.w);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if constexpr (Cfg::SCALEQ) { if (ncol0 + 4 * j4 + e < ep.q_cols) v[e] *= ep.q_scale; }
+              if constexpr (Cfg::GELU) v[e] = gelu_erf(v[e]);
+            }
+            dstp[j4] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                                  __float_as_uint(v[3]));
+          }
         }
         named_bar_sync(bar_id, 128);
         // ---------------- phase B: staging -> global, coalesced, row-remapped
@@ -319,7 +354,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y), f2 = __uint_as_float(v.z),
                   f3 = __uint_as_float(v.w);
             if constexpr (Cfg::RESID) {
-              const uint4 q = ldg_nc16(ep.resid + size_t(tok) * ep.ld32 + col);
+              const uint4 q = resq[it];
               f0 = fmaf(ep.res_scale, f0, __uint_as_float(q.x));
               f1 = fmaf(ep.res_scale, f1, __uint_as_float(q.y));
               f2 = fmaf(ep.res_scale, f2, __uint_as_float(q.z));
@@ -353,6 +388,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         named_bar_sync(bar_id, 128);  // staging free again
+        if constexpr (Cfg::RESID) {
+#pragma unroll
+          for (int it = 0; it < CH / 4; ++it) resq[it] = resn[it];
+        }
       }
       // accumulator drained by this thread
       tc_fence_before();

@@ -219,6 +219,7 @@ class EarthSpecificBlock(nn.Module):
         roll_out < 0, in ``x16_out`` (natural order; default ws.x16)."""
         fp16 = ws.fp16
         Z, H, W, C = ws.Z, ws.H, ws.W, ws.C
+        ops.set_tag("hi" if C == 192 else "lo")
         s1, s2 = self.drop_path.scale(), self.drop_path.scale()
         att = self.attention
         att._run(ws, roll)
@@ -229,6 +230,7 @@ class EarthSpecificBlock(nn.Module):
         ops.mlp_ln_residual(ws.x16, mlp._w1.get(mlp.linear1.weight), mlp.linear1.bias,
                             mlp._w2.get(mlp.linear2.weight), mlp.linear2.bias, self.norm2.weight, self.norm2.bias,
                             ws.hidden, ws.x32, target, Z, H, W, C, roll_out, s2, fp16)
+        ops.set_tag("")
 
     def forward(self, x, Z, H, W, roll):
         C = x.shape[-1]

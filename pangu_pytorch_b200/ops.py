@@ -48,8 +48,46 @@ def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class EventProfile:
+    """Optional per-entry-point device timing (CUDA events on the launching stream).  Used by
+    bench.py to time the dominant kernel *inside* the timed region; off by default."""
+
+    def __init__(self):
+        self.records = []          # (name, tag, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, tag, a, b in self.records:
+            key = f"{name}[{tag}]" if tag else name
+            ms, n = out.get(key, (0.0, 0))
+            out[key] = (ms + a.elapsed_time(b), n + 1)
+        return out
+
+
+_PROFILE = [None]
+_TAG = [""]
+
+
+def set_profile(p) -> None:
+    _PROFILE[0] = p
+
+
+def set_tag(tag: str) -> None:
+    """Label subsequent calls (e.g. 'hi'/'lo') in the event profile."""
+    _TAG[0] = tag
+
+
 def _call(name, *args):
-    _lib.call(name, *args)
+    prof = _PROFILE[0]
+    if prof is None:
+        _lib.call(name, *args)
+    else:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.call(name, *args)
+        b.record()
+        prof.records.append((name, _TAG[0], a, b))
     _LAUNCHES[0] += _KERNELS_PER_CALL[name]
 
 
