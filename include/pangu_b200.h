@@ -115,6 +115,13 @@ int pangu_patch_recover(const void* skip16, const void* x16, const void* w_upper
                         float* out_upper, float* out_surface,
                         int Z, int H, int W, int C, int lat, int lon, int fp16, void* stream);
 
+/* normBackData (era5_data/utils_data.py:324-330) in place on the normalised model outputs
+ * upper [5,13,lat,lon] / surface [4,lat,lon], with the INPUT-order statistics the model takes
+ * (surface [4], upper [13,5] whose level axis is reversed w.r.t. the data; the level reversal of
+ * weatherStatistics_output, :225-233, is applied inside).  Glue between autoregressive steps. */
+int pangu_denorm_fields(float* upper, float* surface, const float* surface_mean, const float* surface_std,
+                        const float* upper_mean, const float* upper_std, int lat, int lon, void* stream);
+
 /* Generic nn.Linear forward used by the stand-alone module API (EarthAttention3D.linear2,
  * Mlp.linear1/2 outside the fused block path) and by the unit tests of the tcgen05 GEMM engine:
  * out = a16 [M,K] * w16 [N,K]^T + bias.  gelu == 0: fp32 out32 and 16-bit out16 (both required),

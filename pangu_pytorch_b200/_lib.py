@@ -30,6 +30,7 @@ SIGNATURES = {
     "pangu_upsample": [_P] * 8 + [_I, _I, _I, _I, _I, _I, _P],
     "pangu_patch_recover": [_P] * 8 + [_I, _I, _I, _I, _I, _I, _I, _P],
     "pangu_linear": [_P] * 5 + [_I, _I, _I, _I, _I, _P],
+    "pangu_denorm_fields": [_P] * 6 + [_I, _I, _P],
 }
 
 _lib = None

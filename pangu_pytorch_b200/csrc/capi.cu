@@ -434,6 +434,18 @@ extern "C" int pangu_patch_recover(const void* skip16, const void* x16, const vo
   return 0;
 }
 
+extern "C" int pangu_denorm_fields(float* upper, float* surface, const float* surface_mean, const float* surface_std,
+                                   const float* upper_mean, const float* upper_std, int lat, int lon, void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(lat > 0 && lon > 0 && (size_t(lat) * lon) % 4 == 0, "denorm: lat*lon must be a multiple of 4");
+  const int plane4 = int(size_t(lat) * lon / 4);
+  dim3 grid((plane4 + 255) / 256 < 64 ? (plane4 + 255) / 256 : 64, 69);
+  denorm_fields_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(upper, surface, surface_mean, surface_std,
+                                                                            upper_mean, upper_std, plane4);
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int pangu_linear(const void* a16, const void* w16, const float* bias, float* out32, void* out16, int M,
                             int N, int K, int gelu, int fp16, void* stream) {
   PG_TRY(ensure_init());

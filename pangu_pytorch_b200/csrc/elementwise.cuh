@@ -166,6 +166,33 @@ __global__ void __launch_bounds__(256) to_window16_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------
+// normBackData (era5_data/utils_data.py:324-330) in place on the model's normalised outputs:
+// plane p < 65 is upper-air (c = p / 13, level l = p % 13, statistics row 12 - l of the
+// (13,1,1,5) input-order arrays, i.e. weatherStatistics_output's level reversal), p >= 65 surface.
+__global__ void __launch_bounds__(256) denorm_fields_kernel(float* __restrict__ upper, float* __restrict__ surface,
+                                                            const float* __restrict__ s_mean,
+                                                            const float* __restrict__ s_std,
+                                                            const float* __restrict__ u_mean,
+                                                            const float* __restrict__ u_std, int plane4) {
+  const int p = blockIdx.y;
+  float m, s;
+  float4* base;
+  if (p < 65) {
+    const int c = p / 13, l = p % 13;
+    m = u_mean[(12 - l) * 5 + c]; s = u_std[(12 - l) * 5 + c];
+    base = reinterpret_cast<float4*>(upper) + size_t(p) * plane4;
+  } else {
+    m = s_mean[p - 65]; s = s_std[p - 65];
+    base = reinterpret_cast<float4*>(surface) + size_t(p - 65) * plane4;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane4; i += gridDim.x * blockDim.x) {
+    float4 v = base[i];
+    v.x = fmaf(v.x, s, m); v.y = fmaf(v.y, s, m); v.z = fmaf(v.z, s, m); v.w = fmaf(v.w, s, m);
+    base[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // dst[r][0..kd) = cast(src[r][0..ks)), zero for columns ks..kd (K padding of conv_surface)
 template <bool kFp16>
 __global__ void cast16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int rows, int ks, int kd) {

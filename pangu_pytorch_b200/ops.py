@@ -20,7 +20,7 @@ _LAUNCHES = [0]          # kernels launched through this module (bench.py report
 _KERNELS_PER_CALL = {
     "pangu_cast16": 1, "pangu_to_window16": 1, "pangu_patch_embed": 3, "pangu_qkv": 1,
     "pangu_window_attention": 1, "pangu_proj_ln_residual": 1, "pangu_mlp_ln_residual": 2,
-    "pangu_downsample": 2, "pangu_upsample": 2, "pangu_patch_recover": 2, "pangu_linear": 1,
+    "pangu_downsample": 2, "pangu_upsample": 2, "pangu_patch_recover": 2, "pangu_linear": 1, "pangu_denorm_fields": 1,
 }
 
 
@@ -180,3 +180,11 @@ def linear(a16, w16, bias, out32, out16, gelu: bool, fp16: bool) -> None:
     N = w16.shape[0]
     _call("pangu_linear", _p(a16, h), _p(w16, h), _p(bias, torch.float32), _p(out32, torch.float32),
           _p(out16, h), M, N, K, int(bool(gelu)), int(fp16), _stream())
+
+
+def denorm_fields(upper, surface, s_mean, s_std, u_mean, u_std) -> None:
+    """In-place ``normBackData`` on the model outputs (input-order statistics)."""
+    f = torch.float32
+    lat, lon = surface.shape[-2], surface.shape[-1]
+    _call("pangu_denorm_fields", _p(upper, f, "upper"), _p(surface, f, "surface"), _p(s_mean, f), _p(s_std, f),
+          _p(u_mean, f), _p(u_std, f), lat, lon, _stream())

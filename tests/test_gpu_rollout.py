@@ -1,0 +1,77 @@
+"""BASELINE.json config 2/3 on the GPU: de-normalisation glue, chained forecast steps (checked per
+step against the oracle, teacher-forced and free-running) and ensemble sharding on one device."""
+import pytest
+import torch
+
+from oracle import pangu_oracle as O
+from tests.util import TOL_MODEL
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _model(p, fmt):
+    import pangu_pytorch_b200 as pb
+    pb.set_operand_dtype(fmt)
+    pb.free_workspaces()
+    m = pb.PanguModel(device=DEV)
+    m.load_state_dict(p, strict=True)
+    return m.to(DEV).eval()
+
+
+def _err(got, ref):
+    got, ref = got.detach().double().cpu(), ref.double()
+    return float(((got - ref).flatten(2).norm(dim=2) / ref.flatten(2).norm(dim=2)).max())
+
+
+def test_denorm_fields_matches_normBackData():
+    from pangu_pytorch_b200.rollout import denormalize_
+    g = torch.Generator().manual_seed(3)
+    up, sf = torch.randn(1, 5, 13, 721, 96, generator=g), torch.randn(1, 4, 721, 96, generator=g)
+    stats = (torch.randn(4, generator=g), 0.5 + torch.rand(4, generator=g),
+             torch.randn(13, 1, 1, 5, generator=g), 0.5 + torch.rand(13, 1, 1, 5, generator=g))
+    ru, rs = O.norm_back_data(up, sf, O.output_statistics(stats))
+    gu, gs = denormalize_(up.to(DEV).clone(), sf.to(DEV).clone(), stats)
+    assert torch.allclose(gu.cpu(), ru, rtol=1e-6, atol=1e-6) and torch.allclose(gs.cpu(), rs, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("fmt", ["bf16", "fp16"])
+def test_three_step_rollout_on_strip(fmt):
+    """x_{k+1} = normBack(model(x_k)) on a 96-column strip, 3 chained steps."""
+    from pangu_pytorch_b200.rollout import rollout
+    p = O.reference_like_weights(seed=0)
+    m = _model(p, fmt)
+    up, sf, stats, maps, ch = O.synthetic_inputs(seed=1, lat=721, lon=96)
+    ref = O.rollout(p, up, sf, stats, maps, ch, steps=3)
+    d = lambda t: t.to(DEV)
+    dstats = [d(s) for s in stats]
+    free = rollout(m, d(up), d(sf), dstats, d(maps), d(ch), steps=3)
+    # free running: error may grow, bounded by ~2x the single-step tolerance
+    for k, ((gu, gs), (ru, rs)) in enumerate(zip(free, ref)):
+        eu, es = _err(gu, ru), _err(gs, rs)
+        print(f"rollout {fmt} free-running step {k + 1}: upper {eu:.3e} surface {es:.3e}")
+        assert eu < 2 * TOL_MODEL[fmt] and es < 2 * TOL_MODEL[fmt]
+    # teacher forced: both fed the oracle's x_k
+    for k in range(1, 3):
+        iu, is_ = ref[k - 1]
+        gu, gs = rollout(m, d(iu), d(is_), dstats, d(maps), d(ch), steps=1)[0]
+        eu, es = _err(gu, ref[k][0]), _err(gs, ref[k][1])
+        print(f"rollout {fmt} teacher-forced step {k + 1}: upper {eu:.3e} surface {es:.3e}")
+        assert eu < TOL_MODEL[fmt] and es < TOL_MODEL[fmt]
+
+
+def test_ensemble_members_are_independent_and_sharded():
+    from pangu_pytorch_b200 import ensemble
+    p = O.reference_like_weights(seed=0)
+    m = _model(p, "bf16")
+    up, sf, stats, maps, ch = O.synthetic_inputs(seed=1, lat=721, lon=96)
+    d = lambda t: t.to(DEV)
+    args = (m, d(up), d(sf), [d(s) for s in stats], d(maps), d(ch))
+    summ = lambda ou, os_: (float(ou.double().mean()), float(os_.double().mean()))
+    whole = ensemble.run_ensemble(*args, n_members=4, rank=0, world=1, reduce=summ)
+    parts = {}
+    for r in range(2):
+        parts.update(ensemble.run_ensemble(*args, n_members=4, rank=r, world=2, reduce=summ))
+    assert sorted(whole) == sorted(parts) == [0, 1, 2, 3]
+    assert all(whole[k] == parts[k] for k in whole)           # bit-identical regardless of sharding
+    assert len({whole[k] for k in whole}) == 4                # perturbations differ
