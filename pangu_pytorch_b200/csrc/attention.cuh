@@ -23,7 +23,8 @@ constexpr int ATT_WARPS = 9;                 // 9 x 16 query rows
 constexpr int ATT_THREADS = ATT_WARPS * 32;  // 288
 constexpr int ATT_TILE_BYTES = ATT_TOK * ATT_D * 2;   // 9216
 constexpr int ATT_BUF_BYTES = 3 * ATT_TILE_BYTES;     // q, k, v
-constexpr int ATT_SMEM_BYTES = 2 * ATT_BUF_BYTES;     // double buffered
+constexpr int ATT_STAGES = 3;                          // cp.async ring depth (one barrier per window)
+constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_BUF_BYTES;
 
 struct AttnArgs {
   const void* qkv;     // [nLon*types*144][3C] 16-bit, window order, q pre-scaled
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) window_attention_kernel(const 
   };
 
   prefetch(lw0, 0);
+  if (lw0 + 1 < lw1) prefetch(lw0 + 1, 1);
 
   // ---- bias (+mask) tile into registers, accumulator-fragment layout:
   //      bz[j][0..1] = row r0, cols 8j + 2*q4 + {0,1};  bz[j][2..3] = row r0 + 8
@@ -130,9 +132,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) window_attention_kernel(const 
 
   constexpr float kLog2e = 1.4426950408889634f;
   int buf = 0;
-  for (int lw = lw0; lw < lw1; ++lw, buf ^= 1) {
-    if (lw + 1 < lw1) { prefetch(lw + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
+  for (int lw = lw0; lw < lw1; ++lw, buf = (buf + 1 == ATT_STAGES ? 0 : buf + 1)) {
+    // window lw has landed once at most one younger group is still in flight
+    if (lw + 1 < lw1) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();   // (a) everyone's copies of window lw are visible, (b) everyone finished window lw-1
+    if (lw + 2 < lw1) prefetch(lw + 2, (buf + 2) % ATT_STAGES);   // refills the buffer read in iteration lw-1
     const uint32_t sq = sbase + buf * ATT_BUF_BYTES, sk = sq + ATT_TILE_BYTES, sv = sk + ATT_TILE_BYTES;
 
     // ---- S = Q K^T  (16 rows x 144 keys per warp)
@@ -232,7 +236,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) window_attention_kernel(const 
         stg16(outp + (row0 + r) * (size_t(a.C) * 2) + head * 64 + c * 16, v);
       }
     }
-    __syncthreads();   // everyone done with buf before it is refilled two iterations later
   }
 }
 

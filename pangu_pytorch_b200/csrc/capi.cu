@@ -70,6 +70,22 @@ extern "C" int pangu_check_device(void) { return ensure_init(); }
 
 // 2-D K-major operand map: dim0 = K (contiguous), dim1 = rows; box = 64 x box_rows, 128 B swizzle,
 // out-of-bounds rows read as zero (this is what pads ragged M tails).
+// 2-D map of a row-major 16-bit output [rows, cols]: box = 32 columns x 128 rows, 64 B swizzle
+static int make_out_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems) {
+  PG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (pitch_elems * 2) % 16 == 0 && cols % 32 == 0,
+             "output not TMA-storable (base %p, pitch %llu, cols %llu)", base, (unsigned long long)pitch_elems,
+             (unsigned long long)cols);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled(out) failed (%d)", int(r));
+  return 0;
+}
+
 static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t k, uint64_t pitch_elems,
                     uint32_t box_rows) {
   PG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "operand base %p not 16 B aligned", base);
@@ -94,14 +110,15 @@ struct CfgBase {
                         GROUPCOL = false;
   static constexpr int RECOVER = RC_NONE;
   static constexpr int CH = 32;
+  static constexpr bool TMA16 = false;   // 16-bit row-major output written with TMA bulk stores
 };
 struct CfgQKV : CfgBase {      // linear1 of attention: bias, q-scale, 16-bit out
   static constexpr int BN = 192, UN = 192, STAGES = 4;
-  static constexpr bool SCALEQ = true, OUT16 = true;
+  static constexpr bool SCALEQ = true, OUT16 = true, TMA16 = true;
 };
 struct CfgMLP1 : CfgBase {     // Mlp.linear1: bias + exact GELU, 16-bit out
   static constexpr int BN = 256, UN = 256, STAGES = 3;
-  static constexpr bool GELU = true, OUT16 = true;
+  static constexpr bool GELU = true, OUT16 = true, TMA16 = true;
 };
 struct CfgLNRes192 : CfgBase { // bias + LayerNorm(192) + residual, fp32 + 16-bit out
   static constexpr int BN = 192, UN = 192, STAGES = 4;
@@ -146,6 +163,12 @@ static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t 
   PG_TRY(make_map(&ma, o.a, o.M, o.k1, o.a_pitch, BLOCK_M));
   if (o.k2 > 0) PG_TRY(make_map(&ma2, o.a2, o.M, o.k2, o.a2_pitch, BLOCK_M)); else ma2 = ma;
   PG_TRY(make_map(&mb, o.b, o.N, o.k1 + o.k2, o.b_pitch, Cfg::UN));
+  CUtensorMap mo = ma;
+  if constexpr (Cfg::TMA16) {
+    PG_REQUIRE(ep.rowmap == RM_IDENT && ep.dstmap == DM_IDENT && ep.row_base == 0 && ep.out16 != nullptr,
+               "TMA-store epilogue needs an identity row map");
+    PG_TRY(make_out_map(&mo, ep.out16, o.M, o.N, ep.ld16));
+  }
   GemmShape sh;
   sh.M = o.M;
   sh.num_m_blocks = (o.M + BLOCK_M - 1) / BLOCK_M;
@@ -160,7 +183,7 @@ static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t 
   }
   const int tiles = sh.num_m_blocks * sh.num_n_blocks;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, kNumThreads, T::SMEM_BYTES, stream>>>(ma, ma2, mb, sh, ep);
+  kern<<<grid, kNumThreads, T::SMEM_BYTES, stream>>>(ma, ma2, mb, mo, sh, ep);
   PG_CUDA(cudaGetLastError());
   return 0;
 }

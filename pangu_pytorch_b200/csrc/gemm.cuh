@@ -73,14 +73,16 @@ struct GemmTraits {
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_PITCH = CH * 4 + 16;      // bytes; == 16 (mod 128) -> conflict-free 16 B rows
-  static constexpr int STG_BYTES = BLOCK_M * STG_PITCH;
+  // TMA16 configs stage two [128 rows][32 cols] 16-bit tiles (SWIZZLE_64B, 8 KB each) per warpgroup
+  static constexpr int STG_BYTES = Cfg::TMA16 ? 2 * 8192 : ((BLOCK_M * STG_PITCH + 1023) / 1024) * 1024;
   static constexpr int PAR_BYTES = 3 * BN * 4;       // bias / gamma / beta per warpgroup
   static constexpr int TAB_BYTES = 2 * BLOCK_M * 4;  // row -> token, row -> 16-bit destination row
-  static constexpr int WG_BYTES = STG_BYTES + PAR_BYTES + TAB_BYTES;
+  static constexpr int WG_BYTES = ((STG_BYTES + PAR_BYTES + TAB_BYTES + 1023) / 1024) * 1024;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * WG_BYTES + BAR_BYTES;
   static_assert(BN % UN == 0 && UN % 16 == 0 && UN <= 256, "bad N tiling");
   static_assert(BN % CH == 0 && (CH == 16 || CH == 32), "bad epilogue chunk");
+  static_assert(!Cfg::TMA16 || (CH == 32 && !Cfg::LN && !Cfg::OUT32 && Cfg::RECOVER == 0), "TMA16: plain 16-bit output");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024 B alignment");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
@@ -91,7 +93,8 @@ constexpr int kEpiThreads = 256;
 template <class Cfg, bool kFp16>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-            const __grid_constant__ CUtensorMap tmB, const GemmShape shape, const EpiArgs ep) {
+            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+            const GemmShape shape, const EpiArgs ep) {
   using T = GemmTraits<Cfg>;
   constexpr int BN = T::BN, UN = T::UN, CH = T::CH;
   extern __shared__ uint8_t smem_raw[];
@@ -115,6 +118,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
+    if constexpr (Cfg::TMA16) tma_prefetch_desc(&tmOut);
     for (int s = 0; s < T::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -206,6 +210,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     int loaded_n_blk = -1;
+    [[maybe_unused]] int sbuf = 0;   // TMA16: staging buffer parity, alternates across chunks AND tiles
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / shape.num_n_blocks, n_blk = tile % shape.num_n_blocks;
       // ---- per-tile tables (overlaps the mainloop of this tile)
@@ -242,6 +247,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (tok >= 0) dst[it] = ldg16(ep.resid + size_t(tok) * ep.ld32 + (n_blk * BN + cc + pc * 4));
         }
       };
+      if constexpr (Cfg::TMA16) {
+        // ------- 16-bit row-major output, identity row map: registers -> swizzled smem tile -> TMA store.
+        // One named barrier per chunk; the issuing thread drains its previous bulk store before the
+        // barrier, so the other staging buffer is known to be free when the next chunk starts.
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t tacc16 = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int c0 = wg * 32; c0 < BN; c0 += 64) {
+          uint32_t r[32];
+          tmem_ld32(tacc16 + c0, r);
+          tmem_ld_wait();
+          const int ncol0 = n_blk * BN + c0;
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+          uint8_t* tile = stg + sbuf * 8192;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {          // 4 x 16 B (8 columns each) per 64 B row
+            float v[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 bb = b4[2 * q + h];
+              v[4 * h + 0] = __uint_as_float(r[8 * q + 4 * h + 0]) + bb.x;
+              v[4 * h + 1] = __uint_as_float(r[8 * q + 4 * h + 1]) + bb.y;
+              v[4 * h + 2] = __uint_as_float(r[8 * q + 4 * h + 2]) + bb.z;
+              v[4 * h + 3] = __uint_as_float(r[8 * q + 4 * h + 3]) + bb.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if constexpr (Cfg::SCALEQ) { if (ncol0 + 8 * q + e < ep.q_cols) v[e] *= ep.q_scale; }
+              if constexpr (Cfg::GELU) v[e] = gelu_erf(v[e]);
+            }
+            uint4 h16;
+            h16.x = pack16<kFp16>(v[0], v[1]); h16.y = pack16<kFp16>(v[2], v[3]);
+            h16.z = pack16<kFp16>(v[4], v[5]); h16.w = pack16<kFp16>(v[6], v[7]);
+            // SWIZZLE_64B: 16 B chunk index XOR bits [7,9) of the byte address (= (row >> 1) & 3)
+            *reinterpret_cast<uint4*>(tile + row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) = h16;
+          }
+          fence_proxy_async_smem();
+          if (tid == 0) bulk_wait_read<0>();     // store issued from the other buffer has been read out
+          named_bar_sync(bar_id, 128);
+          if (tid == 0) {
+            tma_store_2d(&tmOut, tile, ncol0, m_blk * BLOCK_M);
+            bulk_commit();
+          }
+          sbuf ^= 1;
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+        if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+
       [[maybe_unused]] uint4 resq[CH / 4];
       if constexpr (Cfg::RESID) load_resid(wg * CH, resq);   // first chunk: latency hidden by the mainloop wait
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -400,6 +457,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
 
+  if constexpr (Cfg::TMA16) {
+    if (warp >= 2 && (((warp - 2) & 3) * 32 + lane) == 0) bulk_wait_all();   // smem must outlive the bulk stores
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
