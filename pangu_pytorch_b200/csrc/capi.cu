@@ -4,10 +4,12 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 
@@ -314,6 +316,39 @@ extern "C" int pangu_window_attention(const void* qkv16, const float* earth_bias
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   dim3 grid(base, best_split);
+  static const bool use_mma_sync = getenv("PANGU_B200_ATTN_MMA_SYNC") != nullptr;   // development A/B switch
+  if (!use_mma_sync) {
+    // tcgen05 path: qkv [Tp, 3C] viewed as a 2-D tensor, one 32-column x 144-row box per q/k/v tile
+    const int Tp = g.nLon * g.types * 144;
+    CUtensorMap mq;
+    {
+      PG_REQUIRE((reinterpret_cast<uintptr_t>(qkv16) & 15) == 0, "qkv base not 16 B aligned");
+      cuuint64_t dims[2] = {cuuint64_t(3 * C), cuuint64_t(Tp)};
+      cuuint64_t strides[1] = {cuuint64_t(3 * C) * 2};
+      cuuint32_t box[2] = {32, 144};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = g_encode(&mq, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(qkv16), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled(qkv) failed (%d)", int(r));
+    }
+    static bool tc_attr[2] = {false, false};
+    if (fp16) {
+      if (!tc_attr[1]) {
+        PG_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
+        tc_attr[1] = true;
+      }
+      window_attention_tc_kernel<true><<<grid, ATC_THREADS, ATC_SMEM_BYTES, s>>>(mq, a);
+    } else {
+      if (!tc_attr[0]) {
+        PG_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
+        tc_attr[0] = true;
+      }
+      window_attention_tc_kernel<false><<<grid, ATC_THREADS, ATC_SMEM_BYTES, s>>>(mq, a);
+    }
+    PG_CUDA(cudaGetLastError());
+    return 0;
+  }
   static bool attr_done[2] = {false, false};
   if (fp16) {
     if (!attr_done[1]) {

@@ -122,6 +122,25 @@ def test_attention_module(fmt, tag):
         assert err < TOL_BLOCK[fmt]
 
 
+@pytest.mark.parametrize("tag,nlon", [("hi", 8), ("lo", 15)])
+def test_attention_long_window_walk(tag, nlon):
+    """One CTA walks more longitude windows than the smem ring / tail-warp rotation is deep
+    (regression: mbarrier phase aliasing when a waiter skips phases)."""
+    _fmt("fp16")
+    dim, heads, H = (192, 6, 181) if tag == "hi" else (384, 12, 91)
+    pre = f"layers.EarthSpecificLayer{0 if tag == 'hi' else 1}.blocks.EarthSpecificBlock1."
+    p = O.stress_weights(seed=7)
+    blk = _load_block(dim, heads, pre, p)
+    types = 124 if tag == "hi" else 64
+    x = torch.randn(nlon, types, 144, dim, generator=torch.Generator().manual_seed(9))
+    mask = O.shift_mask(8, H)
+    ref = O.window_attention(x, p, pre + "attention.", heads, mask)
+    got = blk.attention(x.to(DEV), mask.to(DEV))
+    per_window = ((got.cpu().double() - ref.double()).flatten(2).norm(dim=2) / ref.double().flatten(2).norm(dim=2))
+    print(f"attention {tag} nlon={nlon}: worst window rel-L2 {float(per_window.max()):.3e}")
+    assert float(per_window.max()) < TOL_BLOCK["fp16"]
+
+
 @pytest.mark.parametrize("fmt", FORMATS)
 @pytest.mark.parametrize("tag", ["hi", "lo"])
 def test_block_against_oracle_and_golden(fmt, tag):
