@@ -269,22 +269,26 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = tmem + (uint32_t(quad * 32) << 16);
     const int c0 = 72 * h;
-    // ---- bias (+mask) row slice -> TMEM, once
+    // ---- bias (+mask) row slice -> TMEM, once: 18 independent 16-byte loads in flight per thread
     {
-      const float* brow = bt + size_t(r) * ATT_TOK + c0;
-#pragma unroll 1
-      for (int cc = 0; cc < 72; cc += 8) {
+      const float4* brow = reinterpret_cast<const float4*>(bt + size_t(r) * ATT_TOK + c0);
+      float4 bv[18];
+#pragma unroll
+      for (int q = 0; q < 18; ++q) bv[q] = __ldg(brow + q);
+#pragma unroll
+      for (int q = 0; q < 18; q += 2) {
         uint32_t v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float b = brow[cc + e];
-          const int cj = c0 + cc + e;
+          const float4 f = bv[q + (e >> 2)];
+          float b = (e & 3) == 0 ? f.x : (e & 3) == 1 ? f.y : (e & 3) == 2 ? f.z : f.w;
+          const int cj = c0 + 4 * q + e;
           const bool mz = zsplit && ((r / 72) != (cj / 72));
           const bool mh = hsplit && ((((r / 12) % 6) < 3) != (((cj / 12) % 6) < 3));
           if (mz || mh) b += -100.0f;
           v[e] = __float_as_uint(b);
         }
-        tmem_st8(lane_addr + ATC_COL_BIAS + c0 + cc, v);
+        tmem_st8(lane_addr + ATC_COL_BIAS + c0 + 4 * q, v);
       }
       tmem_st_wait();
     }
@@ -316,7 +320,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
       const int b = i & 1;
       mbar_wait(&sfull_bar[b], (i >> 1) & 1);
       tc_fence_after();
-      float x[72];
+      f32x2 x[36];               // 72 logits of this thread's row slice, two per 64-bit register pair
       // S and bias slices in 16-column pieces (72 = 4 x 16 + 8) to bound the live registers
 #pragma unroll
       for (int part = 0; part < 4; ++part) {
@@ -325,7 +329,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
         tmem_ld16(lane_addr + ATC_COL_BIAS + c0 + 16 * part, ba);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) x[16 * part + e] = __uint_as_float(sa[e]) + __uint_as_float(ba[e]);
+        for (int e = 0; e < 8; ++e)
+          x[8 * part + e] = add2(pack2(__uint_as_float(sa[2 * e]), __uint_as_float(sa[2 * e + 1])),
+                                 pack2(__uint_as_float(ba[2 * e]), __uint_as_float(ba[2 * e + 1])));
       }
       {
         uint32_t s8[8], b8[8];
@@ -333,24 +339,39 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
         tmem_ld8(lane_addr + ATC_COL_BIAS + c0 + 64, b8);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 8; ++e) x[64 + e] = __uint_as_float(s8[e]) + __uint_as_float(b8[e]);
+        for (int e = 0; e < 4; ++e)
+          x[32 + e] = add2(pack2(__uint_as_float(s8[2 * e]), __uint_as_float(s8[2 * e + 1])),
+                           pack2(__uint_as_float(b8[2 * e]), __uint_as_float(b8[2 * e + 1])));
       }
-      float pm = x[0];
+      float pm;
+      {
+        float a0, a1;
+        unpack2(x[0], a0, a1);
+        pm = fmaxf(a0, a1);
 #pragma unroll
-      for (int e = 1; e < 72; ++e) pm = fmaxf(pm, x[e]);
+        for (int e = 1; e < 36; ++e) { unpack2(x[e], a0, a1); pm = max3(pm, a0, a1); }
+      }
       s_max[(b * 2 + h) * 128 + r] = pm;
       tc_fence_before();
       named_bar_sync(1, 256);      // all S slices are in registers (P may now overwrite S) + max exchange
       tc_fence_after();
       const float m = fmaxf(pm, s_max[(b * 2 + (h ^ 1)) * 128 + r]) * kLog2e;
-      float l = 0.f;
+      const f32x2 l2e2 = pack2(kLog2e, kLog2e), negm2 = pack2(-m, -m);
+      f32x2 lsum = pack2(0.f, 0.f);
       uint32_t pk[36];
 #pragma unroll
       for (int e = 0; e < 36; ++e) {
-        const float p0 = fast_exp2(fmaf(x[2 * e], kLog2e, -m));
-        const float p1 = fast_exp2(fmaf(x[2 * e + 1], kLog2e, -m));
-        l += p0 + p1;
+        float a0, a1;
+        unpack2(fma2(x[e], l2e2, negm2), a0, a1);
+        const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+        lsum = add2(lsum, pack2(p0, p1));
         pk[e] = pack16<kFp16>(p0, p1);
+      }
+      float l;
+      {
+        float a0, a1;
+        unpack2(lsum, a0, a1);
+        l = a0 + a1;
       }
       const uint32_t pcol = lane_addr + ATC_COL_S + 144 * b + 36 * h;
 #pragma unroll

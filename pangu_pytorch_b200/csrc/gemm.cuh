@@ -274,9 +274,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               v[4 * h + 3] = __uint_as_float(r[8 * q + 4 * h + 3]) + bb.w;
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              if constexpr (Cfg::SCALEQ) { if (ncol0 + 8 * q + e < ep.q_cols) v[e] *= ep.q_scale; }
-              if constexpr (Cfg::GELU) v[e] = gelu_erf(v[e]);
+            for (int e = 0; e < 8; e += 2) {
+              if constexpr (Cfg::SCALEQ) {
+                if (ncol0 + 8 * q + e < ep.q_cols) { v[e] *= ep.q_scale; v[e + 1] *= ep.q_scale; }   // q_cols is even
+              }
+              if constexpr (Cfg::GELU) gelu_erf2(v[e], v[e + 1]);
             }
             uint4 h16;
             h16.x = pack16<kFp16>(v[0], v[1]); h16.y = pack16<kFp16>(v[2], v[3]);
