@@ -33,6 +33,8 @@ struct AttnArgs {
   int C, heads, types, nLon, nH;
   int roll;            // add the shifted-window mask
   int lon_per_cta;     // longitude windows walked by one CTA
+  int debug;           // development only: bit0 skip tail math, bit1 skip softmax math, bit2 skip stores
+  long long* trace;    // development only: per-role clock64 timeline of CTA (0,0), [role 8][window 32][event 4]
 };
 
 // swizzled byte offset of 16-byte chunk c (0..3) of row r in a [144][32] 16-bit tile

@@ -14,7 +14,7 @@
 // TMEM columns (512): [0,144) bias+mask | [144,288) S0/P0 | [288,432) S1/P1 | [432,464) O0 | [464,496) O1.
 // Warps (512 threads): 0 TMA producer, 1 MMA issuer, 2-7 tail warps (window i -> warp 2 + i%6; a lone
 // mma.sync warp needs ~4-5k cycles per window, six of them keep up with the ~1.3k-cycle window period),
-// 8-15 softmax: thread = (row r = 32*(warp%4)+lane, half h = (warp-8)/4) owns 72 columns of its row.
+// 8-15 softmax: two warpgroups alternate windows; thread = one full query row (TMEM lane 32*(warp%4)+lane).
 #pragma once
 #include "attention.cuh"
 
@@ -80,9 +80,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);      // [ATC_STAGES]
   uint64_t* empty_bar = full_bar + ATC_STAGES;                 // [ATC_STAGES]  count 2: PV commit + tail warp
   uint64_t* sfull_bar = empty_bar + ATC_STAGES;                         // [2]  S ready in TMEM
-  uint64_t* pfull_bar = sfull_bar + 2;                         // [2]  P written (256 softmax threads)
+  uint64_t* pfull_bar = sfull_bar + 2;                         // [2]  P written (128 threads of the owning warpgroup)
   uint64_t* ofull_bar = pfull_bar + 2;                         // [2]  O ready
-  uint64_t* oempty_bar = ofull_bar + 2;                        // [2]  O read out (256 softmax threads)
+  uint64_t* oempty_bar = ofull_bar + 2;                        // [2]  O read out (128 threads of the owning warpgroup)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oempty_bar + 2);
   float* s_max = reinterpret_cast<float*>(misc + 256);         // [2 buf][2 half][128]
   float* s_sum = s_max + 512;                                  // [2 buf][2 half][128]
@@ -100,8 +100,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
     tma_prefetch_desc(&tmQKV);
     for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&sfull_bar[b], 1); mbar_init(&pfull_bar[b], 256);
-      mbar_init(&ofull_bar[b], 1); mbar_init(&oempty_bar[b], 256);
+      mbar_init(&sfull_bar[b], 1); mbar_init(&pfull_bar[b], 128);
+      mbar_init(&ofull_bar[b], 1); mbar_init(&oempty_bar[b], 128);
     }
     fence_barrier_init();
   }
@@ -115,6 +115,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
   const bool zsplit = a.roll && (zw == a.types / a.nH - 1);
   const bool hsplit = a.roll && (hw == a.nH - 1);
   const float* bt = a.bias + (size_t(t) * a.heads + head) * (ATT_TOK * ATT_TOK);
+  const bool tracing = a.trace != nullptr && blockIdx.x == 5 && blockIdx.y == 0;
+  auto TR = [&](int role, int i, int ev) { if (tracing && i < 32) a.trace[(role * 32 + i) * 4 + ev] = clock64(); };
   constexpr float kLog2e = 1.4426950408889634f;
 
   if (warp == 0) {
@@ -123,6 +125,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
       for (int i = 0; i < nwin; ++i) {
         const int st = i % ATC_STAGES;
         mbar_wait(&empty_bar[st], ((i / ATC_STAGES) & 1) ^ 1);
+        TR(0, i, 0);
         uint8_t* dst = ring + st * ATC_STAGE_BYTES;
         const int row0 = ((lw0 + i) * a.types + t) * ATT_TOK;
         mbar_arrive_expect_tx(&full_bar[st], ATC_STAGE_BYTES);
@@ -139,6 +142,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
       auto issue_s = [&](int i) {
         const int st = i % ATC_STAGES, b = i & 1;
         mbar_wait(&full_bar[st], (i / ATC_STAGES) & 1);
+        TR(1, i, 0);
         tc_fence_after();
         const uint32_t sq = smem_u32(ring + st * ATC_STAGE_BYTES);
         const uint64_t dq = make_sdesc_sw64(sq), dk = make_sdesc_sw64(sq + ATT_TILE_BYTES);
@@ -151,8 +155,11 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
       for (int i = 0; i < nwin; ++i) {
         const int st = i % ATC_STAGES, b = i & 1;
         if (i + 1 < nwin) issue_s(i + 1);
+        TR(1, i, 1);
         mbar_wait(&pfull_bar[b], (i >> 1) & 1);
+        TR(1, i, 2);
         mbar_wait(&oempty_bar[b], ((i >> 1) & 1) ^ 1);
+        TR(1, i, 3);
         tc_fence_after();
         const uint32_t sv = smem_u32(ring + st * ATC_STAGE_BYTES + 2 * ATT_TILE_BYTES);
         const uint64_t dv = make_sdesc_sw64(sv);
@@ -160,8 +167,10 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
         for (int kk = 0; kk < 9; ++kk)   // 144 keys = 9 x K16: P advances 8 TMEM columns, V 16 rows = 1024 B
           umma_f16_ts(tmem + ATC_COL_O + 32 * b, tmem + ATC_COL_S + 144 * b + 8 * kk, dv + uint64_t(kk * 64), idesc_o,
                       kk);
+        TR(5, i, 0);
         umma_commit(&ofull_bar[b]);
         umma_commit(&empty_bar[st]);
+        TR(5, i, 1);
       }
     }
   } else if (warp < 2 + ATC_TAIL_WARPS) {
@@ -169,19 +178,35 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
     const int g = lane >> 2, q4 = lane & 3;
     const int r0 = 128 + g;
     // bias(+mask) rows 128..143 -> smem once (each tail warp fills a slice; visibility via the named barrier)
-    for (int idx = (warp - 2) * 32 + lane; idx < 16 * 144; idx += ATC_TAIL_WARPS * 32) {
-      const int rr = idx / 144, cj = idx % 144, ri = 128 + rr;
-      float b = bt[size_t(ri) * ATT_TOK + cj];
-      const bool mz = zsplit && ((ri / 72) != (cj / 72));
-      const bool mh = hsplit && ((((ri / 12) % 6) < 3) != (((cj / 12) % 6) < 3));
-      if (mz || mh) b += -100.0f;
-      s_tbias[rr * ATC_TB_PITCH + cj] = b;
+    {
+      // 16 x 144 floats = 576 float4; 192 threads x 3 independent 16-byte loads each (rows 128..143 are contiguous)
+      const float4* src = reinterpret_cast<const float4*>(bt + size_t(128) * ATT_TOK);
+      const int tl = (warp - 2) * 32 + lane;
+      float4 v[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v[k] = __ldg(src + tl + k * (ATC_TAIL_WARPS * 32));
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int f4 = tl + k * (ATC_TAIL_WARPS * 32);
+        const int rr = f4 / 36, cj0 = (f4 % 36) * 4, ri = 128 + rr;
+        float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cj = cj0 + q;
+          const bool mz = zsplit && ((ri / 72) != (cj / 72));
+          const bool mh = hsplit && ((((ri / 12) % 6) < 3) != (((cj / 12) % 6) < 3));
+          if (mz || mh) e[q] += -100.0f;
+        }
+        *reinterpret_cast<float4*>(s_tbias + rr * ATC_TB_PITCH + cj0) = make_float4(e[0], e[1], e[2], e[3]);
+      }
     }
     named_bar_sync(2, ATC_TAIL_WARPS * 32);
     for (int i = warp - 2; i < nwin; i += ATC_TAIL_WARPS) {
       const int st = i % ATC_STAGES;
       mbar_wait(&full_bar[st], (i / ATC_STAGES) & 1);
       uint8_t* tile = ring + st * ATC_STAGE_BYTES;
+      if (lane == 0) TR(2, i, 0);
+      if (a.debug & 1) { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[st]); continue; }
       const uint32_t sq = smem_u32(tile), sk = sq + ATT_TILE_BYTES, sv = sk + ATT_TILE_BYTES;
       uint32_t qa[2][4];
       {
@@ -259,18 +284,21 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[st]);
+      if (lane == 0) { TR(2, i, 1); mbar_arrive(&empty_bar[st]); }
     }
     // windows handled by the other tail warp still need this warp's half of the "tail" arrival? No:
     // exactly one tail warp arrives per window (count 2 = PV commit + that warp).
   } else {
-    // ============================== softmax + O epilogue (8 warps) ==============================
-    const int quad = warp & 3, h = (warp - 8) >> 2;
+    // ============================== softmax + O epilogue (2 warpgroups) ==============================
+    // Warpgroup wg owns the windows i = wg (mod 2) and the S/P/O buffers b = wg; a thread owns one
+    // full query row (TMEM lane).  Two passes over TMEM (max, then exp) keep the register footprint
+    // small; the other warpgroup's window hides this one's TMEM / MUFU latency.
+    const int quad = warp & 3, wg = (warp - 8) >> 2;
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = tmem + (uint32_t(quad * 32) << 16);
-    const int c0 = 72 * h;
-    // ---- bias (+mask) row slice -> TMEM, once: 18 independent 16-byte loads in flight per thread
+    // ---- bias (+mask) -> TMEM, once: this warpgroup fills columns [72*wg, 72*wg + 72) of every row
     {
+      const int c0 = 72 * wg;
       const float4* brow = reinterpret_cast<const float4*>(bt + size_t(r) * ATT_TOK + c0);
       float4 bv[18];
 #pragma unroll
@@ -281,110 +309,129 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float4 f = bv[q + (e >> 2)];
-          float b = (e & 3) == 0 ? f.x : (e & 3) == 1 ? f.y : (e & 3) == 2 ? f.z : f.w;
+          float bb = (e & 3) == 0 ? f.x : (e & 3) == 1 ? f.y : (e & 3) == 2 ? f.z : f.w;
           const int cj = c0 + 4 * q + e;
           const bool mz = zsplit && ((r / 72) != (cj / 72));
           const bool mh = hsplit && ((((r / 12) % 6) < 3) != (((cj / 12) % 6) < 3));
-          if (mz || mh) b += -100.0f;
-          v[e] = __float_as_uint(b);
+          if (mz || mh) bb += -100.0f;
+          v[e] = __float_as_uint(bb);
         }
         tmem_st8(lane_addr + ATC_COL_BIAS + c0 + 4 * q, v);
       }
       tmem_st_wait();
+      tc_fence_before();
+      named_bar_sync(1, 256);      // the other warpgroup's half of every bias row is in TMEM too
+      tc_fence_after();
     }
-    auto epilogue = [&](int j) {
-      const int b = j & 1;
+    const int b = wg;
+    const uint32_t s_addr = lane_addr + ATC_COL_S + 144 * b;
+    const uint32_t bias_addr = lane_addr + ATC_COL_BIAS;
+    float l_prev = 1.f;
+    auto epilogue = [&](int j, float l) {
       mbar_wait(&ofull_bar[b], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t o[16];
-      tmem_ld16(lane_addr + ATC_COL_O + 32 * b + 16 * h, o);
+      uint32_t o[32];
+      tmem_ld32(lane_addr + ATC_COL_O + 32 * b, o);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&oempty_bar[b]);
-      const float inv = 1.0f / (s_sum[(b * 2 + 0) * 128 + r] + s_sum[(b * 2 + 1) * 128 + r]);
-      uint4 lo, hi;
-      lo.x = pack16<kFp16>(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-      lo.y = pack16<kFp16>(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-      lo.z = pack16<kFp16>(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-      lo.w = pack16<kFp16>(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-      hi.x = pack16<kFp16>(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
-      hi.y = pack16<kFp16>(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
-      hi.z = pack16<kFp16>(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
-      hi.w = pack16<kFp16>(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+      if (a.debug & 4) return;
+      const float inv = 1.0f / l;
       const size_t row = (size_t(lw0 + j) * a.types + t) * ATT_TOK + r;
-      uint8_t* dst = reinterpret_cast<uint8_t*>(a.out) + row * (size_t(a.C) * 2) + head * 64 + h * 32;
-      stg16(dst, lo);
-      stg16(dst + 16, hi);
+      uint8_t* dst = reinterpret_cast<uint8_t*>(a.out) + row * (size_t(a.C) * 2) + head * 64;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 v;
+        v.x = pack16<kFp16>(__uint_as_float(o[8 * q + 0]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
+        v.y = pack16<kFp16>(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
+        v.z = pack16<kFp16>(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
+        v.w = pack16<kFp16>(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
+        stg16(dst + 16 * q, v);
+      }
     };
-    for (int i = 0; i < nwin; ++i) {
-      const int b = i & 1;
+    int last = -1;
+    for (int i = wg; i < nwin; i += 2) {
+      if (r == 0) TR(3, i, 0);
       mbar_wait(&sfull_bar[b], (i >> 1) & 1);
+      if (r == 0) TR(3, i, 1);
       tc_fence_after();
-      f32x2 x[36];               // 72 logits of this thread's row slice, two per 64-bit register pair
-      // S and bias slices in 16-column pieces (72 = 4 x 16 + 8) to bound the live registers
-#pragma unroll
-      for (int part = 0; part < 4; ++part) {
-        uint32_t sa[16], ba[16];
-        tmem_ld16(lane_addr + ATC_COL_S + 144 * b + c0 + 16 * part, sa);
-        tmem_ld16(lane_addr + ATC_COL_BIAS + c0 + 16 * part, ba);
+      if (a.debug & 2) {
+        if (last >= 0) epilogue(last, l_prev);
+        tc_fence_before(); mbar_arrive(&pfull_bar[b]); last = i; continue;
+      }
+      // ---- pass 1: row maximum of S + bias over the 144 keys.  TMEM loads are software pipelined:
+      //      the loads of piece p+1 are in flight while piece p is reduced (tcgen05.wait::ld is global).
+      float pm = -INFINITY;
+      {
+        uint32_t sa[2][16], ba[2][16];
+        tmem_ld16(s_addr, sa[0]);
+        tmem_ld16(bias_addr, ba[0]);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          x[8 * part + e] = add2(pack2(__uint_as_float(sa[2 * e]), __uint_as_float(sa[2 * e + 1])),
-                                 pack2(__uint_as_float(ba[2 * e]), __uint_as_float(ba[2 * e + 1])));
-      }
-      {
-        uint32_t s8[8], b8[8];
-        tmem_ld8(lane_addr + ATC_COL_S + 144 * b + c0 + 64, s8);
-        tmem_ld8(lane_addr + ATC_COL_BIAS + c0 + 64, b8);
-        tmem_ld_wait();
+        for (int part = 0; part < 9; ++part) {
+          const int cur = part & 1;
+          if (part + 1 < 9) {
+            tmem_ld16(s_addr + 16 * (part + 1), sa[cur ^ 1]);
+            tmem_ld16(bias_addr + 16 * (part + 1), ba[cur ^ 1]);
+          }
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          x[32 + e] = add2(pack2(__uint_as_float(s8[2 * e]), __uint_as_float(s8[2 * e + 1])),
-                           pack2(__uint_as_float(b8[2 * e]), __uint_as_float(b8[2 * e + 1])));
+          for (int e = 0; e < 8; ++e) {
+            float a0, a1;
+            unpack2(add2(pack2(__uint_as_float(sa[cur][2 * e]), __uint_as_float(sa[cur][2 * e + 1])),
+                         pack2(__uint_as_float(ba[cur][2 * e]), __uint_as_float(ba[cur][2 * e + 1]))), a0, a1);
+            pm = max3(pm, a0, a1);
+          }
+          tmem_ld_wait();
+        }
       }
-      float pm;
-      {
-        float a0, a1;
-        unpack2(x[0], a0, a1);
-        pm = fmaxf(a0, a1);
-#pragma unroll
-        for (int e = 1; e < 36; ++e) { unpack2(x[e], a0, a1); pm = max3(pm, a0, a1); }
-      }
-      s_max[(b * 2 + h) * 128 + r] = pm;
-      tc_fence_before();
-      named_bar_sync(1, 256);      // all S slices are in registers (P may now overwrite S) + max exchange
-      tc_fence_after();
-      const float m = fmaxf(pm, s_max[(b * 2 + (h ^ 1)) * 128 + r]) * kLog2e;
+      if (r == 0) TR(3, i, 2);
+      // ---- output of this warpgroup's previous window (its PV finished long ago)
+      if (last >= 0) epilogue(last, l_prev);
+      if (r == 0) TR(3, i, 3);
+      // ---- pass 2: P = exp2((S + bias - max) log2e), packed 16-bit, written over S
+      const float m = pm * kLog2e;
       const f32x2 l2e2 = pack2(kLog2e, kLog2e), negm2 = pack2(-m, -m);
       f32x2 lsum = pack2(0.f, 0.f);
-      uint32_t pk[36];
+      {
+        uint32_t sa[2][16], ba[2][16];
+        tmem_ld16(s_addr, sa[0]);
+        tmem_ld16(bias_addr, ba[0]);
+        tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 36; ++e) {
-        float a0, a1;
-        unpack2(fma2(x[e], l2e2, negm2), a0, a1);
-        const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
-        lsum = add2(lsum, pack2(p0, p1));
-        pk[e] = pack16<kFp16>(p0, p1);
+        for (int part = 0; part < 9; ++part) {
+          const int cur = part & 1;
+          uint32_t pk[8];
+          if (part + 1 < 9) {
+            tmem_ld16(s_addr + 16 * (part + 1), sa[cur ^ 1]);
+            tmem_ld16(bias_addr + 16 * (part + 1), ba[cur ^ 1]);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float a0, a1;
+            const f32x2 x = add2(pack2(__uint_as_float(sa[cur][2 * e]), __uint_as_float(sa[cur][2 * e + 1])),
+                                 pack2(__uint_as_float(ba[cur][2 * e]), __uint_as_float(ba[cur][2 * e + 1])));
+            unpack2(fma2(x, l2e2, negm2), a0, a1);
+            const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+            lsum = add2(lsum, pack2(p0, p1));
+            pk[e] = pack16<kFp16>(p0, p1);
+          }
+          tmem_ld_wait();   // piece p+1 has landed: S columns [16(p+1), +16) are in registers before ...
+          // ... P columns [8p, +8) overwrite S columns that this thread has already consumed (8p+8 <= 16(p+1))
+          tmem_st8(s_addr + 8 * part, pk);
+        }
       }
-      float l;
       {
         float a0, a1;
         unpack2(lsum, a0, a1);
-        l = a0 + a1;
+        l_prev = a0 + a1;
       }
-      const uint32_t pcol = lane_addr + ATC_COL_S + 144 * b + 36 * h;
-#pragma unroll
-      for (int e = 0; e < 32; e += 8) tmem_st8(pcol + e, pk + e);
-      tmem_st4(pcol + 32, pk + 32);
-      s_sum[(b * 2 + h) * 128 + r] = l;
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&pfull_bar[b]);
-      if (i > 0) epilogue(i - 1);
+      if (r == 0) TR(4, i, 0);
+      last = i;
     }
-    named_bar_sync(1, 256);      // partner's row sum of the last window is visible
-    epilogue(nwin - 1);
+    if (last >= 0) epilogue(last, l_prev);
   }
 
   tc_fence_before();

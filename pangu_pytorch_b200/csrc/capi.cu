@@ -309,10 +309,19 @@ extern "C" int pangu_window_attention(const void* qkv16, const float* earth_bias
     const double ctas = double(base) * nsp;
     const double waves = ctas / g_num_sms;
     const double full = double(long(waves + 0.999999));
-    // cost model: waves * (per windows + ~1.5 windows of fixed bias-load cost)
-    const double cost = full * (per + 1.5);
+    // cost model: waves * (per windows + ~4.5 window-times of fixed per-CTA cost: TMEM alloc, bias tile
+    // load, pipeline fill and drain -- measured on B200, see profiles/)
+    const double cost = full * (per + 4.5);
     const double eff = 1.0 / cost;
     if (eff > best_eff) { best_eff = eff; best_split = nsp; a.lon_per_cta = per; }
+  }
+  a.debug = 0;
+  a.trace = nullptr;
+  if (const char* e = getenv("PANGU_B200_ATTN_TRACE")) a.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+  if (const char* e = getenv("PANGU_B200_ATTN_DEBUG")) a.debug = atoi(e);
+  if (const char* e = getenv("PANGU_B200_ATTN_PER")) {
+    a.lon_per_cta = atoi(e);
+    best_split = (g.nLon + a.lon_per_cta - 1) / a.lon_per_cta;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   dim3 grid(base, best_split);
