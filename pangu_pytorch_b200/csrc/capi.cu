@@ -72,14 +72,14 @@ extern "C" int pangu_check_device(void) { return ensure_init(); }
 
 // 2-D K-major operand map: dim0 = K (contiguous), dim1 = rows; box = 64 x box_rows, 128 B swizzle,
 // out-of-bounds rows read as zero (this is what pads ragged M tails).
-// 2-D map of a row-major 16-bit output [rows, cols]: box = 32 columns x 128 rows, 64 B swizzle
+// 2-D map of a row-major 16-bit output [rows, cols]: box = 32 columns x 32 rows (one warp's slab), 64 B swizzle
 static int make_out_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems) {
   PG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (pitch_elems * 2) % 16 == 0 && cols % 32 == 0,
              "output not TMA-storable (base %p, pitch %llu, cols %llu)", base, (unsigned long long)pitch_elems,
              (unsigned long long)cols);
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {pitch_elems * 2};
-  cuuint32_t box[2] = {32, 128};
+  cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -113,22 +113,27 @@ struct CfgBase {
   static constexpr int RECOVER = RC_NONE;
   static constexpr int CH = 32;
   static constexpr bool TMA16 = false;   // 16-bit row-major output written with TMA bulk stores
+  static constexpr int CLUSTER = 1;      // 2: CTA pairs share every weight (B) tile by TMA multicast
 };
 struct CfgQKV : CfgBase {      // linear1 of attention: bias, q-scale, 16-bit out
   static constexpr int BN = 192, UN = 192, STAGES = 4;
   static constexpr bool SCALEQ = true, OUT16 = true, TMA16 = true;
+  static constexpr int CLUSTER = 2;
 };
 struct CfgMLP1 : CfgBase {     // Mlp.linear1: bias + exact GELU, 16-bit out
   static constexpr int BN = 256, UN = 256, STAGES = 3;
   static constexpr bool GELU = true, OUT16 = true, TMA16 = true;
+  static constexpr int CLUSTER = 2;
 };
 struct CfgLNRes192 : CfgBase { // bias + LayerNorm(192) + residual, fp32 + 16-bit out
   static constexpr int BN = 192, UN = 192, STAGES = 4;
   static constexpr bool LN = true, RESID = true, OUT32 = true, OUT16 = true;
+  static constexpr int CLUSTER = 2;
 };
 struct CfgLNRes384 : CfgBase { // bias + LayerNorm(384) + residual
   static constexpr int BN = 384, UN = 192, STAGES = 3, CH = 16;
   static constexpr bool LN = true, RESID = true, OUT32 = true, OUT16 = true;
+  static constexpr int CLUSTER = 2;
 };
 struct CfgPlain192 : CfgBase { // (bias) -> fp32 + 16-bit (embed, downsample.linear, upsample.linear2, tests)
   static constexpr int BN = 192, UN = 192, STAGES = 4;
@@ -164,7 +169,7 @@ static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t 
   CUtensorMap ma, ma2, mb;
   PG_TRY(make_map(&ma, o.a, o.M, o.k1, o.a_pitch, BLOCK_M));
   if (o.k2 > 0) PG_TRY(make_map(&ma2, o.a2, o.M, o.k2, o.a2_pitch, BLOCK_M)); else ma2 = ma;
-  PG_TRY(make_map(&mb, o.b, o.N, o.k1 + o.k2, o.b_pitch, Cfg::UN));
+  PG_TRY(make_map(&mb, o.b, o.N, o.k1 + o.k2, o.b_pitch, Cfg::CLUSTER == 2 ? Cfg::BN / 2 : Cfg::UN));
   CUtensorMap mo = ma;
   if constexpr (Cfg::TMA16) {
     PG_REQUIRE(ep.rowmap == RM_IDENT && ep.dstmap == DM_IDENT && ep.row_base == 0 && ep.out16 != nullptr,
@@ -183,9 +188,24 @@ static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t 
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
     attr_done = true;
   }
-  const int tiles = sh.num_m_blocks * sh.num_n_blocks;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, kNumThreads, T::SMEM_BYTES, stream>>>(ma, ma2, mb, mo, sh, ep);
+  constexpr int CL = Cfg::CLUSTER;
+  const int units = ((sh.num_m_blocks + CL - 1) / CL) * sh.num_n_blocks;
+  const int max_units = g_num_sms / CL;
+  const int grid = (units < max_units ? units : max_units) * CL;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = T::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PG_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, ma2, mb, mo, sh, ep));
   PG_CUDA(cudaGetLastError());
   return 0;
 }

@@ -65,6 +65,7 @@ struct GemmTraits {
   static constexpr int NUM_B = BN / UN;
   static constexpr int CH = Cfg::CH;                 // epilogue chunk (columns)
   static constexpr int STAGES = Cfg::STAGES;
+  static constexpr int CL = Cfg::CLUSTER;            // CTAs per cluster sharing each B tile by TMA multicast
   static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS_RAW = ACC_STAGES * BN;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
@@ -81,7 +82,9 @@ struct GemmTraits {
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * WG_BYTES + BAR_BYTES;
   static_assert(BN % UN == 0 && UN % 16 == 0 && UN <= 256, "bad N tiling");
+  static_assert(CL == 1 || (CL == 2 && (BN / 2) % 8 == 0 && BN / 2 <= 256), "bad cluster B split");
   static_assert(BN % CH == 0 && (CH == 16 || CH == 32), "bad epilogue chunk");
+  static_assert(!Cfg::TMA16 || BN % 64 == 0, "TMA16: both warpgroups take whole 32-column chunks");
   static_assert(!Cfg::TMA16 || (CH == 32 && !Cfg::LN && !Cfg::OUT32 && Cfg::RECOVER == 0), "TMA16: plain 16-bit output");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024 B alignment");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
@@ -112,7 +115,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = shape.num_m_blocks * shape.num_n_blocks;
+  // Work units: (group of CL consecutive m-blocks, n-block).  The CL CTAs of a cluster take the
+  // m-blocks of one group (same n-block, k-blocks in lockstep) and share each B tile by multicast.
+  constexpr int CL = T::CL;
+  const int cta_rank = CL == 1 ? 0 : int(cluster_ctarank());
+  const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
+  const int num_units = ((shape.num_m_blocks + CL - 1) / CL) * shape.num_n_blocks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -121,7 +129,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if constexpr (Cfg::TMA16) tma_prefetch_desc(&tmOut);
     for (int s = 0; s < T::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);     // one tcgen05.commit arrival per CTA of the cluster
     }
     for (int a = 0; a < T::ACC_STAGES; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -131,7 +139,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1) tmem_alloc<T::TMEM_COLS>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL == 1) __syncthreads(); else cluster_sync_all();   // peer barriers initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -140,8 +148,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / shape.num_n_blocks, n_blk = tile % shape.num_n_blocks;
+      for (int unit = unit0; unit < num_units; unit += unit_stride) {
+        const int m_blk = (unit / shape.num_n_blocks) * CL + cta_rank, n_blk = unit % shape.num_n_blocks;
         for (int kb = 0; kb < shape.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + stage * T::STAGE_BYTES;
@@ -151,9 +159,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_load_2d(&tmA, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
           else
             tma_load_2d(&tmA2, &full_bar[stage], sa, (kb - shape.k_split) * BLOCK_K, m_blk * BLOCK_M);
+          if constexpr (CL == 1) {
 #pragma unroll
-          for (int j = 0; j < T::NUM_B; ++j)
-            tma_load_2d_hint(&tmB, &full_bar[stage], sb + j * UN * 128, kb * BLOCK_K, n_blk * BN + j * UN, kEvictLast);
+            for (int j = 0; j < T::NUM_B; ++j)
+              tma_load_2d_hint(&tmB, &full_bar[stage], sb + j * UN * 128, kb * BLOCK_K, n_blk * BN + j * UN, kEvictLast);
+          } else {
+            // this CTA fetches its 1/CL slice of the B tile and multicasts it to the whole cluster
+            constexpr int SL = BN / CL;
+            tma_load_2d_mcast(&tmB, &full_bar[stage], sb + cta_rank * SL * 128, kb * BLOCK_K, n_blk * BN + cta_rank * SL,
+                              uint16_t((1 << CL) - 1), kEvictLast);
+          }
           if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -166,7 +181,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = unit0; unit < num_units; unit += unit_stride) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < shape.num_k_blocks; ++kb) {
@@ -184,7 +199,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                           (kb | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees the ring slot once these MMAs have read it
+          // frees the ring slot (in every CTA of the cluster: the peer multicasts into it) once read
+          if constexpr (CL == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], uint16_t((1 << CL) - 1));
           if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
@@ -211,8 +227,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t acc_phase = 0;
     int loaded_n_blk = -1;
     [[maybe_unused]] int sbuf = 0;   // TMA16: staging buffer parity, alternates across chunks AND tiles
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / shape.num_n_blocks, n_blk = tile % shape.num_n_blocks;
+    for (int unit = unit0; unit < num_units; unit += unit_stride) {
+      const int m_blk = (unit / shape.num_n_blocks) * CL + cta_rank, n_blk = unit % shape.num_n_blocks;
       // ---- per-tile tables (overlaps the mainloop of this tile)
       named_bar_sync(bar_id, 128);  // previous tile's phase B done with tables/params
       {
@@ -248,20 +264,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       };
       if constexpr (Cfg::TMA16) {
-        // ------- 16-bit row-major output, identity row map: registers -> swizzled smem tile -> TMA store.
-        // One named barrier per chunk; the issuing thread drains its previous bulk store before the
-        // barrier, so the other staging buffer is known to be free when the next chunk starts.
+        // ------- 16-bit row-major output, identity row map.  Every warp is autonomous: it converts its
+        // own 32 accumulator rows chunk by chunk into a private swizzled [32 x 64 B] smem slab and one lane
+        // issues a TMA bulk store per slab (double buffered) -- no cross-warp barrier in the loop.  The
+        // TMEM load of the next chunk is in flight while the current one is being converted.
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t tacc16 = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
-#pragma unroll 1
-        for (int c0 = wg * 32; c0 < BN; c0 += 64) {
-          uint32_t r[32];
-          tmem_ld32(tacc16 + c0, r);
-          tmem_ld_wait();
+        uint8_t* wstg = stg + ((warp - 2) & 3) * 4096;
+        constexpr int NCH = BN / 64;               // chunks of 32 columns per warpgroup
+        uint32_t rb[2][32];
+        tmem_ld32(tacc16 + wg * 32, rb[0]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c0 = wg * 32 + 64 * ci;
+          uint32_t (&r)[32] = rb[ci & 1];
+          if (ci + 1 < NCH) tmem_ld32(tacc16 + c0 + 64, rb[(ci + 1) & 1]);
+          if (lane == 0) bulk_wait_read<1>();      // the store issued two chunks ago has read this slab
+          __syncwarp();
           const int ncol0 = n_blk * BN + c0;
           const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
-          uint8_t* tile = stg + sbuf * 8192;
+          uint8_t* tile = wstg + sbuf * 2048;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {          // 4 x 16 B (8 columns each) per 64 B row
             float v[8];
@@ -283,17 +307,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint4 h16;
             h16.x = pack16<kFp16>(v[0], v[1]); h16.y = pack16<kFp16>(v[2], v[3]);
             h16.z = pack16<kFp16>(v[4], v[5]); h16.w = pack16<kFp16>(v[6], v[7]);
-            // SWIZZLE_64B: 16 B chunk index XOR bits [7,9) of the byte address (= (row >> 1) & 3)
-            *reinterpret_cast<uint4*>(tile + row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) = h16;
+            // SWIZZLE_64B: 16 B chunk index XOR bits [7,9) of the byte address (= (slab row >> 1) & 3)
+            *reinterpret_cast<uint4*>(tile + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = h16;
           }
           fence_proxy_async_smem();
-          if (tid == 0) bulk_wait_read<0>();     // store issued from the other buffer has been read out
-          named_bar_sync(bar_id, 128);
-          if (tid == 0) {
-            tma_store_2d(&tmOut, tile, ncol0, m_blk * BLOCK_M);
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, tile, ncol0, m_blk * BLOCK_M + quad * 32);
             bulk_commit();
           }
           sbuf ^= 1;
+          if (ci + 1 < NCH) tmem_ld_wait();
         }
         tc_fence_before();
         mbar_arrive(&tempty_bar[acc]);
@@ -460,10 +484,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   if constexpr (Cfg::TMA16) {
-    if (warp >= 2 && (((warp - 2) & 3) * 32 + lane) == 0) bulk_wait_all();   // smem must outlive the bulk stores
+    if (warp >= 2 && lane == 0) bulk_wait_all();   // smem must outlive the bulk stores
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL == 1) __syncthreads(); else cluster_sync_all();   // no remote arrive / multicast may target an exited CTA
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<T::TMEM_COLS>(tmem_base);
