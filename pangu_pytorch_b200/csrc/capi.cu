@@ -220,6 +220,7 @@ static EpiArgs epi_defaults() {
   e.Z = 8; e.H = 1; e.W = 12;
   e.res_scale = 1.f; e.q_scale = 1.f; e.eps = 1e-5f;
   e.rowmap = RM_IDENT; e.dstmap = DM_IDENT;
+  if (const char* d = getenv("PANGU_B200_GEMM_DEBUG")) e.debug = atoi(d);
   return e;
 }
 

@@ -55,6 +55,7 @@ struct EpiArgs {
   float res_scale;      // DropPath factor on the normalised branch (1 in eval)
   float eps;
   int lat, lon;         // RECOVER: output field extents (721, 1440)
+  int debug;            // development only: bit0 no residual loads, bit1 no stores, bit2 no epilogue math
 };
 
 // ---------------------------------------------------------------------------------------
@@ -74,13 +75,13 @@ struct GemmTraits {
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_PITCH = CH * 4 + 16;      // bytes; == 16 (mod 128) -> conflict-free 16 B rows
-  // TMA16 configs stage two [128 rows][32 cols] 16-bit tiles (SWIZZLE_64B, 8 KB each) per warpgroup
-  static constexpr int STG_BYTES = Cfg::TMA16 ? 2 * 8192 : ((BLOCK_M * STG_PITCH + 1023) / 1024) * 1024;
-  static constexpr int PAR_BYTES = 3 * BN * 4;       // bias / gamma / beta per warpgroup
-  static constexpr int TAB_BYTES = 2 * BLOCK_M * 4;  // row -> token, row -> 16-bit destination row
-  static constexpr int WG_BYTES = ((STG_BYTES + PAR_BYTES + TAB_BYTES + 1023) / 1024) * 1024;
+  // per-warp staging slab: [32 rows][STG_PITCH] fp32, or (TMA16) two [32 rows][64 B] SWIZZLE_64B tiles
+  static constexpr int SLAB_BYTES = Cfg::TMA16 ? 4096 : ((32 * STG_PITCH + 511) / 512) * 512;
+  static constexpr int PAR_BYTES = 3 * BN * 4;       // bias / gamma / beta (shared by the 8 epilogue warps)
+  static constexpr int TAB_BYTES = 8 * 64 * 4;       // per warp: row -> token, row -> 16-bit destination row
+  static constexpr int EPI_BYTES = ((8 * SLAB_BYTES + PAR_BYTES + TAB_BYTES + 1023) / 1024) * 1024;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * WG_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
   static_assert(BN % UN == 0 && UN % 16 == 0 && UN <= 256, "bad N tiling");
   static_assert(CL == 1 || (CL == 2 && (BN / 2) % 8 == 0 && BN / 2 <= 256), "bad cluster B split");
   static_assert(BN % CH == 0 && (CH == 16 || CH == 32), "bad epilogue chunk");
@@ -106,7 +107,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;
   uint8_t* wg_area = smem + T::STAGES * T::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wg_area + 2 * T::WG_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wg_area + T::EPI_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + T::STAGES;          // [STAGES]
   uint64_t* tfull_bar = bars + 2 * T::STAGES;      // [ACC_STAGES]
@@ -209,83 +210,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ================================ epilogue ================================
-    const int wg = (warp - 2) >> 2;            // 0 / 1: alternates column chunks
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;          // tile row owned by this thread (phase A)
-    const int tid = ((warp - 2) & 3) * 32 + lane;  // 0..127 inside the warpgroup (phase B)
-    uint8_t* my = wg_area + wg * T::WG_BYTES;
-    uint8_t* stg = my;
-    float* s_bias = reinterpret_cast<float*>(my + T::STG_BYTES);
+    // Eight autonomous warps.  Warp w may touch TMEM lanes [32*(w%4), +32): it owns those 32 tile rows;
+    // the two warps of a lane quadrant take alternate column chunks.  No cross-warp barrier is needed in
+    // the steady state: tables, staging slab and output stores are all per warp (__syncwarp only).
+    const int quad = warp & 3;                 // TMEM lane quadrant
+    const int half = (warp - 2) >> 2;          // 0 / 1: which column chunks
+    const int wslot = warp - 2;                // 0..7
+    uint8_t* slab = wg_area + wslot * T::SLAB_BYTES;                       // [32 rows][STG_PITCH] or 2 x 2 KB (TMA16)
+    float* s_bias = reinterpret_cast<float*>(wg_area + 8 * T::SLAB_BYTES); // shared by the 8 warps
     float* s_gamma = s_bias + BN;
     float* s_beta = s_gamma + BN;
-    int* s_tok = reinterpret_cast<int*>(my + T::STG_BYTES + T::PAR_BYTES);
-    int* s_dst = s_tok + BLOCK_M;
-    const int bar_id = 1 + wg;
+    int* s_tok = reinterpret_cast<int*>(s_beta + BN) + wslot * 64;         // per warp: row -> token
+    int* s_dst = s_tok + 32;                                               //           row -> 16-bit dest row
     const Geo geo = make_geo(ep.Z, ep.H, ep.W);
 
     int acc = 0;
     uint32_t acc_phase = 0;
     int loaded_n_blk = -1;
-    [[maybe_unused]] int sbuf = 0;   // TMA16: staging buffer parity, alternates across chunks AND tiles
+    [[maybe_unused]] int sbuf = 0;   // TMA16: slab parity, alternates across chunks AND tiles
     for (int unit = unit0; unit < num_units; unit += unit_stride) {
       const int m_blk = (unit / shape.num_n_blocks) * CL + cta_rank, n_blk = unit % shape.num_n_blocks;
-      // ---- per-tile tables (overlaps the mainloop of this tile)
-      named_bar_sync(bar_id, 128);  // previous tile's phase B done with tables/params
-      {
-        const int g = m_blk * BLOCK_M + tid;  // logical A row
-        int tok = -1;
-        if (g < shape.M) {
-          if (ep.rowmap == RM_IDENT) tok = g + ep.row_base;
-          else if (ep.rowmap == RM_WIN2TOK) tok = win_row_to_token(geo, g, ep.roll_in);
-          else tok = upsample_row_to_token(geo, g, n_blk);
+      // ---- epilogue parameters of this n-block (uniform decision across the 8 warps; LN kernels: once)
+      if (loaded_n_blk != n_blk) {
+        named_bar_sync(1, kEpiThreads);
+        for (int c = threadIdx.x - 64; c < BN; c += kEpiThreads) {
+          s_bias[c] = ep.bias ? ep.bias[n_blk * BN + c] : 0.f;
+          if constexpr (Cfg::LN) { s_gamma[c] = ep.gamma[c]; s_beta[c] = ep.beta[c]; }
         }
-        int dst = tok;
-        if (ep.dstmap == DM_TOK2WIN && tok >= 0) dst = token_to_win_row(geo, tok, ep.roll_out);
-        s_tok[tid] = tok;
-        s_dst[tid] = dst;
-        if (loaded_n_blk != n_blk) {
-          for (int c = tid; c < BN; c += 128) {
-            s_bias[c] = ep.bias ? ep.bias[n_blk * BN + c] : 0.f;
-            if constexpr (Cfg::LN) { s_gamma[c] = ep.gamma[c]; s_beta[c] = ep.beta[c]; }
-          }
-          loaded_n_blk = n_blk;
-        }
+        named_bar_sync(1, kEpiThreads);
+        loaded_n_blk = n_blk;
       }
-      named_bar_sync(bar_id, 128);
+      const uint32_t tacc = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
 
-      auto load_resid = [&](int cc, uint4 (&dst)[CH / 4]) {
-#pragma unroll
-        for (int it = 0; it < CH / 4; ++it) {
-          const int id = it * 128 + tid;
-          const int rr = id / (CH / 4), pc = id % (CH / 4);
-          const int tok = s_tok[rr];
-          dst[it] = make_uint4(0u, 0u, 0u, 0u);
-          if (tok >= 0) dst[it] = ldg16(ep.resid + size_t(tok) * ep.ld32 + (n_blk * BN + cc + pc * 4));
-        }
-      };
       if constexpr (Cfg::TMA16) {
-        // ------- 16-bit row-major output, identity row map.  Every warp is autonomous: it converts its
-        // own 32 accumulator rows chunk by chunk into a private swizzled [32 x 64 B] smem slab and one lane
-        // issues a TMA bulk store per slab (double buffered) -- no cross-warp barrier in the loop.  The
-        // TMEM load of the next chunk is in flight while the current one is being converted.
+        // ------- 16-bit row-major output, identity row map: registers -> private swizzled [32 x 64 B]
+        // slab -> one TMA bulk store per slab (double buffered).  The TMEM load of the next chunk is in
+        // flight while the current one is being converted.
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        const uint32_t tacc16 = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
-        uint8_t* wstg = stg + ((warp - 2) & 3) * 4096;
-        constexpr int NCH = BN / 64;               // chunks of 32 columns per warpgroup
+        constexpr int NCH = BN / 64;               // chunks of 32 columns per warp
         uint32_t rb[2][32];
-        tmem_ld32(tacc16 + wg * 32, rb[0]);
+        tmem_ld32(tacc + half * 32, rb[0]);
         tmem_ld_wait();
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
-          const int c0 = wg * 32 + 64 * ci;
+          const int c0 = half * 32 + 64 * ci;
           uint32_t (&r)[32] = rb[ci & 1];
-          if (ci + 1 < NCH) tmem_ld32(tacc16 + c0 + 64, rb[(ci + 1) & 1]);
+          if (ci + 1 < NCH) tmem_ld32(tacc + c0 + 64, rb[(ci + 1) & 1]);
           if (lane == 0) bulk_wait_read<1>();      // the store issued two chunks ago has read this slab
           __syncwarp();
           const int ncol0 = n_blk * BN + c0;
           const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
-          uint8_t* tile = wstg + sbuf * 2048;
+          uint8_t* tile = slab + sbuf * 2048;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {          // 4 x 16 B (8 columns each) per 64 B row
             float v[8];
@@ -325,84 +301,119 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         continue;
       }
 
-      [[maybe_unused]] uint4 resq[CH / 4];
-      if constexpr (Cfg::RESID) load_resid(wg * CH, resq);   // first chunk: latency hidden by the mainloop wait
+      // ---- per-warp row tables (overlap the mainloop of this tile)
+      __syncwarp();
+      {
+        const int g = m_blk * BLOCK_M + quad * 32 + lane;  // logical A row of this lane
+        int tok = -1;
+        if (g < shape.M) {
+          if (ep.rowmap == RM_IDENT) tok = g + ep.row_base;
+          else if (ep.rowmap == RM_WIN2TOK) tok = win_row_to_token(geo, g, ep.roll_in);
+          else tok = upsample_row_to_token(geo, g, n_blk);
+        }
+        int dst = tok;
+        if (ep.dstmap == DM_TOK2WIN && tok >= 0) dst = token_to_win_row(geo, tok, ep.roll_out);
+        s_tok[lane] = tok;
+        s_dst[lane] = dst;
+      }
+      __syncwarp();
+
+      constexpr int PPR = CH / 4;                // 16 B fp32 pieces per row of a chunk
+      // phase-B item (it, lane) -> (row rr of this warp's 32, piece pc): PPR lanes cover one row
+      auto load_resid = [&](int cc, uint4 (&dst)[PPR]) {
+#pragma unroll
+        for (int it = 0; it < PPR; ++it) {
+          const int id = it * 32 + lane;
+          const int rr = id / PPR, pc = id % PPR;
+          const int tok = s_tok[rr];
+          dst[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (tok >= 0 && !(ep.debug & 1)) dst[it] = ldg16(ep.resid + size_t(tok) * ep.ld32 + (n_blk * BN + cc + pc * 4));
+        }
+      };
+      [[maybe_unused]] uint4 resq[PPR];
+      if constexpr (Cfg::RESID) load_resid(half * CH, resq);   // first chunk: latency hidden by the mainloop wait
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+      if (ep.debug & 4) {
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+        if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
 
       float mean = 0.f, rstd = 1.f;
       if constexpr (Cfg::LN) {
-        // thread-local LayerNorm statistics over the whole row (shifted sums)
-        float shift = 0.f, s1 = 0.f, s2 = 0.f;
+        // thread-local LayerNorm statistics over the whole row (shifted sums, packed fp32x2 math)
+        float shift = 0.f;
+        f32x2 s1 = pack2(0.f, 0.f), s2 = pack2(0.f, 0.f);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(tacc + c0, r);
           tmem_ld_wait();
           if (c0 == 0) shift = __uint_as_float(r[0]) + s_bias[0];
+          const f32x2 nshift = pack2(-shift, -shift);
           const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 bb = b4[j4];
-            const float v0 = __uint_as_float(r[4 * j4]) + bb.x - shift, v1 = __uint_as_float(r[4 * j4 + 1]) + bb.y - shift;
-            const float v2 = __uint_as_float(r[4 * j4 + 2]) + bb.z - shift, v3 = __uint_as_float(r[4 * j4 + 3]) + bb.w - shift;
-            s1 += (v0 + v1) + (v2 + v3);
-            s2 = fmaf(v0, v0, s2); s2 = fmaf(v1, v1, s2); s2 = fmaf(v2, v2, s2); s2 = fmaf(v3, v3, s2);
+            const f32x2 v01 = add2(add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y)), nshift);
+            const f32x2 v23 = add2(add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w)), nshift);
+            s1 = add2(s1, add2(v01, v23));
+            s2 = fma2(v01, v01, s2);
+            s2 = fma2(v23, v23, s2);
           }
         }
+        float s1a, s1b, s2a, s2b;
+        unpack2(s1, s1a, s1b);
+        unpack2(s2, s2a, s2b);
         const float inv_n = 1.0f / float(BN);
-        const float m = s1 * inv_n;
-        const float var = fmaxf(s2 * inv_n - m * m, 0.f);
+        const float m = (s1a + s1b) * inv_n;
+        const float var = fmaxf((s2a + s2b) * inv_n - m * m, 0.f);
         mean = shift + m;
         rstd = rsqrtf(var + ep.eps);
       }
+      // y = ((acc + bias) - mean) * rstd * gamma + beta  ==  (acc + bias) * a + b  then * gamma + beta
+      const f32x2 ln_a = pack2(rstd, rstd), ln_b = pack2(-mean * rstd, -mean * rstd);
 
 #pragma unroll 1
-      for (int c0 = wg * CH; c0 < BN; c0 += 2 * CH) {
-        // ---------------- residual prefetch for the NEXT chunk's phase-B items (consumed two barriers later)
-        [[maybe_unused]] uint4 resn[CH / 4];
+      for (int c0 = half * CH; c0 < BN; c0 += 2 * CH) {
+        // ---------------- residual prefetch for the NEXT chunk's phase-B items
+        [[maybe_unused]] uint4 resn[PPR];
         if constexpr (Cfg::RESID) {
           if (c0 + 2 * CH < BN) load_resid(c0 + 2 * CH, resn);
         }
-        // ---------------- phase A: TMEM -> registers -> math -> staging (row per thread)
+        // ---------------- phase A: TMEM -> registers -> math -> slab (row per lane)
         {
           uint32_t r[CH];
           if constexpr (CH == 32) tmem_ld32(tacc + c0, r); else tmem_ld16(tacc + c0, r);
           tmem_ld_wait();
-          const int ncol0 = n_blk * BN + c0;
           const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
           const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
           const float4* e4 = reinterpret_cast<const float4*>(s_beta + c0);
-          uint4* dstp = reinterpret_cast<uint4*>(stg + row * T::STG_PITCH);
+          uint4* dstp = reinterpret_cast<uint4*>(slab + lane * T::STG_PITCH);
 #pragma unroll
           for (int j4 = 0; j4 < CH / 4; ++j4) {
             const float4 bb = b4[j4];
-            float v[4] = {__uint_as_float(r[4 * j4]) + bb.x, __uint_as_float(r[4 * j4 + 1]) + bb.y,
-                          __uint_as_float(r[4 * j4 + 2]) + bb.z, __uint_as_float(r[4 * j4 + 3]) + bb.w};
+            f32x2 v01 = add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y));
+            f32x2 v23 = add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w));
             if constexpr (Cfg::LN) {
               const float4 gg = g4[j4], ee = e4[j4];
-              v[0] = fmaf((v[0] - mean) * rstd, gg.x, ee.x);
-              v[1] = fmaf((v[1] - mean) * rstd, gg.y, ee.y);
-              v[2] = fmaf((v[2] - mean) * rstd, gg.z, ee.z);
-              v[3] = fmaf((v[3] - mean) * rstd, gg.w, ee.w);
+              v01 = fma2(fma2(v01, ln_a, ln_b), pack2(gg.x, gg.y), pack2(ee.x, ee.y));
+              v23 = fma2(fma2(v23, ln_a, ln_b), pack2(gg.z, gg.w), pack2(ee.z, ee.w));
             }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if constexpr (Cfg::SCALEQ) { if (ncol0 + 4 * j4 + e < ep.q_cols) v[e] *= ep.q_scale; }
-              if constexpr (Cfg::GELU) v[e] = gelu_erf(v[e]);
-            }
-            dstp[j4] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
-                                  __float_as_uint(v[3]));
+            float v0, v1, v2, v3;
+            unpack2(v01, v0, v1);
+            unpack2(v23, v2, v3);
+            dstp[j4] = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
           }
         }
-        named_bar_sync(bar_id, 128);
-        // ---------------- phase B: staging -> global, coalesced, row-remapped
+        __syncwarp();
+        // ---------------- phase B: slab -> global, coalesced (PPR lanes per row), row-remapped
         if constexpr (Cfg::RECOVER != RC_NONE) {
-          constexpr int PPR = CH / 4;  // 16 B fp32 pieces per row
 #pragma unroll
           for (int it = 0; it < PPR; ++it) {
-            const int id = it * 128 + tid;
+            const int id = it * 32 + lane;
             const int rr = id / PPR, pc = id % PPR;
             const int tok = s_tok[rr];
             if (tok < 0) continue;
@@ -421,19 +432,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int c = grp >> 2;
               off = (size_t(c) * ep.lat + la) * ep.lon + 4 * wt;
             }
-            const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * T::STG_PITCH + pc * 16);
+            const uint4 v = *reinterpret_cast<const uint4*>(slab + rr * T::STG_PITCH + pc * 16);
             stg16(ep.out32 + off, v);
           }
         } else if constexpr (Cfg::OUT32) {
-          constexpr int PPR = CH / 4;
 #pragma unroll
           for (int it = 0; it < PPR; ++it) {
-            const int id = it * 128 + tid;
+            const int id = it * 32 + lane;
             const int rr = id / PPR, pc = id % PPR;
             const int tok = s_tok[rr];
-            if (tok < 0) continue;
+            if (tok < 0 || (ep.debug & 2)) continue;
             const int col = (Cfg::GROUPCOL ? 0 : n_blk * BN) + c0 + pc * 4;
-            uint4 v = *reinterpret_cast<const uint4*>(stg + rr * T::STG_PITCH + pc * 16);
+            uint4 v = *reinterpret_cast<const uint4*>(slab + rr * T::STG_PITCH + pc * 16);
             float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y), f2 = __uint_as_float(v.z),
                   f3 = __uint_as_float(v.w);
             if constexpr (Cfg::RESID) {
@@ -451,17 +461,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         } else {
-          // 16-bit only: 8 columns (32 B of staging) -> one 16 B store
-          constexpr int PPR = CH / 8;
+          // 16-bit only: 8 columns (32 B of the slab) -> one 16 B store
+          constexpr int PPR8 = CH / 8;
 #pragma unroll
-          for (int it = 0; it < PPR; ++it) {
-            const int id = it * 128 + tid;
-            const int rr = id / PPR, pc = id % PPR;
+          for (int it = 0; it < PPR8; ++it) {
+            const int id = it * 32 + lane;
+            const int rr = id / PPR8, pc = id % PPR8;
             const int tok = s_tok[rr];
             if (tok < 0) continue;
             const int col = (Cfg::GROUPCOL ? 0 : n_blk * BN) + c0 + pc * 8;
-            const uint4 a = *reinterpret_cast<const uint4*>(stg + rr * T::STG_PITCH + pc * 32);
-            const uint4 b = *reinterpret_cast<const uint4*>(stg + rr * T::STG_PITCH + pc * 32 + 16);
+            const uint4 a = *reinterpret_cast<const uint4*>(slab + rr * T::STG_PITCH + pc * 32);
+            const uint4 b = *reinterpret_cast<const uint4*>(slab + rr * T::STG_PITCH + pc * 32 + 16);
             uint4 h;
             h.x = pack16<kFp16>(__uint_as_float(a.x), __uint_as_float(a.y));
             h.y = pack16<kFp16>(__uint_as_float(a.z), __uint_as_float(a.w));
@@ -470,10 +480,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             stg16(reinterpret_cast<uint16_t*>(ep.out16) + size_t(s_dst[rr]) * ep.ld16 + col, h);
           }
         }
-        named_bar_sync(bar_id, 128);  // staging free again
+        __syncwarp();  // slab free again
         if constexpr (Cfg::RESID) {
 #pragma unroll
-          for (int it = 0; it < CH / 4; ++it) resq[it] = resn[it];
+          for (int it = 0; it < PPR; ++it) resq[it] = resn[it];
         }
       }
       // accumulator drained by this thread
