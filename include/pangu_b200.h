@@ -122,6 +122,16 @@ int pangu_patch_recover(const void* skip16, const void* x16, const void* w_upper
 int pangu_denorm_fields(float* upper, float* surface, const float* surface_mean, const float* surface_std,
                         const float* upper_mean, const float* upper_std, int lat, int lon, void* stream);
 
+/* Training loss of models/pangu_sample.py:57-67: normData(target) (era5_data/utils_data.py:315-321) then
+ * mean(|out - tgt| * w_upper) + 0.25 * mean(|out_s - tgt_s| * w_surface), weights era5_data/config.py:45-46.
+ * Targets are PHYSICAL fields; statistics are the input-order arrays (level reversal applied inside).
+ * upper_weights_host[5] / surface_weights_host[4] are HOST pointers (copied into the launch).  loss: device
+ * float[1]; ws_acc: device double[2] scratch; grad_*: optional dL/d(output) (seed of the backward pass). */
+int pangu_l1_loss(const float* out_upper, const float* out_surface, const float* tgt_upper, const float* tgt_surface,
+                  const float* surface_mean, const float* surface_std, const float* upper_mean, const float* upper_std,
+                  const float* upper_weights_host, const float* surface_weights_host, float* loss, double* ws_acc,
+                  float* grad_upper, float* grad_surface, int lat, int lon, void* stream);
+
 /* Generic nn.Linear forward used by the stand-alone module API (EarthAttention3D.linear2,
  * Mlp.linear1/2 outside the fused block path) and by the unit tests of the tcgen05 GEMM engine:
  * out = a16 [M,K] * w16 [N,K]^T + bias.  gelu == 0: fp32 out32 and 16-bit out16 (both required),

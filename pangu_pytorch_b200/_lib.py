@@ -31,6 +31,7 @@ SIGNATURES = {
     "pangu_patch_recover": [_P] * 8 + [_I, _I, _I, _I, _I, _I, _I, _P],
     "pangu_linear": [_P] * 5 + [_I, _I, _I, _I, _I, _P],
     "pangu_denorm_fields": [_P] * 6 + [_I, _I, _P],
+    "pangu_l1_loss": [_P] * 14 + [_I, _I, _P],
 }
 
 _lib = None

@@ -534,6 +534,32 @@ extern "C" int pangu_denorm_fields(float* upper, float* surface, const float* su
   return 0;
 }
 
+extern "C" int pangu_l1_loss(const float* out_upper, const float* out_surface, const float* tgt_upper,
+                             const float* tgt_surface, const float* surface_mean, const float* surface_std,
+                             const float* upper_mean, const float* upper_std, const float* upper_weights_host,
+                             const float* surface_weights_host, float* loss, double* ws_acc, float* grad_upper,
+                             float* grad_surface, int lat, int lon, void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(lat > 0 && lon > 0 && (size_t(lat) * lon) % 4 == 0, "l1_loss: lat*lon must be a multiple of 4");
+  PG_REQUIRE(upper_weights_host && surface_weights_host && loss && ws_acc, "l1_loss: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  L1Args a;
+  a.out_u = out_upper; a.out_s = out_surface; a.tgt_u = tgt_upper; a.tgt_s = tgt_surface;
+  a.s_mean = surface_mean; a.s_std = surface_std; a.u_mean = upper_mean; a.u_std = upper_std;
+  a.acc = ws_acc; a.grad_u = grad_upper; a.grad_s = grad_surface;
+  for (int i = 0; i < 5; ++i) a.wu[i] = upper_weights_host[i];
+  for (int i = 0; i < 4; ++i) a.ws[i] = surface_weights_host[i];
+  a.plane4 = int(size_t(lat) * lon / 4);
+  const double nu = 65.0 * lat * lon, ns = 4.0 * lat * lon;
+  a.inv_nu = float(1.0 / nu); a.inv_ns = float(1.0 / ns);
+  PG_CUDA(cudaMemsetAsync(ws_acc, 0, 2 * sizeof(double), s));
+  dim3 grid((a.plane4 + 255) / 256 < 32 ? (a.plane4 + 255) / 256 : 32, 69);
+  l1_loss_kernel<<<grid, 256, 0, s>>>(a);
+  l1_finalize_kernel<<<1, 1, 0, s>>>(ws_acc, loss, 1.0 / nu, 1.0 / ns);
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int pangu_linear(const void* a16, const void* w16, const float* bias, float* out32, void* out16, int M,
                             int N, int K, int gelu, int fp16, void* stream) {
   PG_TRY(ensure_init());

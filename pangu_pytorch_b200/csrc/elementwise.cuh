@@ -193,6 +193,67 @@ __global__ void __launch_bounds__(256) denorm_fields_kernel(float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
+// Training loss of the reference (models/pangu_sample.py:57-67): the target is normalised with the
+// output-order statistics (normData, era5_data/utils_data.py:315-321), then
+//   L = mean(|o - t| * w_upper[c]) + 0.25 * mean(|o_s - t_s| * w_surface[c]).
+// Plane p < 65: upper (c = p/13, level l = p%13, statistics row 12-l); p >= 65: surface.  Partial sums go
+// to two fp64 accumulators; optionally dL/d(output) is written (seed of the backward pass).
+struct L1Args {
+  const float* out_u; const float* out_s; const float* tgt_u; const float* tgt_s;
+  const float* s_mean; const float* s_std; const float* u_mean; const float* u_std;
+  double* acc;            // [2] zero-initialised: sum_upper, sum_surface
+  float* grad_u; float* grad_s;   // nullable
+  float wu[5], ws[4];
+  int plane4;             // lat*lon / 4
+  float inv_nu, inv_ns;   // 1 / numel
+};
+__global__ void __launch_bounds__(256) l1_loss_kernel(const L1Args a) {
+  const int p = blockIdx.y;
+  const bool up = p < 65;
+  float m, s, w;
+  const float4 *o, *t;
+  float4* g;
+  if (up) {
+    const int c = p / 13, l = p % 13;
+    m = a.u_mean[(12 - l) * 5 + c]; s = a.u_std[(12 - l) * 5 + c]; w = a.wu[c];
+    o = reinterpret_cast<const float4*>(a.out_u) + size_t(p) * a.plane4;
+    t = reinterpret_cast<const float4*>(a.tgt_u) + size_t(p) * a.plane4;
+    g = a.grad_u ? reinterpret_cast<float4*>(a.grad_u) + size_t(p) * a.plane4 : nullptr;
+  } else {
+    m = a.s_mean[p - 65]; s = a.s_std[p - 65]; w = a.ws[p - 65];
+    o = reinterpret_cast<const float4*>(a.out_s) + size_t(p - 65) * a.plane4;
+    t = reinterpret_cast<const float4*>(a.tgt_s) + size_t(p - 65) * a.plane4;
+    g = a.grad_s ? reinterpret_cast<float4*>(a.grad_s) + size_t(p - 65) * a.plane4 : nullptr;
+  }
+  const float gs = up ? w * a.inv_nu : 0.25f * w * a.inv_ns;
+  float sum = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.plane4; i += gridDim.x * blockDim.x) {
+    const float4 ov = o[i], tv = t[i];
+    const float d0 = ov.x - (tv.x - m) / s, d1 = ov.y - (tv.y - m) / s, d2 = ov.z - (tv.z - m) / s,
+                d3 = ov.w - (tv.w - m) / s;
+    sum += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+    if (g) {
+      g[i] = make_float4(d0 > 0.f ? gs : (d0 < 0.f ? -gs : 0.f), d1 > 0.f ? gs : (d1 < 0.f ? -gs : 0.f),
+                         d2 > 0.f ? gs : (d2 < 0.f ? -gs : 0.f), d3 > 0.f ? gs : (d3 < 0.f ? -gs : 0.f));
+    }
+  }
+  sum *= w;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) tot += double(part[k]);
+    atomicAdd(a.acc + (up ? 0 : 1), tot);
+  }
+}
+__global__ void l1_finalize_kernel(const double* acc, float* loss, double inv_nu, double inv_ns) {
+  loss[0] = float(acc[0] * inv_nu + 0.25 * acc[1] * inv_ns);
+}
+
+// ---------------------------------------------------------------------------------------
 // dst[r][0..kd) = cast(src[r][0..ks)), zero for columns ks..kd (K padding of conv_surface)
 template <bool kFp16>
 __global__ void cast16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int rows, int ks, int kd) {

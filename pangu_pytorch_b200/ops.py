@@ -20,7 +20,7 @@ _LAUNCHES = [0]          # kernels launched through this module (bench.py report
 _KERNELS_PER_CALL = {
     "pangu_cast16": 1, "pangu_to_window16": 1, "pangu_patch_embed": 3, "pangu_qkv": 1,
     "pangu_window_attention": 1, "pangu_proj_ln_residual": 1, "pangu_mlp_ln_residual": 2,
-    "pangu_downsample": 2, "pangu_upsample": 2, "pangu_patch_recover": 2, "pangu_linear": 1, "pangu_denorm_fields": 1,
+    "pangu_downsample": 2, "pangu_upsample": 2, "pangu_patch_recover": 2, "pangu_linear": 1, "pangu_denorm_fields": 1, "pangu_l1_loss": 2,
 }
 
 
@@ -188,3 +188,27 @@ def denorm_fields(upper, surface, s_mean, s_std, u_mean, u_std) -> None:
     lat, lon = surface.shape[-2], surface.shape[-1]
     _call("pangu_denorm_fields", _p(upper, f, "upper"), _p(surface, f, "surface"), _p(s_mean, f), _p(s_std, f),
           _p(u_mean, f), _p(u_std, f), lat, lon, _stream())
+
+
+UPPER_WEIGHTS = (3.00, 0.60, 1.50, 0.77, 0.54)      # era5_data/config.py:45
+SURFACE_WEIGHTS = (1.50, 0.77, 0.66, 3.00)          # era5_data/config.py:46
+
+
+def l1_loss(out_upper, out_surface, tgt_upper, tgt_surface, s_mean, s_std, u_mean, u_std, want_grad: bool = False,
+            upper_weights=UPPER_WEIGHTS, surface_weights=SURFACE_WEIGHTS):
+    """Weighted L1 training loss of the reference (targets in physical units, normalised inside).
+    Returns (loss[1] device tensor, grad_upper | None, grad_surface | None)."""
+    import ctypes
+    f = torch.float32
+    dev = out_upper.device
+    lat, lon = out_surface.shape[-2], out_surface.shape[-1]
+    loss = torch.empty(1, dtype=f, device=dev)
+    acc = torch.empty(2, dtype=torch.float64, device=dev)
+    gu = torch.empty_like(out_upper) if want_grad else None
+    gs = torch.empty_like(out_surface) if want_grad else None
+    wu = (ctypes.c_float * 5)(*upper_weights)
+    ws = (ctypes.c_float * 4)(*surface_weights)
+    _call("pangu_l1_loss", _p(out_upper, f), _p(out_surface, f), _p(tgt_upper, f), _p(tgt_surface, f), _p(s_mean, f),
+          _p(s_std, f), _p(u_mean, f), _p(u_std, f), ctypes.cast(wu, c_void_p), ctypes.cast(ws, c_void_p), _p(loss, f),
+          _p(acc, torch.float64), _p(gu, f), _p(gs, f), lat, lon, _stream())
+    return loss, gu, gs

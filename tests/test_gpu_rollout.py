@@ -75,3 +75,28 @@ def test_ensemble_members_are_independent_and_sharded():
     assert sorted(whole) == sorted(parts) == [0, 1, 2, 3]
     assert all(whole[k] == parts[k] for k in whole)           # bit-identical regardless of sharding
     assert len({whole[k] for k in whole}) == 4                # perturbations differ
+
+
+def test_weighted_l1_loss_and_output_gradient():
+    """models/pangu_sample.py:57-67 on the GPU vs the oracle (and autograd of the oracle for dL/d out)."""
+    from pangu_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    lat, lon = 721, 96
+    ou, os_ = torch.randn(1, 5, 13, lat, lon, generator=g), torch.randn(1, 4, lat, lon, generator=g)
+    stats = (torch.randn(4, generator=g), 0.5 + torch.rand(4, generator=g),
+             torch.randn(13, 1, 1, 5, generator=g), 0.5 + torch.rand(13, 1, 1, 5, generator=g))
+    ostats = O.output_statistics(stats)
+    tu_n, ts_n = torch.randn(1, 5, 13, lat, lon, generator=g), torch.randn(1, 4, lat, lon, generator=g)
+    tu, ts = O.norm_back_data(tu_n, ts_n, ostats)                       # physical-unit targets
+    ou_r, os_r = ou.clone().requires_grad_(True), os_.clone().requires_grad_(True)
+    ref = O.weighted_l1_loss(ou_r, os_r, *O.norm_data(tu, ts, ostats))
+    ref.backward()
+    d = lambda t: t.to(DEV).contiguous()
+    loss, gu, gs = ops.l1_loss(d(ou), d(os_), d(tu), d(ts), d(stats[0]), d(stats[1]), d(stats[2].reshape(13, 5)),
+                               d(stats[3].reshape(13, 5)), want_grad=True)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref)) < 2e-6 * abs(float(ref))
+    # gradient: sign(o - t) * w / N; compare where |o - t| is not at the fp32 noise floor
+    for got, want, o, t in ((gu, ou_r.grad, ou, O.norm_data(tu, ts, ostats)[0]), (gs, os_r.grad, os_, O.norm_data(tu, ts, ostats)[1])):
+        mask = (o - t).abs() > 1e-4
+        assert torch.allclose(got.cpu()[mask], want[mask], rtol=1e-5, atol=0)

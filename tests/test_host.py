@@ -133,3 +133,46 @@ def test_device_index_maps_bit_exact_on_host(tmp_path, H, W, roll):
             h, w = 2 * h2 + grp // 2, 2 * w2 + grp % 2
             want = np.where(h >= H, -1, (z * H + h) * W + w)
             assert np.array_equal(up[grp * T2:(grp + 1) * T2], want)
+
+
+def test_lora_merge_matches_restated_peft_semantics():
+    """finetune/lora_tune.py:124-139 (peft, third party): y = Wx + b + (alpha/r) B(Ax); merged weights
+    reproduce it, modules_to_save replace the frozen originals, result is a strict 223-key state_dict."""
+    from pangu_pytorch_b200.lora import merge_lora_state_dict
+    g = torch.Generator().manual_seed(4)
+    base = {"upsample.linear1.weight": torch.randn(768, 384, generator=g) * 0.02,
+            "upsample.norm.weight": torch.ones(192),
+            "layers.EarthSpecificLayer0.blocks.EarthSpecificBlock0.linear.linear1.weight": torch.randn(768, 192, generator=g) * 0.02,
+            "layers.EarthSpecificLayer0.blocks.EarthSpecificBlock0.linear.linear1.bias": torch.randn(768, generator=g),
+            "_output_layer.conv.weight": torch.randn(160, 384, 1, generator=g)}
+    peft = {}
+    adapters = {}
+    for k, v in base.items():
+        mod, leaf = k.rsplit(".", 1)
+        if leaf == "weight" and v.ndim == 2:
+            peft[f"base_model.model.{mod}.base_layer.weight"] = v
+            a, b = torch.randn(16, v.shape[1], generator=g) * 0.1, torch.randn(v.shape[0], 16, generator=g) * 0.1
+            adapters[mod] = (a, b)
+            peft[f"base_model.model.{mod}.lora_A.default.weight"] = a
+            peft[f"base_model.model.{mod}.lora_B.default.weight"] = b
+        elif mod == "_output_layer.conv":
+            peft[f"base_model.model.{mod}.original_module.weight"] = v
+            peft[f"base_model.model.{mod}.modules_to_save.default.weight"] = v + 1.0
+        elif k.endswith("linear1.bias"):
+            peft[f"base_model.model.{mod}.base_layer.bias"] = v
+        else:
+            peft[f"base_model.model.{k}"] = v
+    merged = merge_lora_state_dict(peft, lora_alpha=16.0)
+    assert sorted(merged) == sorted(base)
+    assert torch.equal(merged["_output_layer.conv.weight"], base["_output_layer.conv.weight"] + 1.0)
+    assert torch.equal(merged["upsample.norm.weight"], base["upsample.norm.weight"])
+    mod = "layers.EarthSpecificLayer0.blocks.EarthSpecificBlock0.linear.linear1"
+    x = torch.randn(7, 192, generator=g)
+    a, b = adapters[mod]
+    want = O.lora_linear(x, base[mod + ".weight"], base[mod + ".bias"], a, b, alpha=16.0, r=16)
+    got = torch.nn.functional.linear(x, merged[mod + ".weight"], merged[mod + ".bias"])
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+    with pytest.raises(ValueError):
+        bad = dict(peft)
+        bad.pop(f"base_model.model.{mod}.lora_B.default.weight")
+        merge_lora_state_dict(bad)
