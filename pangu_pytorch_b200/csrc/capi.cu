@@ -114,6 +114,7 @@ struct CfgBase {
   static constexpr int CH = 32;
   static constexpr bool TMA16 = false;   // 16-bit row-major output written with TMA bulk stores
   static constexpr int CLUSTER = 1;      // 2: CTA pairs share every weight (B) tile by TMA multicast
+  static constexpr bool NSPLIT = false;  // CTA pair splits the LayerNorm row (N) instead of M; stats via DSMEM
 };
 struct CfgQKV : CfgBase {      // linear1 of attention: bias, q-scale, 16-bit out
   static constexpr int BN = 192, UN = 192, STAGES = 4;
@@ -130,10 +131,11 @@ struct CfgLNRes192 : CfgBase { // bias + LayerNorm(192) + residual, fp32 + 16-bi
   static constexpr bool LN = true, RESID = true, OUT32 = true, OUT16 = true;
   static constexpr int CLUSTER = 2;
 };
-struct CfgLNRes384 : CfgBase { // bias + LayerNorm(384) + residual
-  static constexpr int BN = 384, UN = 192, STAGES = 3, CH = 16;
+struct CfgLNRes384 : CfgBase { // bias + LayerNorm(384) + residual: a CTA pair, 192 columns each, stats over DSMEM
+  static constexpr int BN = 192, UN = 192, STAGES = 4;
   static constexpr bool LN = true, RESID = true, OUT32 = true, OUT16 = true;
   static constexpr int CLUSTER = 2;
+  static constexpr bool NSPLIT = true;
 };
 struct CfgPlain192 : CfgBase { // (bias) -> fp32 + 16-bit (embed, downsample.linear, upsample.linear2, tests)
   static constexpr int BN = 192, UN = 192, STAGES = 4;
@@ -164,12 +166,13 @@ template <class Cfg, bool kFp16>
 static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t stream) {
   using T = GemmTraits<Cfg>;
   PG_REQUIRE(o.N % Cfg::BN == 0, "N=%d not a multiple of the %d-column tile", o.N, Cfg::BN);
+  PG_REQUIRE(!Cfg::NSPLIT || (o.N == 2 * Cfg::BN && o.k2 == 0), "NSPLIT GEMM needs N == 2 * BN");
   PG_REQUIRE(o.k1 % 64 == 0 && o.k2 % 64 == 0 && o.k1 > 0, "K (%d + %d) must be multiples of 64", o.k1, o.k2);
   PG_REQUIRE(o.M > 0, "empty M");
   CUtensorMap ma, ma2, mb;
-  PG_TRY(make_map(&ma, o.a, o.M, o.k1, o.a_pitch, BLOCK_M));
+  PG_TRY(make_map(&ma, o.a, o.M, o.k1, o.a_pitch, Cfg::NSPLIT ? 64 : BLOCK_M));
   if (o.k2 > 0) PG_TRY(make_map(&ma2, o.a2, o.M, o.k2, o.a2_pitch, BLOCK_M)); else ma2 = ma;
-  PG_TRY(make_map(&mb, o.b, o.N, o.k1 + o.k2, o.b_pitch, Cfg::CLUSTER == 2 ? Cfg::BN / 2 : Cfg::UN));
+  PG_TRY(make_map(&mb, o.b, o.N, o.k1 + o.k2, o.b_pitch, (Cfg::CLUSTER == 2 && !Cfg::NSPLIT) ? Cfg::BN / 2 : Cfg::UN));
   CUtensorMap mo = ma;
   if constexpr (Cfg::TMA16) {
     PG_REQUIRE(ep.rowmap == RM_IDENT && ep.dstmap == DM_IDENT && ep.row_base == 0 && ep.out16 != nullptr,
@@ -189,7 +192,7 @@ static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t 
     attr_done = true;
   }
   constexpr int CL = Cfg::CLUSTER;
-  const int units = ((sh.num_m_blocks + CL - 1) / CL) * sh.num_n_blocks;
+  const int units = Cfg::NSPLIT ? sh.num_m_blocks : ((sh.num_m_blocks + CL - 1) / CL) * sh.num_n_blocks;
   const int max_units = g_num_sms / CL;
   const int grid = (units < max_units ? units : max_units) * CL;
   cudaLaunchConfig_t cfg;

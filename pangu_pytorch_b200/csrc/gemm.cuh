@@ -67,6 +67,7 @@ struct GemmTraits {
   static constexpr int CH = Cfg::CH;                 // epilogue chunk (columns)
   static constexpr int STAGES = Cfg::STAGES;
   static constexpr int CL = Cfg::CLUSTER;            // CTAs per cluster sharing each B tile by TMA multicast
+  static constexpr bool NSPLIT = Cfg::NSPLIT;        // cluster pair splits the N (LayerNorm) dimension instead of M
   static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS_RAW = ACC_STAGES * BN;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
@@ -80,10 +81,11 @@ struct GemmTraits {
   static constexpr int PAR_BYTES = 3 * BN * 4;       // bias / gamma / beta (shared by the 8 epilogue warps)
   static constexpr int TAB_BYTES = 8 * 64 * 4;       // per warp: row -> token, row -> 16-bit destination row
   static constexpr int EPI_BYTES = ((8 * SLAB_BYTES + PAR_BYTES + TAB_BYTES + 1023) / 1024) * 1024;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 256 + (Cfg::NSPLIT ? 2 * 128 * 16 : 0);   // + LN partial-stat mailboxes
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
   static_assert(BN % UN == 0 && UN % 16 == 0 && UN <= 256, "bad N tiling");
   static_assert(CL == 1 || (CL == 2 && (BN / 2) % 8 == 0 && BN / 2 <= 256), "bad cluster B split");
+  static_assert(!NSPLIT || (CL == 2 && Cfg::LN && NUM_B == 1), "NSPLIT: LayerNorm row split over a CTA pair");
   static_assert(BN % CH == 0 && (CH == 16 || CH == 32), "bad epilogue chunk");
   static_assert(!Cfg::TMA16 || BN % 64 == 0, "TMA16: both warpgroups take whole 32-column chunks");
   static_assert(!Cfg::TMA16 || (CH == 32 && !Cfg::LN && !Cfg::OUT32 && Cfg::RECOVER == 0), "TMA16: plain 16-bit output");
@@ -113,6 +115,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull_bar = bars + 2 * T::STAGES;      // [ACC_STAGES]
   uint64_t* tempty_bar = tfull_bar + T::ACC_STAGES;  // [ACC_STAGES]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + T::ACC_STAGES);
+  // NSPLIT: LayerNorm partial statistics of the peer CTA arrive here (one float4 per row and accumulator stage)
+  [[maybe_unused]] uint64_t* xfull_bar = bars + 24;     // [2] 128 remote arrivals (peer's row owners)
+  [[maybe_unused]] uint64_t* xempty_bar = bars + 26;    // [2] 256 remote arrivals (peer's readers)
+  [[maybe_unused]] float4* xch = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,7 +127,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int CL = T::CL;
   const int cta_rank = CL == 1 ? 0 : int(cluster_ctarank());
   const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
-  const int num_units = ((shape.num_m_blocks + CL - 1) / CL) * shape.num_n_blocks;
+  // NSPLIT: both CTAs of the pair take the SAME m-block and one half of the LayerNorm row each (n = rank)
+  const int num_units = T::NSPLIT ? shape.num_m_blocks : ((shape.num_m_blocks + CL - 1) / CL) * shape.num_n_blocks;
+  auto unit_m = [&](int unit) { return T::NSPLIT ? unit : (unit / shape.num_n_blocks) * CL + cta_rank; };
+  auto unit_n = [&](int unit) { return T::NSPLIT ? cta_rank : unit % shape.num_n_blocks; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -135,6 +144,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int a = 0; a < T::ACC_STAGES; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], kEpiThreads);
+      if constexpr (T::NSPLIT) { mbar_init(&xfull_bar[a], 128); mbar_init(&xempty_bar[a], kEpiThreads); }
     }
     fence_barrier_init();
   }
@@ -150,12 +160,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = unit0; unit < num_units; unit += unit_stride) {
-        const int m_blk = (unit / shape.num_n_blocks) * CL + cta_rank, n_blk = unit % shape.num_n_blocks;
+        const int m_blk = unit_m(unit), n_blk = unit_n(unit);
         for (int kb = 0; kb < shape.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + stage * T::STAGE_BYTES;
           uint8_t* sb = sa + T::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], T::STAGE_BYTES);
+          if constexpr (T::NSPLIT) {
+            // the pair shares the A tile: each CTA fetches 64 of its 128 rows and multicasts them;
+            // the weight slice (this CTA's half of the output columns) is private
+            tma_load_2d_mcast(&tmA, &full_bar[stage], sa + cta_rank * 64 * 128, kb * BLOCK_K, m_blk * BLOCK_M + cta_rank * 64,
+                              uint16_t(3), kEvictFirst);
+            tma_load_2d_hint(&tmB, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BN, kEvictLast);
+          } else {
           if (kb < shape.k_split)
             tma_load_2d(&tmA, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
           else
@@ -169,6 +186,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             constexpr int SL = BN / CL;
             tma_load_2d_mcast(&tmB, &full_bar[stage], sb + cta_rank * SL * 128, kb * BLOCK_K, n_blk * BN + cta_rank * SL,
                               uint16_t((1 << CL) - 1), kEvictLast);
+          }
           }
           if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -229,13 +247,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int loaded_n_blk = -1;
     [[maybe_unused]] int sbuf = 0;   // TMA16: slab parity, alternates across chunks AND tiles
     for (int unit = unit0; unit < num_units; unit += unit_stride) {
-      const int m_blk = (unit / shape.num_n_blocks) * CL + cta_rank, n_blk = unit % shape.num_n_blocks;
+      const int m_blk = unit_m(unit), n_blk = unit_n(unit);
       // ---- epilogue parameters of this n-block (uniform decision across the 8 warps; LN kernels: once)
       if (loaded_n_blk != n_blk) {
         named_bar_sync(1, kEpiThreads);
         for (int c = threadIdx.x - 64; c < BN; c += kEpiThreads) {
           s_bias[c] = ep.bias ? ep.bias[n_blk * BN + c] : 0.f;
-          if constexpr (Cfg::LN) { s_gamma[c] = ep.gamma[c]; s_beta[c] = ep.beta[c]; }
+          if constexpr (Cfg::LN) {
+            const int gc = (T::NSPLIT ? n_blk * BN : 0) + c;     // LN affine is indexed by the row position
+            s_gamma[c] = ep.gamma[gc]; s_beta[c] = ep.beta[gc];
+          }
         }
         named_bar_sync(1, kEpiThreads);
         loaded_n_blk = n_blk;
@@ -367,11 +388,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float s1a, s1b, s2a, s2b;
         unpack2(s1, s1a, s1b);
         unpack2(s2, s2a, s2b);
+        if constexpr (T::NSPLIT) {
+          // exchange (sum, sum of squares, shift) of this half row with the peer CTA through DSMEM
+          const float my1 = s1a + s1b, my2 = s2a + s2b;
+          const uint32_t peer = uint32_t(cta_rank ^ 1);
+          if (half == 0) {
+            mbar_wait_cluster(&xempty_bar[acc], acc_phase ^ 1);  // peer has consumed my previous message in this slot
+            st_cluster_f4(mapa_u32(smem_u32(&xch[acc * 128 + quad * 32 + lane]), peer), my1, my2, shift, 0.f);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&xfull_bar[acc]), peer));
+          }
+          mbar_wait_cluster(&xfull_bar[acc], acc_phase);
+          const float4 o = xch[acc * 128 + quad * 32 + lane];
+          mbar_arrive_cluster(mapa_u32(smem_u32(&xempty_bar[acc]), peer));
+          const float n = float(BN), inv_n2 = 1.0f / float(2 * BN);
+          const float mu = (my1 + n * shift + o.x + n * o.z) * inv_n2;
+          const float d0 = shift - mu, d1 = o.z - mu;
+          const float m2 = (my2 + 2.f * d0 * my1 + n * d0 * d0) + (o.y + 2.f * d1 * o.x + n * d1 * d1);
+          mean = mu;
+          rstd = rsqrtf(fmaxf(m2 * inv_n2, 0.f) + ep.eps);
+        } else {
         const float inv_n = 1.0f / float(BN);
         const float m = (s1a + s1b) * inv_n;
         const float var = fmaxf((s2a + s2b) * inv_n - m * m, 0.f);
         mean = shift + m;
         rstd = rsqrtf(var + ep.eps);
+        }
       }
       // y = ((acc + bias) - mean) * rstd * gamma + beta  ==  (acc + bias) * a + b  then * gamma + beta
       const f32x2 ln_a = pack2(rstd, rstd), ln_b = pack2(-mean * rstd, -mean * rstd);
