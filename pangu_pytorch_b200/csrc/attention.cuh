@@ -32,7 +32,8 @@ struct AttnArgs {
   void* out;           // [nLon*types*144][C] 16-bit, window order, channel = head*32 + d
   int C, heads, types, nLon, nH;
   int roll;            // add the shifted-window mask
-  int lon_per_cta;     // longitude windows walked by one CTA
+  int lon_per_cta;     // (mma.sync v1 kernel) longitude windows walked by one CTA
+  int plane_rows;      // (tcgen05 kernel) rows per (q|k|v, head) plane of the head-major qkv buffer
   int debug;           // development only: bit0 skip tail math, bit1 skip softmax math, bit2 skip stores
   long long* trace;    // development only: per-role clock64 timeline of CTA (0,0), [role 8][window 32][event 4]
 };

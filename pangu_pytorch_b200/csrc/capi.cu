@@ -115,10 +115,11 @@ struct CfgBase {
   static constexpr bool TMA16 = false;   // 16-bit row-major output written with TMA bulk stores
   static constexpr int CLUSTER = 1;      // 2: CTA pairs share every weight (B) tile by TMA multicast
   static constexpr bool NSPLIT = false;  // CTA pair splits the LayerNorm row (N) instead of M; stats via DSMEM
+  static constexpr bool HEADMAJOR = false;  // TMA16: output stored as [N/32 planes][plane_rows][32]
 };
 struct CfgQKV : CfgBase {      // linear1 of attention: bias, q-scale, 16-bit out
   static constexpr int BN = 192, UN = 192, STAGES = 4;
-  static constexpr bool SCALEQ = true, OUT16 = true, TMA16 = true;
+  static constexpr bool SCALEQ = true, OUT16 = true, TMA16 = true, HEADMAJOR = true;
   static constexpr int CLUSTER = 2;
 };
 struct CfgMLP1 : CfgBase {     // Mlp.linear1: bias + exact GELU, 16-bit out
@@ -162,6 +163,8 @@ struct GemmOperands {
   int M, N;
 };
 
+static inline int sh_rows_padded(int M) { return (M + BLOCK_M - 1) / BLOCK_M * BLOCK_M; }
+
 template <class Cfg, bool kFp16>
 static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t stream) {
   using T = GemmTraits<Cfg>;
@@ -177,7 +180,12 @@ static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t 
   if constexpr (Cfg::TMA16) {
     PG_REQUIRE(ep.rowmap == RM_IDENT && ep.dstmap == DM_IDENT && ep.row_base == 0 && ep.out16 != nullptr,
                "TMA-store epilogue needs an identity row map");
-    PG_TRY(make_out_map(&mo, ep.out16, o.M, o.N, ep.ld16));
+    if constexpr (Cfg::HEADMAJOR) {
+      PG_REQUIRE(ep.plane_rows >= sh_rows_padded(o.M), "head-major output planes too short");
+      PG_TRY(make_out_map(&mo, ep.out16, uint64_t(o.N / 32) * ep.plane_rows, 32, 32));
+    } else {
+      PG_TRY(make_out_map(&mo, ep.out16, o.M, o.N, ep.ld16));
+    }
   }
   GemmShape sh;
   sh.M = o.M;
@@ -311,6 +319,7 @@ extern "C" int pangu_qkv(const void* x16w, const void* w16, const float* bias, v
   GemmOperands o{x16w, uint64_t(C), nullptr, 0, C, 0, w16, uint64_t(C), Tp, 3 * C};
   EpiArgs ep = epi_defaults();
   ep.bias = bias; ep.out16 = qkv16; ep.ld16 = 3 * C;
+  ep.plane_rows = sh_rows_padded(Tp);    // head-major: [3*heads planes][plane_rows][32]
   ep.q_cols = C; ep.q_scale = 0.17677669529663687f;   // 32^-0.5, models/layers.py:289
   return launch_gemm<CfgQKV>(o, ep, fp16, static_cast<cudaStream_t>(stream));
 }
@@ -323,78 +332,54 @@ extern "C" int pangu_window_attention(const void* qkv16, const float* earth_bias
   AttnArgs a;
   a.qkv = qkv16; a.bias = earth_bias; a.out = att16;
   a.C = C; a.heads = heads; a.types = g.types; a.nLon = g.nLon; a.nH = g.nH; a.roll = roll ? 1 : 0;
-  // split the longitude walk so that the grid is a few waves of the SM count
-  const int base = g.types * heads;
-  int best_split = 1;
-  double best_eff = 0.0;
-  for (int sp = 1; sp <= g.nLon && sp <= 6; ++sp) {
-    const int per = (g.nLon + sp - 1) / sp;
-    const int nsp = (g.nLon + per - 1) / per;
-    const double ctas = double(base) * nsp;
-    const double waves = ctas / g_num_sms;
-    const double full = double(long(waves + 0.999999));
-    // cost model: waves * (per windows + ~4.5 window-times of fixed per-CTA cost: TMEM alloc, bias tile
-    // load, pipeline fill and drain -- measured on B200, see profiles/)
-    const double cost = full * (per + 4.5);
-    const double eff = 1.0 / cost;
-    if (eff > best_eff) { best_eff = eff; best_split = nsp; a.lon_per_cta = per; }
-  }
+  a.lon_per_cta = g.nLon;
   a.debug = 0;
   a.trace = nullptr;
   if (const char* e = getenv("PANGU_B200_ATTN_TRACE")) a.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
-  if (const char* e = getenv("PANGU_B200_ATTN_DEBUG")) a.debug = atoi(e);
-  if (const char* e = getenv("PANGU_B200_ATTN_PER")) {
-    a.lon_per_cta = atoi(e);
-    best_split = (g.nLon + a.lon_per_cta - 1) / a.lon_per_cta;
-  }
+  const int Tp = g.nLon * g.types * 144;
+  a.plane_rows = sh_rows_padded(Tp);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  dim3 grid(base, best_split);
-  static const bool use_mma_sync = getenv("PANGU_B200_ATTN_MMA_SYNC") != nullptr;   // development A/B switch
-  if (!use_mma_sync) {
-    // tcgen05 path: qkv [Tp, 3C] viewed as a 2-D tensor, one 32-column x 144-row box per q/k/v tile
-    const int Tp = g.nLon * g.types * 144;
-    CUtensorMap mq;
-    {
-      PG_REQUIRE((reinterpret_cast<uintptr_t>(qkv16) & 15) == 0, "qkv base not 16 B aligned");
-      cuuint64_t dims[2] = {cuuint64_t(3 * C), cuuint64_t(Tp)};
-      cuuint64_t strides[1] = {cuuint64_t(3 * C) * 2};
-      cuuint32_t box[2] = {32, 144};
-      cuuint32_t estr[2] = {1, 1};
-      CUresult r = g_encode(&mq, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(qkv16), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled(qkv) failed (%d)", int(r));
-    }
-    static bool tc_attr[2] = {false, false};
-    if (fp16) {
-      if (!tc_attr[1]) {
-        PG_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
-        tc_attr[1] = true;
-      }
-      window_attention_tc_kernel<true><<<grid, ATC_THREADS, ATC_SMEM_BYTES, s>>>(mq, a);
-    } else {
-      if (!tc_attr[0]) {
-        PG_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
-        tc_attr[0] = true;
-      }
-      window_attention_tc_kernel<false><<<grid, ATC_THREADS, ATC_SMEM_BYTES, s>>>(mq, a);
-    }
-    PG_CUDA(cudaGetLastError());
-    return 0;
+  PG_REQUIRE((reinterpret_cast<uintptr_t>(qkv16) & 15) == 0 && (reinterpret_cast<uintptr_t>(earth_bias) & 15) == 0,
+             "qkv / bias base not 16 B aligned");
+  // head-major qkv: [3*heads planes][plane_rows][32] viewed as a 2-D tensor of 64 B rows; box = one 144-row tile
+  CUtensorMap mq, mb;
+  {
+    cuuint64_t dims[2] = {32, cuuint64_t(3) * heads * a.plane_rows};
+    cuuint64_t strides[1] = {64};
+    cuuint32_t box[2] = {32, 144};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&mq, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(qkv16), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled(qkv) failed (%d)", int(r));
   }
-  static bool attr_done[2] = {false, false};
+  // earth_specific_bias [types*heads*144 rows][144] fp32; box = 16 key columns x 144 query rows (9216 B)
+  {
+    cuuint64_t dims[2] = {144, cuuint64_t(g.types) * heads * 144};
+    cuuint64_t strides[1] = {144 * 4};
+    cuuint32_t box[2] = {16, 144};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(earth_bias), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled(bias) failed (%d)", int(r));
+  }
+  // persistent: one CTA per SM, each takes an equal contiguous share of the (type, head, lon window) units
+  const long long units = (long long)g.types * heads * g.nLon;
+  const int pgrid = int(units < g_num_sms ? units : g_num_sms);
+  static bool tc_attr[2] = {false, false};
   if (fp16) {
-    if (!attr_done[1]) {
-      PG_CUDA(cudaFuncSetAttribute(window_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-      attr_done[1] = true;
+    if (!tc_attr[1]) {
+      PG_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
+      tc_attr[1] = true;
     }
-    window_attention_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(a);
+    window_attention_tc_kernel<true><<<pgrid, ATC_THREADS, ATC_SMEM_BYTES, s>>>(mq, mb, a);
   } else {
-    if (!attr_done[0]) {
-      PG_CUDA(cudaFuncSetAttribute(window_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-      attr_done[0] = true;
+    if (!tc_attr[0]) {
+      PG_CUDA(cudaFuncSetAttribute(window_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM_BYTES));
+      tc_attr[0] = true;
     }
-    window_attention_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(a);
+    window_attention_tc_kernel<false><<<pgrid, ATC_THREADS, ATC_SMEM_BYTES, s>>>(mq, mb, a);
   }
   PG_CUDA(cudaGetLastError());
   return 0;

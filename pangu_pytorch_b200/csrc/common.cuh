@@ -60,14 +60,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time: never use it to poll two barriers)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > PANGU_SPIN_LIMIT) {
-      printf("pangu_b200: mbarrier timeout block %d thread %d bar %p parity %u\n", (int)blockIdx.x,
-             (int)threadIdx.x, (void*)bar, parity);
-      __trap();
-    }
+    ++spins;
+    if (spins == PANGU_SPIN_LIMIT && (blockIdx.x == 5 || threadIdx.x == 0))      // report, keep spinning so that every stuck role gets to report, then trap
+      printf("pangu_b200: mbarrier timeout block %d thread %d smem 0x%x parity %u\n", (int)blockIdx.x,
+             (int)threadIdx.x, smem_u32(bar), parity);
+    if (spins > PANGU_SPIN_LIMIT + (PANGU_SPIN_LIMIT >> 1)) __trap();
   }
 }
 
@@ -152,6 +164,10 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// bring [p, p + bytes) into L2 without touching shared memory (bytes % 16 == 0)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // L2 eviction-priority descriptors (createpolicy.fractional encodings used by CUTLASS)
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;

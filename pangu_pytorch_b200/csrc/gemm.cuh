@@ -55,6 +55,7 @@ struct EpiArgs {
   float res_scale;      // DropPath factor on the normalised branch (1 in eval)
   float eps;
   int lat, lon;         // RECOVER: output field extents (721, 1440)
+  int plane_rows;       // HEADMAJOR: rows per 32-column plane of the 16-bit output
   int debug;            // development only: bit0 no residual loads, bit1 no stores, bit2 no epilogue math
 };
 
@@ -309,10 +310,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmOut, tile, ncol0, m_blk * BLOCK_M + quad * 32);
-            bulk_commit();
+          if (lane == 0 && m_blk < shape.num_m_blocks) {   // an odd m-block count leaves the pair's last tile out of range
+            if constexpr (Cfg::HEADMAJOR)     // out16 is [N/32 planes][plane_rows][32]: a 32-column chunk is one plane
+              tma_store_2d(&tmOut, tile, 0, (ncol0 >> 5) * ep.plane_rows + m_blk * BLOCK_M + quad * 32);
+            else
+              tma_store_2d(&tmOut, tile, ncol0, m_blk * BLOCK_M + quad * 32);
           }
+          if (lane == 0) bulk_commit();
           sbuf ^= 1;
           if (ci + 1 < NCH) tmem_ld_wait();
         }

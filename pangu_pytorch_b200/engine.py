@@ -7,7 +7,7 @@ HBM layout of one resolution (``GridWorkspace``), T = Z*H*W real tokens, Tp = wi
     x16      [T , C ] 16-bit shadow of x32, natural order   (A operand of Mlp.linear1, ...)
     x16w[r]  [Tp, C ] 16-bit shadow in WINDOW order for roll state r in {0,1}; the +5 latitude
                              pad rows are zeroed once here and never written again
-    qkv      [Tp, 3C] 16-bit window order, q pre-scaled
+    qkv      [3C/32, Tp', 32] 16-bit, one plane per (q|k|v, head), window order rows, q pre-scaled
     att      [Tp, C ] 16-bit window order, heads merged
     hidden   [T , 4C] 16-bit GELU(linear1) activations
 """
@@ -61,7 +61,8 @@ class GridWorkspace:
         self.x32 = torch.empty(T, C, dtype=torch.float32, device=device)
         self.x16 = torch.empty(T, C, dtype=h, device=device)
         self.x16w = [torch.zeros(Tp, C, dtype=h, device=device) for _ in range(2)]
-        self.qkv = torch.empty(Tp, 3 * C, dtype=h, device=device)
+        # head-major: [3*heads planes][Tp rounded up to 128][32] (csrc/attention_tc.cuh)
+        self.qkv = torch.empty(3 * C // 32, (Tp + 127) // 128 * 128, 32, dtype=h, device=device)
         self.att = torch.empty(Tp, C, dtype=h, device=device)
         self.hidden = torch.empty(T, 4 * C, dtype=h, device=device)
 

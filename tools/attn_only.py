@@ -18,27 +18,33 @@ ws.qkv.normal_()
 ebias = torch.randn(1, ws.types, heads, 144, 144, device=dev) * 0.02
 trace = None
 if os.environ.get('ATTN_TRACE'):
-    trace = torch.zeros(8 * 32 * 4, dtype=torch.int64, device=dev)
+    trace = torch.zeros(8 * 64 * 4, dtype=torch.int64).pin_memory()   # host-mapped: readable even after a device trap
     os.environ['PANGU_B200_ATTN_TRACE'] = str(trace.data_ptr())
-for roll in (0, 1):
-    ops.window_attention(ws.qkv, ebias, ws.att, Z, H, W, C, heads, roll, False)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        ops.window_attention(ws.qkv, ebias, ws.att, Z, H, W, C, heads, roll, False)
-    e1.record()
-    torch.cuda.synchronize()
-    print(tag, W, "roll", roll, "ms %.4f" % (e0.elapsed_time(e1) / iters), "mean|out| %.5f" % float(ws.att.float().abs().mean()),
-          "debug", os.environ.get("PANGU_B200_ATTN_DEBUG"), "per", os.environ.get("PANGU_B200_ATTN_PER"), flush=True)
+def run():
+  for roll in (0, 1):
+      ops.window_attention(ws.qkv, ebias, ws.att, Z, H, W, C, heads, roll, False)
+      torch.cuda.synchronize()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      for _ in range(iters):
+          ops.window_attention(ws.qkv, ebias, ws.att, Z, H, W, C, heads, roll, False)
+      e1.record()
+      torch.cuda.synchronize()
+      print(tag, W, "roll", roll, "ms %.4f" % (e0.elapsed_time(e1) / iters), "mean|out| %.5f" % float(ws.att.float().abs().mean()),
+            "debug", os.environ.get("PANGU_B200_ATTN_DEBUG"), "per", os.environ.get("PANGU_B200_ATTN_PER"), flush=True)
+
+try:
+    run()
+except Exception as e:
+    print('FAILED:', str(e)[:100])
 
 if trace is not None:
-    tr = trace.cpu().view(8, 32, 4)
+    tr = trace.view(8, 64, 4)
     t0 = int(tr[tr > 0].min())
     names = {0: "TMA  [slot free]", 1: "MMA  [full, S issued, pfull, oempty]", 2: "TAIL [start, done]",
-             3: "SOFT [enter, sfull, pass1 done, epi done]", 4: "SOFT [pfull arrive]", 5: "MMA2 [PV issued, committed]"}
-    for role in range(6):
+             3: "SOFT [enter, sfull, pass1 done, epi done]", 4: "SOFT [pfull arrive]", 5: "-", 6: "SEG  [start, bias staged, tail-warp0 done, all done]"}
+    for role in range(7):
         print(names[role])
-        for i in range(0, 16):
+        for i in range(0, 64):
             row = [int(x) - t0 if int(x) > 0 else -1 for x in tr[role, i]]
             print("   win %2d: %s" % (i, row))
