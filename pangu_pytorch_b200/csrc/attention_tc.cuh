@@ -29,7 +29,7 @@
 // S of window g+2 is queued right behind PV of window g (the tensor pipe executes in issue order, so PV
 // has read P before the next S overwrites it).  The MMA warp runs converged with warp-uniform operands
 // (only the tcgen05 instructions are elected) and polls "next S" / "next PV" without blocking on either.
-// Warps (512 threads): 0 TMA producer, 1 MMA issuer, 2-7 tail warps (ring stage s belongs to warp 2+s),
+// Warps (512 threads): 0 TMA producer, 1 MMA issuer, 2-7 tail warps (ring stage s belongs to warp 2 + s%6),
 // 8-15 softmax: two warpgroups alternate windows; thread = one full query row (TMEM lane).
 #pragma once
 #include "attention.cuh"
@@ -37,13 +37,13 @@
 namespace pg {
 
 constexpr int ATC_THREADS = 512;
-constexpr int ATC_STAGES = 6;
-constexpr int ATC_TAIL_WARPS = ATC_STAGES;                       // warps 2..7: a tail warp owns one ring stage, so it
-                                                                 // sees every phase of that stage's mbarriers in order
+constexpr int ATC_STAGES = 8;
+constexpr int ATC_TAIL_WARPS = 6;                                // warps 2..7: ring stage s belongs to tail warp 2 + s % 6, so
+                                                                 // every phase of a stage's mbarriers is seen by one warp, in order
 constexpr int ATC_STAGE_BYTES = ATT_BUF_BYTES;                   // 27648: Q, K, V tiles (or 3 bias boxes) of 9216 B
 constexpr int ATC_TB_PITCH = 148;                                // floats per row of the tail bias tile in smem
 constexpr int ATC_TB_BYTES = 16 * ATC_TB_PITCH * 4;              // rows 128..143
-constexpr int ATC_SMEM_BYTES = 1024 + ATC_STAGES * ATC_STAGE_BYTES + ATC_TB_BYTES + 1024;
+constexpr int ATC_SMEM_BYTES = 1024 + ATC_STAGES * ATC_STAGE_BYTES + ATC_TB_BYTES + 512;
 constexpr uint32_t ATC_COL_BIAS = 0, ATC_COL_S = 144, ATC_COL_O = 432;
 static_assert(ATC_SMEM_BYTES <= 232448, "attention shared memory budget");
 static_assert(3 * ATC_STAGE_BYTES == ATT_TOK * ATT_TOK * 4, "a bias tile is exactly three ring slots");
@@ -278,10 +278,10 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         const int r0 = 128 + gq;
         const float* tb0 = s_tbias + gq * ATC_TB_PITCH + 2 * q4;
         const float* tb1 = tb0 + 8 * ATC_TB_PITCH;
-        // this warp owns ring stage warp-2: windows whose slot qb + 3 + i falls on it
-        int i = ((warp - 2) - (qb + 3) % ATC_STAGES + ATC_STAGES) % ATC_STAGES;
-        for (; i < nwin; i += ATC_STAGES) {
-          const int g = gbase + i, q = qb + 3 + i, st = warp - 2;
+        // this warp owns the ring stages s with s % 6 == warp - 2: it takes the windows whose slot falls on them
+        for (int i = 0; i < nwin; ++i) {
+          const int g = gbase + i, q = qb + 3 + i, st = q % ATC_STAGES;
+          if (st % ATC_TAIL_WARPS != warp - 2) continue;
           mbar_wait(&full_bar[st], (q / ATC_STAGES) & 1);
           uint8_t* tile = ring + st * ATC_STAGE_BYTES;
           if (lane == 0) TR(2, g, 0);
@@ -425,6 +425,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         for (int i = (wg - gbase % 2 + 2) % 2; i < nwin; i += 2) {
           const int g = gbase + i;
           if (r == 0) TR(3, g, 0);
+          // ---- output of this warpgroup's previous window: its PV is queued right ahead of this window's S
+          if (last >= 0) epilogue(last, l_prev);
+          if (r == 0) TR(3, g, 3);
           mbar_wait(&sfull_bar[wg], (g >> 1) & 1);
           if (r == 0) TR(3, g, 1);
           tc_fence_after();
@@ -458,9 +461,6 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             }
           }
           if (r == 0) TR(3, g, 2);
-          // ---- output of this warpgroup's previous window (its PV finished long ago)
-          if (last >= 0) epilogue(last, l_prev);
-          if (r == 0) TR(3, g, 3);
           // ---- pass 2: P = exp2(y - max), packed 16-bit, written over the first 72 columns of y
           const f32x2 negm2 = pack2(-pm, -pm);
           f32x2 lsum = pack2(0.f, 0.f);

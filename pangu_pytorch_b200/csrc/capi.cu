@@ -12,6 +12,7 @@
 #include "attention_tc.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "mlp_fused.cuh"
 
 using namespace pg;
 
@@ -225,6 +226,40 @@ static int launch_gemm(const GemmOperands& o, const EpiArgs& ep, int fp16, cudaS
   return fp16 ? launch_gemm_t<Cfg, true>(o, ep, s) : launch_gemm_t<Cfg, false>(o, ep, s);
 }
 
+template <int C, bool kFp16>
+static int launch_mlp_fused_t(const void* x16_in, const void* w1_16, const void* w2_16, const MlpArgs& a, cudaStream_t stream) {
+  using T = MlpTraits<C>;
+  CUtensorMap mx, m1, m2;
+  PG_TRY(make_map(&mx, x16_in, a.T, C, C, 128));
+  PG_TRY(make_map(&m1, w1_16, 4 * C, C, C, 32));          // W1 [4C, C]: a CTA fetches 32 of a chunk's 64 hidden rows
+  PG_TRY(make_map(&m2, w2_16, C, 4 * C, 4 * C, 96));      // W2 [C, 4C]: a CTA fetches 96 of a half's 192 output rows
+  auto kern = mlp_fused_kernel<C, kFp16>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int units = (a.num_tiles + 1) / 2;
+  const int max_pairs = g_num_sms / 2;
+  const int pairs = units < max_pairs ? units : max_pairs;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(MF_THREADS);
+  cfg.dynamicSmemBytes = T::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PG_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, m1, m2, a));
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static EpiArgs epi_defaults() {
   EpiArgs e;
   memset(&e, 0, sizeof(e));
@@ -411,6 +446,19 @@ extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, cons
   PG_TRY(check_grid(Z, H, W, C, 0));
   const int T = Z * H * W;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static const bool unfused = getenv("PANGU_B200_MLP_UNFUSED") != nullptr;     // development A/B switch
+  if (!unfused) {
+    // one kernel: the hidden activation stays in tensor memory (ws_hidden is not touched)
+    MlpArgs a;
+    a.b1 = b1; a.b2 = b2; a.gamma = gamma; a.beta = beta;
+    a.x32 = x32; a.out16 = x16_out;
+    a.T = T; a.num_tiles = (T + 127) / 128;
+    a.Z = Z; a.H = H; a.W = W;
+    a.roll_out = roll_out < 0 ? -1 : (roll_out > 0 ? 1 : 0);
+    a.res_scale = res_scale; a.eps = 1e-5f;
+    if (C == 192) return fp16 ? launch_mlp_fused_t<192, true>(x16_in, w1_16, w2_16, a, s) : launch_mlp_fused_t<192, false>(x16_in, w1_16, w2_16, a, s);
+    return fp16 ? launch_mlp_fused_t<384, true>(x16_in, w1_16, w2_16, a, s) : launch_mlp_fused_t<384, false>(x16_in, w1_16, w2_16, a, s);
+  }
   {
     GemmOperands o{x16_in, uint64_t(C), nullptr, 0, C, 0, w1_16, uint64_t(C), T, 4 * C};
     EpiArgs ep = epi_defaults();

@@ -1,0 +1,423 @@
+// Fused Mlp + LayerNorm + residual of one EarthSpecificBlock (reference models/layers.py:250-251, 264-270):
+//
+//     x <- x + s * LN2( GELU(x16 W1^T + b1) W2^T + b2 )
+//
+// in ONE persistent tcgen05 kernel: the 4C-wide hidden activation never leaves the SM.
+// Per 128-token tile (one CTA; CTA pairs share every weight tile by TMA multicast):
+//
+//   X tile [128 x C] 16-bit          TMA -> smem (resident for the tile, K-slab granular reuse)
+//   for each hidden chunk c of 64 units:
+//     GEMM1  Hacc[128x64]  = X W1[c]^T            tcgen05.mma SS, fp32 accumulators in TMEM (2 buffers)
+//     GELU   H = gelu_erf(Hacc + b1[c]) -> 16-bit, written back INTO TMEM over its own accumulator
+//     GEMM2  Y[128xC]     += H W2[:, c]^T         tcgen05.mma with A = H from TMEM, B = W2 slab from smem
+//   epilogue: Y + b2 -> LayerNorm (thread = row) -> * s + residual -> fp32 stream (in place) and 16-bit
+//             shadow (natural order, or scattered to window order for the next block's QKV GEMM)
+//
+// The MMA warp issues  G1(c+NB-1), G2(c)  alternately (NB = Hacc buffers), so the tensor pipe always has
+// GEMM1 work queued while the GELU warps are busy; the tensor pipe executes in issue order, which is what
+// makes the in-place reuse of the Hacc buffers safe (G2(c) has read H(c) before G1(c+NB) overwrites it).
+// TMEM: Y [0,C) then NB Hacc buffers of 64 columns (C=192: 4 buffers, C=384: 2).
+// Warps (448 threads): 0 TMA producer, 1 MMA issuer, 2-5 LayerNorm epilogue (one per TMEM lane quadrant),
+// 6-13 GELU (two warpgroups alternate chunks).
+#pragma once
+#include "common.cuh"
+#include "geometry.cuh"
+#include "gemm.cuh"
+
+namespace pg {
+
+constexpr int MF_THREADS = 448;
+
+template <int C>
+struct MlpTraits {
+  static constexpr int KX = C / 64;                    // K slabs of X (GEMM1)
+  static constexpr int NH = C / 192;                   // 192-column halves of Y (GEMM2 N per instruction)
+  static constexpr int NCH = 4 * C / 64;               // hidden chunks of 64 units
+  static constexpr int COL_H = C;                      // Hacc buffers follow the Y accumulator in TMEM
+  static constexpr int NB = (C == 192) ? 4 : 2;        // Hacc buffers of 64 columns: GEMM1 runs NB-1 chunks ahead of GEMM2
+  static_assert(C + NB * 64 <= 512 && NCH % NB == 0, "TMEM budget / buffer rotation");
+  static constexpr int S1 = (C == 192) ? 8 : 6;        // ring 1: W1 units [64 hidden x 64 k]  = 8 KB
+  static constexpr int S2 = (C == 192) ? 3 : 2;        // ring 2: W2 units [192 out x 64 k]   = 24 KB
+  static constexpr int X_BYTES = KX * 16384;
+  static constexpr int R1_UNIT = 8192, R2_UNIT = 24576;
+  static constexpr int STG_PITCH = 32 * 4 + 16;        // epilogue slab row pitch (bytes), conflict-free 16 B rows
+  static constexpr int SLAB_BYTES = 32 * STG_PITCH;    // 4608 per epilogue warp
+  static constexpr int OFF_R1 = X_BYTES;
+  static constexpr int OFF_R2 = OFF_R1 + S1 * R1_UNIT;
+  static constexpr int OFF_SLAB = OFF_R2 + S2 * R2_UNIT;
+  static constexpr int OFF_PAR = OFF_SLAB + 4 * SLAB_BYTES;       // b1 [4C], b2 / gamma / beta [C] fp32
+  static constexpr int OFF_TAB = OFF_PAR + 7 * C * 4;             // 4 warps x 64 ints
+  static constexpr int OFF_BAR = OFF_TAB + 4 * 64 * 4;
+  static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + 2 * NB + 2;
+  static constexpr int SMEM_BYTES = 1024 + OFF_BAR + ((NUM_BARS * 8 + 16 + 127) / 128) * 128;
+  static_assert(C == 192 || C == 384, "Pangu widths");
+  static_assert(OFF_R1 % 1024 == 0 && OFF_R2 % 1024 == 0 && OFF_SLAB % 512 == 0, "operand alignment");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+struct MlpArgs {
+  const float* b1;      // [4C]
+  const float* b2;      // [C]
+  const float* gamma;   // LayerNorm weight [C]
+  const float* beta;    // LayerNorm bias [C]
+  float* x32;           // residual stream [T, C], updated in place
+  void* out16;          // 16-bit shadow of the new x32
+  int T;                // tokens
+  int num_tiles;        // ceil(T / 128)
+  int Z, H, W;          // token grid (window scatter)
+  int roll_out;         // < 0: out16 in natural order, else window order of that roll state
+  float res_scale;      // DropPath factor (1 in eval)
+  float eps;
+};
+
+// D[tmem] (+)= A[tmem, 16-bit packed] * B[smem]
+__device__ __forceinline__ void umma_f16_ts_(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32_(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait_() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int C, bool kFp16>
+__global__ void __launch_bounds__(MF_THREADS, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const MlpArgs a) {
+  using T = MlpTraits<C>;
+  constexpr int KX = T::KX, NH = T::NH, NCH = T::NCH, S1 = T::S1, S2 = T::S2, NB = T::NB;
+  extern __shared__ uint8_t mf_raw[];
+  uint8_t* smem = mf_raw + ((1024u - (smem_u32(mf_raw) & 1023u)) & 1023u);
+  uint8_t* xs = smem;                          // X tile: KX slabs [128 rows][128 B], SWIZZLE_128B
+  uint8_t* r1 = smem + T::OFF_R1;              // W1 units
+  uint8_t* r2 = smem + T::OFF_R2;              // W2 units
+  float* s_b1 = reinterpret_cast<float*>(smem + T::OFF_PAR);
+  float* s_b2 = s_b1 + 4 * C;
+  float* s_gamma = s_b2 + C;
+  float* s_beta = s_gamma + C;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T::OFF_BAR);
+  uint64_t* xfull = bars;                      // [KX]  X slab landed
+  uint64_t* xempty = xfull + KX;               // [KX]  X slab no longer read by GEMM1 of this tile
+  uint64_t* r1full = xempty + KX;              // [S1]
+  uint64_t* r1empty = r1full + S1;             // [S1]  count 2: tcgen05.commit of both CTAs of the pair
+  uint64_t* r2full = r1empty + S1;             // [S2]
+  uint64_t* r2empty = r2full + S2;             // [S2]  count 2
+  uint64_t* hfull = r2empty + S2;              // [NB]  Hacc ready (GEMM1 done)
+  uint64_t* hready = hfull + NB;               // [NB]  H (16-bit) written back by 128 GELU threads
+  uint64_t* yfull = hready + NB;               // [1]   Y complete
+  uint64_t* yempty = yfull + 1;                // [1]   Y drained by the 128 epilogue threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yempty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta_rank = int(cluster_ctarank());
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_units = (a.num_tiles + 1) >> 1;        // a unit = two consecutive tiles, one per CTA of the pair
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    for (int k = 0; k < KX; ++k) { mbar_init(&xfull[k], 1); mbar_init(&xempty[k], 1); }
+    for (int s = 0; s < S1; ++s) { mbar_init(&r1full[s], 1); mbar_init(&r1empty[s], 2); }
+    for (int s = 0; s < S2; ++s) { mbar_init(&r2full[s], 1); mbar_init(&r2empty[s], 2); }
+    for (int b = 0; b < NB; ++b) { mbar_init(&hfull[b], 1); mbar_init(&hready[b], 128); }
+    mbar_init(yfull, 1);
+    mbar_init(yempty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  // epilogue parameters (shared by all tiles)
+  for (int i = threadIdx.x; i < 4 * C; i += MF_THREADS) s_b1[i] = a.b1[i];
+  for (int i = threadIdx.x; i < C; i += MF_THREADS) { s_b2[i] = a.b2[i]; s_gamma[i] = a.gamma[i]; s_beta[i] = a.beta[i]; }
+  tc_fence_before();
+  cluster_sync_all();          // peer barriers are initialised before any multicast / remote commit
+  tc_fence_after();
+  if (*tmem_slot != 0u) __trap();      // all 512 columns: the allocation starts at TMEM address 0
+  constexpr uint32_t tmem = 0u;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    // issue order == consumption order of the MMA warp:  X(tile), W1(0), then per chunk  W1(c+1), W2(c)
+    if (lane == 0) {
+      int p1 = 0, p2 = 0;        // ring positions (running counters)
+      int xuse = 0;              // tiles loaded so far (X barrier phases)
+      auto load_w1 = [&](int c) {          // chunk c (0..NCH-1): KX units
+        for (int k = 0; k < KX; ++k, ++p1) {
+          const int s = p1 % S1;
+          mbar_wait(&r1empty[s], ((p1 / S1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&r1full[s], T::R1_UNIT);
+          // this CTA fetches 32 of the 64 hidden rows and multicasts them to the pair
+          tma_load_2d_mcast(&tmW1, &r1full[s], r1 + s * T::R1_UNIT + cta_rank * 4096, k * 64, c * 64 + cta_rank * 32,
+                            uint16_t(3), kEvictLast);
+        }
+      };
+      auto load_w2 = [&](int c) {          // chunk c: NH units [192 out rows x 64 k]
+        for (int h = 0; h < NH; ++h, ++p2) {
+          const int s = p2 % S2;
+          mbar_wait(&r2empty[s], ((p2 / S2) & 1) ^ 1);
+          mbar_arrive_expect_tx(&r2full[s], T::R2_UNIT);
+          tma_load_2d_mcast(&tmW2, &r2full[s], r2 + s * T::R2_UNIT + cta_rank * 12288, c * 64, h * 192 + cta_rank * 96,
+                            uint16_t(3), kEvictLast);
+        }
+      };
+      auto load_x = [&](int tile, int use) {   // use-th X tile of this CTA; slabs free up as the previous tile's last GEMM1 retires
+        for (int k = 0; k < KX; ++k) {
+          mbar_wait(&xempty[k], (use & 1) ^ 1);
+          mbar_arrive_expect_tx(&xfull[k], 16384);
+          tma_load_2d_hint(&tmX, &xfull[k], xs + k * 16384, k * 64, tile * 128, kEvictFirst);   // rows >= T read as zero
+        }
+      };
+      // flat chunk sequence over this CTA's tiles, same order as the MMA warp:  G1(cgx), G2(cgx - (NB-1))
+      const int my_tiles = (num_units - pair + num_pairs - 1) / num_pairs;
+      const int total = my_tiles * NCH;
+      for (int cgx = 0; cgx < total + NB - 1; ++cgx) {
+        if (cgx < total) {
+          const int tu = cgx / NCH, c = cgx % NCH;
+          if (c == 0) load_x(2 * (pair + tu * num_pairs) + cta_rank, tu);
+          load_w1(c);
+        }
+        if (cgx >= NB - 1) load_w2((cgx - (NB - 1)) % NCH);
+      }
+      (void)xuse;
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    // whole warp converged, warp-uniform operands; one elected lane issues
+    constexpr uint32_t idesc1 = make_idesc_f16(128, 64, kFp16);
+    constexpr uint32_t idesc2 = make_idesc_f16(128, 192, kFp16);
+    const uint32_t xs_u32 = smem_u32(xs), r1_u32 = smem_u32(r1), r2_u32 = smem_u32(r2);
+    int p1 = 0, p2 = 0;
+    int tuse = 0;              // tiles started (X / Y barrier phases)
+    auto gemm1 = [&](int c_in_tile, int tile_use) {      // chunk -> Hacc[cgx & 1]; cgx = global index of that chunk
+      const int cgx = tile_use * NCH + c_in_tile, hb = cgx % NB;
+      for (int k = 0; k < KX; ++k, ++p1) {
+        const int s = p1 % S1;
+        if (c_in_tile == 0) mbar_wait(&xfull[k], tile_use & 1);
+        mbar_wait(&r1full[s], (p1 / S1) & 1);
+        tc_fence_after();
+        const uint64_t da = make_sdesc_sw128(xs_u32 + k * 16384);
+        const uint64_t db = make_sdesc_sw128(r1_u32 + s * T::R1_UNIT);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16_ss(tmem + T::COL_H + 64 * hb, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc1, (k | kk) != 0 ? 1u : 0u);
+          umma_commit_mcast(&r1empty[s], uint16_t(3));
+          if (c_in_tile == NCH - 1) umma_commit(&xempty[k]);     // last reader of this X slab
+          if (k == KX - 1) umma_commit(&hfull[hb]);
+        }
+        __syncwarp();
+      }
+    };
+    auto gemm2 = [&](int c_in_tile, int tile_use) {
+      const int cgx = tile_use * NCH + c_in_tile, hb = cgx % NB;
+      mbar_wait(&hready[hb], (cgx / NB) & 1);
+      if (c_in_tile == 0) mbar_wait(yempty, (tile_use & 1) ^ 1);      // the epilogue has read the previous tile's Y
+      tc_fence_after();
+      for (int h = 0; h < NH; ++h, ++p2) {
+        const int s = p2 % S2;
+        mbar_wait(&r2full[s], (p2 / S2) & 1);
+        tc_fence_after();
+        const uint64_t db = make_sdesc_sw128(r2_u32 + s * T::R2_UNIT);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)     // K = 64 hidden units: H advances 8 TMEM columns per K16
+            umma_f16_ts_(tmem + h * 192, tmem + T::COL_H + 64 * hb + 8 * kk, db + uint64_t(kk * 2), idesc2,
+                         (c_in_tile | kk) != 0 ? 1u : 0u);
+          umma_commit_mcast(&r2empty[s], uint16_t(3));
+          if (c_in_tile == NCH - 1 && h == NH - 1) umma_commit(yfull);
+        }
+        __syncwarp();
+      }
+    };
+    const int my_tiles = (num_units - pair + num_pairs - 1) / num_pairs;
+    const int total = my_tiles * NCH;
+    for (int cgx = 0; cgx < total + NB - 1; ++cgx) {
+      if (cgx < total) gemm1(cgx % NCH, cgx / NCH);
+      if (cgx >= NB - 1) gemm2((cgx - (NB - 1)) % NCH, (cgx - (NB - 1)) / NCH);
+    }
+    (void)tuse;
+  } else if (warp < 6) {
+    // ================================ LayerNorm + residual epilogue ================================
+    // one warp per TMEM lane quadrant; thread = one token row (statistics are thread-local)
+    const int quad = warp & 3;
+    const int ew = warp - 2;
+    uint8_t* slab = smem + T::OFF_SLAB + ew * T::SLAB_BYTES;
+    int* s_tok = reinterpret_cast<int*>(smem + T::OFF_TAB) + ew * 64;
+    int* s_dst = s_tok + 32;
+    const Geo geo = make_geo(a.Z, a.H, a.W);
+    int tuse = 0;
+    for (int unit = pair; unit < num_units; unit += num_pairs, ++tuse) {
+      const int tile = 2 * unit + cta_rank;
+      const uint32_t tacc = tmem + (uint32_t(quad * 32) << 16);
+      __syncwarp();
+      {
+        const int g = tile * 128 + quad * 32 + lane;
+        const int tok = g < a.T ? g : -1;
+        s_tok[lane] = tok;
+        s_dst[lane] = (tok >= 0 && a.roll_out >= 0) ? token_to_win_row(geo, tok, a.roll_out) : tok;
+      }
+      __syncwarp();
+      constexpr int PPR = 8;       // 16 B fp32 pieces per 32-column row chunk
+      auto load_resid = [&](int cc, uint4 (&dst)[PPR]) {
+#pragma unroll
+        for (int it = 0; it < PPR; ++it) {
+          const int id = it * 32 + lane;
+          const int rr = id / PPR, pc = id % PPR;
+          const int tok = s_tok[rr];
+          dst[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (tok >= 0) dst[it] = ldg16(a.x32 + size_t(tok) * C + cc + pc * 4);
+        }
+      };
+      uint4 resq[PPR];
+      load_resid(0, resq);         // latency hidden behind the wait for the accumulator
+      mbar_wait(yfull, tuse & 1);
+      tc_fence_after();
+      // ---- LayerNorm statistics of (acc + b2) over the row: shifted sums, packed fp32x2 math
+      float mean, rstd;
+      {
+        float shift = 0.f;
+        f32x2 s1 = pack2(0.f, 0.f), s2 = pack2(0.f, 0.f);
+#pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tacc + c0, r);
+          tmem_ld_wait();
+          if (c0 == 0) shift = __uint_as_float(r[0]) + s_b2[0];
+          const f32x2 nshift = pack2(-shift, -shift);
+          const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = b4[j4];
+            const f32x2 v01 = add2(add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y)), nshift);
+            const f32x2 v23 = add2(add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w)), nshift);
+            s1 = add2(s1, add2(v01, v23));
+            s2 = fma2(v01, v01, s2);
+            s2 = fma2(v23, v23, s2);
+          }
+        }
+        float s1a, s1b, s2a, s2b;
+        unpack2(s1, s1a, s1b);
+        unpack2(s2, s2a, s2b);
+        const float inv_n = 1.0f / float(C);
+        const float m = (s1a + s1b) * inv_n;
+        const float var = fmaxf((s2a + s2b) * inv_n - m * m, 0.f);
+        mean = shift + m;
+        rstd = rsqrtf(var + a.eps);
+      }
+      const f32x2 ln_a = pack2(rstd, rstd), ln_b = pack2(-mean * rstd, -mean * rstd);
+#pragma unroll 1
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        uint4 resn[PPR];
+        if (c0 + 32 < C) load_resid(c0 + 32, resn);
+        // phase A: TMEM -> registers -> (acc + b2 - mean) * rstd * gamma + beta -> slab (row per lane)
+        {
+          uint32_t r[32];
+          tmem_ld32(tacc + c0, r);
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
+          const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
+          const float4* e4 = reinterpret_cast<const float4*>(s_beta + c0);
+          uint4* dstp = reinterpret_cast<uint4*>(slab + lane * T::STG_PITCH);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = b4[j4], gg = g4[j4], ee = e4[j4];
+            f32x2 v01 = add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y));
+            f32x2 v23 = add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w));
+            v01 = fma2(fma2(v01, ln_a, ln_b), pack2(gg.x, gg.y), pack2(ee.x, ee.y));
+            v23 = fma2(fma2(v23, ln_a, ln_b), pack2(gg.z, gg.w), pack2(ee.z, ee.w));
+            float v0, v1, v2, v3;
+            unpack2(v01, v0, v1);
+            unpack2(v23, v2, v3);
+            dstp[j4] = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+          }
+        }
+        if (c0 + 32 >= C) {          // accumulator fully read: hand the Y buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(yempty);
+        }
+        __syncwarp();
+        // phase B: slab -> global, coalesced (8 lanes per row), + residual; fp32 stream and 16-bit shadow
+#pragma unroll
+        for (int it = 0; it < PPR; ++it) {
+          const int id = it * 32 + lane;
+          const int rr = id / PPR, pc = id % PPR;
+          const int tok = s_tok[rr];
+          if (tok < 0) continue;
+          const int col = c0 + pc * 4;
+          const uint4 v = *reinterpret_cast<const uint4*>(slab + rr * T::STG_PITCH + pc * 16);
+          const uint4 q = resq[it];
+          const float f0 = fmaf(a.res_scale, __uint_as_float(v.x), __uint_as_float(q.x));
+          const float f1 = fmaf(a.res_scale, __uint_as_float(v.y), __uint_as_float(q.y));
+          const float f2 = fmaf(a.res_scale, __uint_as_float(v.z), __uint_as_float(q.z));
+          const float f3 = fmaf(a.res_scale, __uint_as_float(v.w), __uint_as_float(q.w));
+          stg16(a.x32 + size_t(tok) * C + col,
+                make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)));
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.out16) + size_t(s_dst[rr]) * C + col) =
+              make_uint2(pack16<kFp16>(f0, f1), pack16<kFp16>(f2, f3));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < PPR; ++it) resq[it] = resn[it];
+      }
+    }
+  } else {
+    // ================================ GELU warps ================================
+    // warpgroup wgp handles the chunks with (global chunk index & 1) == wgp, i.e. Hacc buffer wgp
+    const int quad = warp & 3, wgp = (warp - 6) >> 2;
+    const uint32_t hbase = tmem + (uint32_t(quad * 32) << 16) + T::COL_H;
+    int cgx = wgp;   // global chunk index of this warpgroup's next chunk (NCH and NB are even: parity is preserved)
+    for (int unit = pair; unit < num_units; unit += num_pairs) {
+      for (int c = wgp; c < NCH; c += 2, cgx += 2) {
+        const int hb = cgx % NB;
+        const uint32_t haddr = hbase + 64 * hb;
+        mbar_wait(&hfull[hb], (cgx / NB) & 1);
+        tc_fence_after();
+        uint32_t r[2][32];
+        tmem_ld32(haddr, r[0]);
+        tmem_ld32(haddr + 32, r[1]);
+        tmem_ld_wait();
+        uint32_t pk[32];
+        const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 64);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = b4[hh * 8 + j4];
+            float v0 = __uint_as_float(r[hh][4 * j4]) + bb.x, v1 = __uint_as_float(r[hh][4 * j4 + 1]) + bb.y;
+            float v2 = __uint_as_float(r[hh][4 * j4 + 2]) + bb.z, v3 = __uint_as_float(r[hh][4 * j4 + 3]) + bb.w;
+            gelu_erf2(v0, v1);
+            gelu_erf2(v2, v3);
+            pk[hh * 16 + 2 * j4] = pack16<kFp16>(v0, v1);
+            pk[hh * 16 + 2 * j4 + 1] = pack16<kFp16>(v2, v3);
+          }
+        }
+        tmem_st32_(haddr, pk);       // H (64 x 16-bit = 32 columns) over the first half of its own accumulator
+        tmem_st_wait_();
+        tc_fence_before();
+        mbar_arrive(&hready[hb]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // no multicast / remote commit may target an exited CTA
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+}  // namespace pg
