@@ -63,19 +63,25 @@ int pangu_patch_embed(const float* upper, const float* surface,
                       int lat, int lon, int fp16, void* stream);
 
 /* EarthAttention3D.linear1 + head split + q*scale (models/layers.py:365-374).
- * x16w [Tp, C] window order -> qkv16 [Tp, 3C] window order, q pre-scaled by 32^-0.5. */
+ * x16w [Tp, C] window order -> qkv16 head-major [3C/32 planes][Tp rounded up to 128][32] (plane = s*heads + head,
+ * s in {q,k,v}; window-order rows), q pre-scaled by 32^-0.5. */
 int pangu_qkv(const void* x16w, const void* w16 /*[3C,C]*/, const float* bias /*[3C]*/,
               void* qkv16, int Z, int H, int W, int C, int fp16, void* stream);
 
 /* q k^T + earth_specific_bias (+ shift mask, gen_mask models/layers.py:153-181) -> softmax ->
  * P v, heads merged (models/layers.py:378-415).  bias: the fp32 parameter
- * [1, types, heads, 144, 144] as stored in the state_dict. */
+ * [1, types, heads, 144, 144] as stored in the state_dict.
+ * qkv16: head-major [3*heads planes][Tp rounded up to 128][32] as written by pangu_qkv.
+ * att16: window_order_out == 0 -> [Z*H*W, C] in NATURAL token order (window reverse, un-roll and crop of
+ *        models/layers.py:227-243 folded into the store; pad rows dropped);
+ *        window_order_out != 0 -> [Tp, C] in window order, pad rows included (EarthAttention3D.forward). */
 int pangu_window_attention(const void* qkv16, const float* earth_bias, void* att16,
-                           int Z, int H, int W, int C, int heads, int roll, int fp16, void* stream);
+                           int Z, int H, int W, int C, int heads, int roll, int window_order_out, int fp16,
+                           void* stream);
 
-/* EarthAttention3D.linear2 + window reverse + un-roll + crop + norm1 + residual
- * (models/layers.py:418, 227-250):  x32[tok] += res_scale * LN1(att W2^T + b2).
- * Also writes x16 (natural order) = cast(x32) for the MLP. In-place on x32. */
+/* EarthAttention3D.linear2 + norm1 + residual (models/layers.py:418, 250) on the natural-order attention
+ * output of pangu_window_attention:  x32[tok] += res_scale * LN1(att[tok] W2^T + b2).
+ * Also writes x16 (natural order) = cast(x32) for the MLP. In-place on x32.  `roll` is unused (kept for ABI). */
 int pangu_proj_ln_residual(const void* att16, const void* w16 /*[C,C]*/, const float* bias,
                            const float* gamma, const float* beta,
                            float* x32, void* x16, int Z, int H, int W, int C, int roll,

@@ -23,7 +23,7 @@ SIGNATURES = {
     "pangu_to_window16": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "pangu_patch_embed": [_P] * 16 + [_I, _I, _I, _P],
     "pangu_qkv": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "pangu_window_attention": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "pangu_window_attention": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "pangu_proj_ln_residual": [_P] * 7 + [_I, _I, _I, _I, _I, _F, _I, _P],
     "pangu_mlp_ln_residual": [_P] * 10 + [_I, _I, _I, _I, _I, _F, _I, _P],
     "pangu_downsample": [_P] * 7 + [_I, _I, _I, _I, _I, _P],

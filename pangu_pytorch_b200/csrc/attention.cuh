@@ -29,8 +29,10 @@ constexpr int ATT_SMEM_BYTES = ATT_STAGES * ATT_BUF_BYTES;
 struct AttnArgs {
   const void* qkv;     // [nLon*types*144][3C] 16-bit, window order, q pre-scaled
   const float* bias;   // [types][heads][144][144] fp32 (earth_specific_bias parameter)
-  void* out;           // [nLon*types*144][C] 16-bit, window order, channel = head*32 + d
+  void* out;           // tcgen05 kernel: [Z*H*W tokens][C] 16-bit, NATURAL order; v1 kernel: window order
   int C, heads, types, nLon, nH;
+  int H, W;            // token grid (natural-order output of the tcgen05 kernel)
+  int natural;         // 1: out rows are natural tokens (pad rows dropped); 0: window order, all rows
   int roll;            // add the shifted-window mask
   int lon_per_cta;     // (mma.sync v1 kernel) longitude windows walked by one CTA
   int plane_rows;      // (tcgen05 kernel) rows per (q|k|v, head) plane of the head-major qkv buffer

@@ -256,6 +256,22 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
       // box p (16 key columns) of the bias tile sits in ring slot qb + p/3 at tile offset (p%3)
       auto box_ptr = [&](int p) { return ring + ((qb + p / 3) % ATC_STAGES) * ATC_STAGE_BYTES + (p % 3) * ATT_TILE_BYTES; };
 
+      // Output goes out in NATURAL token order (window reverse + un-roll + crop of models/layers.py:227-243 folded
+      // into the store address): row k of a window of this type is token (zp, hp, wp) with zp, hp fixed for the
+      // segment and wp advancing by 12 per longitude window; pad rows (hp >= H) are dropped.
+      const int Hp_ = a.H + 5;
+      auto row_base = [&](int k) {            // (zp * H + hp) * W, or -1 for a pad row
+        const int zl = k / 72, hl = (k / 12) % 6;
+        int zp = 2 * zw + zl, hp = 6 * hw + hl;
+        if (a.roll) { zp = (zp + 1) & 7; hp = (hp + 3) % Hp_; }
+        return hp >= a.H ? -1 : (zp * a.H + hp) * a.W;
+      };
+      auto out_row = [&](int base, int k, int lw) {   // output row of window row k in longitude window lw (-1: dropped)
+        if (!a.natural) return (lw * a.types + t) * ATT_TOK + k;      // window order, pad rows included
+        int wp = 12 * lw + (k % 12) + (a.roll ? 6 : 0);
+        wp = wp >= a.W ? wp - a.W : wp;
+        return base < 0 ? -1 : base + wp;
+      };
       if (warp < 8) {
         // ============================== tail warps: rows 128..143 with mma.sync ==============================
         const int tid = threadIdx.x - 64;        // 0..191
@@ -351,13 +367,14 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           }
           __syncwarp();
           {
-            const size_t row0 = (size_t(lw0 + i) * a.types + t) * ATT_TOK + 128;
             uint8_t* outp = reinterpret_cast<uint8_t*>(a.out);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               const int id = k * 32 + lane, r = id >> 2, c = id & 3;
+              const int orow = out_row(row_base(128 + r), 128 + r, lw0 + i);
+              if (orow < 0) continue;
               const uint4 v = *reinterpret_cast<const uint4*>(tile + att_off(128 + r, c));
-              stg16(outp + (row0 + r) * (size_t(a.C) * 2) + head * 64 + c * 16, v);
+              stg16(outp + size_t(orow) * (size_t(a.C) * 2) + head * 64 + c * 16, v);
             }
           }
           __syncwarp();
@@ -398,6 +415,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         if (threadIdx.x >= 256 && threadIdx.x < 259) mbar_arrive(&empty_bar[(qb + threadIdx.x - 256) % ATC_STAGES]);
         if (threadIdx.x == 256) TR(6, seg, 1);
 
+        const int my_base = row_base(r);
         float l_prev = 1.f;
         auto epilogue = [&](int j, float l) {      // j: window index inside the segment
           const int g = gbase + j;
@@ -408,9 +426,10 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(&oempty_bar[wg]);
+          const int orow = out_row(my_base, r, lw0 + j);
+          if (orow < 0) return;                   // zero pad row of the window: its output is cropped away
           const float inv = 1.0f / l;
-          const size_t row = (size_t(lw0 + j) * a.types + t) * ATT_TOK + r;
-          uint8_t* dst = reinterpret_cast<uint8_t*>(a.out) + row * (size_t(a.C) * 2) + head * 64;
+          uint8_t* dst = reinterpret_cast<uint8_t*>(a.out) + size_t(orow) * (size_t(a.C) * 2) + head * 64;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 v;

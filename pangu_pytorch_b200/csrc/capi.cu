@@ -360,13 +360,14 @@ extern "C" int pangu_qkv(const void* x16w, const void* w16, const float* bias, v
 }
 
 extern "C" int pangu_window_attention(const void* qkv16, const float* earth_bias, void* att16, int Z, int H, int W,
-                                      int C, int heads, int roll, int fp16, void* stream) {
+                                      int C, int heads, int roll, int window_order_out, int fp16, void* stream) {
   PG_TRY(ensure_init());
   PG_TRY(check_grid(Z, H, W, C, heads));
   const Geo g = make_geo(Z, H, W);
   AttnArgs a;
   a.qkv = qkv16; a.bias = earth_bias; a.out = att16;
   a.C = C; a.heads = heads; a.types = g.types; a.nLon = g.nLon; a.nH = g.nH; a.roll = roll ? 1 : 0;
+  a.H = H; a.W = W; a.natural = window_order_out ? 0 : 1;
   a.lon_per_cta = g.nLon;
   a.debug = 0;
   a.trace = nullptr;
@@ -425,14 +426,13 @@ extern "C" int pangu_proj_ln_residual(const void* att16, const void* w16, const 
                                       float res_scale, int fp16, void* stream) {
   PG_TRY(ensure_init());
   PG_TRY(check_grid(Z, H, W, C, 0));
-  const Geo g = make_geo(Z, H, W);
-  const int Tp = g.nLon * g.types * 144;
-  GemmOperands o{att16, uint64_t(C), nullptr, 0, C, 0, w16, uint64_t(C), Tp, C};
+  (void)roll;    // att16 arrives in natural token order: the window reverse / un-roll / crop happened in the attention store
+  GemmOperands o{att16, uint64_t(C), nullptr, 0, C, 0, w16, uint64_t(C), Z * H * W, C};
   EpiArgs ep = epi_defaults();
   ep.Z = Z; ep.H = H; ep.W = W;
   ep.bias = bias; ep.gamma = gamma; ep.beta = beta;
   ep.resid = x32; ep.out32 = x32; ep.out16 = x16; ep.ld32 = C; ep.ld16 = C;
-  ep.rowmap = RM_WIN2TOK; ep.roll_in = roll ? 1 : 0; ep.dstmap = DM_IDENT;
+  ep.rowmap = RM_IDENT; ep.dstmap = DM_IDENT;
   ep.res_scale = res_scale;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return C == 192 ? launch_gemm<CfgLNRes192>(o, ep, fp16, s) : launch_gemm<CfgLNRes384>(o, ep, fp16, s);
@@ -446,8 +446,8 @@ extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, cons
   PG_TRY(check_grid(Z, H, W, C, 0));
   const int T = Z * H * W;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static const bool unfused = getenv("PANGU_B200_MLP_UNFUSED") != nullptr;     // development A/B switch
-  if (!unfused) {
+  static const bool fused = getenv("PANGU_B200_MLP_FUSED") != nullptr;     // development A/B switch (off until it wins)
+  if (fused) {
     // one kernel: the hidden activation stays in tensor memory (ws_hidden is not touched)
     MlpArgs a;
     a.b1 = b1; a.b2 = b2; a.gamma = gamma; a.beta = beta;

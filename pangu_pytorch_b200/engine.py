@@ -8,7 +8,7 @@ HBM layout of one resolution (``GridWorkspace``), T = Z*H*W real tokens, Tp = wi
     x16w[r]  [Tp, C ] 16-bit shadow in WINDOW order for roll state r in {0,1}; the +5 latitude
                              pad rows are zeroed once here and never written again
     qkv      [3C/32, Tp', 32] 16-bit, one plane per (q|k|v, head), window order rows, q pre-scaled
-    att      [Tp, C ] 16-bit window order, heads merged
+    att      [Tp, C ] 16-bit heads merged; the block path uses the first T rows in NATURAL token order
     hidden   [T , 4C] 16-bit GELU(linear1) activations
 """
 from __future__ import annotations

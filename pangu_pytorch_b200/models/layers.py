@@ -155,13 +155,13 @@ class EarthAttention3D(nn.Module):
             + (w[:, None] - w[None, :] + ww - 1)
         self.position_index = idx.reshape(-1).to(self.device)
 
-    def _run(self, ws: engine.GridWorkspace, roll: bool):
-        """x16w[roll] -> qkv -> att (both window order)."""
+    def _run(self, ws: engine.GridWorkspace, roll: bool, window_order_out: bool = False):
+        """x16w[roll] -> qkv (head-major, window-order rows) -> att (natural token order unless asked otherwise)."""
         fp16 = ws.fp16
         ops.qkv(ws.x16w[int(roll)], self._w1.get(self.linear1.weight), self.linear1.bias, ws.qkv,
                 ws.Z, ws.H, ws.W, ws.C, fp16)
         ops.window_attention(ws.qkv, self.earth_specific_bias, ws.att, ws.Z, ws.H, ws.W, ws.C, self.head_number,
-                             roll, fp16)
+                             roll, fp16, window_order_out)
 
     def forward(self, x, mask):
         """x: [nLon, types, 144, C] window tensor.  ``mask`` is only inspected for None-ness: the
@@ -173,7 +173,7 @@ class EarthAttention3D(nn.Module):
         x2 = x.detach().reshape(-1, C).contiguous().float()
         roll = mask is not None
         _cast_rows(x2, ws.x16w[int(roll)], fp16)
-        self._run(ws, roll)
+        self._run(ws, roll, window_order_out=True)
         out32 = torch.empty(ws.Tp, C, dtype=torch.float32, device=x.device)
         out16 = torch.empty(ws.Tp, C, dtype=ops.dtype16(fp16), device=x.device)
         ops.linear(ws.att, self._w2.get(self.linear2.weight), self.linear2.bias, out32, out16, False, fp16)

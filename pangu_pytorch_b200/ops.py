@@ -133,10 +133,11 @@ def qkv(x16w, w16, bias, out, Z, H, W, C, fp16: bool) -> None:
           _stream())
 
 
-def window_attention(qkv16, earth_bias, out, Z, H, W, C, heads, roll: bool, fp16: bool) -> None:
+def window_attention(qkv16, earth_bias, out, Z, H, W, C, heads, roll: bool, fp16: bool, window_order_out: bool = False) -> None:
+    """out: [T, C] natural token order (default) or [Tp, C] window order with pad rows (window_order_out)."""
     h = dtype16(fp16)
     _call("pangu_window_attention", _p(qkv16, h, "qkv"), _p(earth_bias, torch.float32, "earth_specific_bias"),
-          _p(out, h), Z, H, W, C, heads, int(bool(roll)), int(fp16), _stream())
+          _p(out, h), Z, H, W, C, heads, int(bool(roll)), int(bool(window_order_out)), int(fp16), _stream())
 
 
 def proj_ln_residual(att16, w16, bias, gamma, beta, x32, x16, Z, H, W, C, roll: bool, res_scale: float,

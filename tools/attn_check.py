@@ -18,7 +18,7 @@ ws.qkv.normal_()
 ebias = torch.randn(1, types, heads, 144, 144, device=dev)
 for roll in (0, 1):
     ws.att.zero_()
-    ops.window_attention(ws.qkv, ebias, ws.att, Z, H, W, C, heads, roll, False)
+    ops.window_attention(ws.qkv, ebias, ws.att, Z, H, W, C, heads, roll, False, True)
     torch.cuda.synchronize()
     q, k, v = [ws.qkv[s * heads:(s + 1) * heads, :Tp].float().view(heads, nlon, types, 144, 32) for s in range(3)]
     S = torch.einsum("hltid,hltjd->hltij", q, k) + ebias[0].permute(1, 0, 2, 3)[:, None]
