@@ -117,6 +117,7 @@ struct CfgBase {
   static constexpr int CLUSTER = 1;      // 2: CTA pairs share every weight (B) tile by TMA multicast
   static constexpr bool NSPLIT = false;  // CTA pair splits the LayerNorm row (N) instead of M; stats via DSMEM
   static constexpr bool HEADMAJOR = false;  // TMA16: output stored as [N/32 planes][plane_rows][32]
+  static constexpr bool RESTMA = false;  // LN + residual epilogue whose fp32 stream moves by TMA (identity row map)
 };
 struct CfgQKV : CfgBase {      // linear1 of attention: bias, q-scale, 16-bit out
   static constexpr int BN = 192, UN = 192, STAGES = 4;
@@ -129,13 +130,13 @@ struct CfgMLP1 : CfgBase {     // Mlp.linear1: bias + exact GELU, 16-bit out
   static constexpr int CLUSTER = 2;
 };
 struct CfgLNRes192 : CfgBase { // bias + LayerNorm(192) + residual, fp32 + 16-bit out
-  static constexpr int BN = 192, UN = 192, STAGES = 4;
-  static constexpr bool LN = true, RESID = true, OUT32 = true, OUT16 = true;
+  static constexpr int BN = 192, UN = 192, STAGES = 3;
+  static constexpr bool LN = true, RESID = true, OUT32 = true, OUT16 = true, RESTMA = true;
   static constexpr int CLUSTER = 2;
 };
 struct CfgLNRes384 : CfgBase { // bias + LayerNorm(384) + residual: a CTA pair, 192 columns each, stats over DSMEM
-  static constexpr int BN = 192, UN = 192, STAGES = 4;
-  static constexpr bool LN = true, RESID = true, OUT32 = true, OUT16 = true;
+  static constexpr int BN = 192, UN = 192, STAGES = 3;
+  static constexpr bool LN = true, RESID = true, OUT32 = true, OUT16 = true, RESTMA = true;
   static constexpr int CLUSTER = 2;
   static constexpr bool NSPLIT = true;
 };
@@ -178,6 +179,20 @@ static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t 
   if (o.k2 > 0) PG_TRY(make_map(&ma2, o.a2, o.M, o.k2, o.a2_pitch, BLOCK_M)); else ma2 = ma;
   PG_TRY(make_map(&mb, o.b, o.N, o.k1 + o.k2, o.b_pitch, (Cfg::CLUSTER == 2 && !Cfg::NSPLIT) ? Cfg::BN / 2 : Cfg::UN));
   CUtensorMap mo = ma;
+  if constexpr (Cfg::RESTMA) {
+    // residual stream == fp32 output, [M, ld32] fp32 in natural row order: 32-column x 32-row SWIZZLE_128B tiles
+    PG_REQUIRE(ep.rowmap == RM_IDENT && ep.row_base == 0 && ep.resid == ep.out32 && ep.out32 != nullptr && ep.out16 != nullptr,
+               "TMA residual epilogue needs an identity row map and an in-place fp32 stream");
+    PG_REQUIRE((reinterpret_cast<uintptr_t>(ep.out32) & 15) == 0 && (size_t(ep.ld32) * 4) % 16 == 0, "fp32 stream not TMA-addressable");
+    cuuint64_t dims[2] = {cuuint64_t(ep.ld32), cuuint64_t(o.M)};
+    cuuint64_t strides[1] = {cuuint64_t(ep.ld32) * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ep.out32, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled(residual) failed (%d)", int(r));
+  }
   if constexpr (Cfg::TMA16) {
     PG_REQUIRE(ep.rowmap == RM_IDENT && ep.dstmap == DM_IDENT && ep.row_base == 0 && ep.out16 != nullptr,
                "TMA-store epilogue needs an identity row map");

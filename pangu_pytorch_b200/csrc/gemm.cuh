@@ -77,18 +77,24 @@ struct GemmTraits {
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_PITCH = CH * 4 + 16;      // bytes; == 16 (mod 128) -> conflict-free 16 B rows
-  // per-warp staging slab: [32 rows][STG_PITCH] fp32, or (TMA16) two [32 rows][64 B] SWIZZLE_64B tiles
-  static constexpr int SLAB_BYTES = Cfg::TMA16 ? 4096 : ((32 * STG_PITCH + 511) / 512) * 512;
+  // per-warp staging slab: [32 rows][STG_PITCH] fp32, or (TMA16) two [32 rows][64 B] SWIZZLE_64B tiles, or
+  // (RESTMA) one [32 rows][128 B] SWIZZLE_128B residual / output tile per column chunk the warp owns
+  static constexpr int RES_SLOTS = BN / 64;          // chunks of 32 columns per epilogue warp and tile
+  static constexpr int SLAB_BYTES = Cfg::RESTMA ? RES_SLOTS * 4096 : Cfg::TMA16 ? 4096 : ((32 * STG_PITCH + 511) / 512) * 512;
   static constexpr int PAR_BYTES = 3 * BN * 4;       // bias / gamma / beta (shared by the 8 epilogue warps)
   static constexpr int TAB_BYTES = 8 * 64 * 4;       // per warp: row -> token, row -> 16-bit destination row
   static constexpr int EPI_BYTES = ((8 * SLAB_BYTES + PAR_BYTES + TAB_BYTES + 1023) / 1024) * 1024;
-  static constexpr int BAR_BYTES = 256 + (Cfg::NSPLIT ? 2 * 128 * 16 : 0);   // + LN partial-stat mailboxes
+  static constexpr int BAR_BYTES = 256 + (Cfg::NSPLIT ? 2 * 128 * 16 : 0)    // + LN partial-stat mailboxes
+                                   + (Cfg::RESTMA ? 8 * RES_SLOTS * 8 : 0);   // + per-warp residual-landed barriers
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
   static_assert(BN % UN == 0 && UN % 16 == 0 && UN <= 256, "bad N tiling");
   static_assert(CL == 1 || (CL == 2 && (BN / 2) % 8 == 0 && BN / 2 <= 256), "bad cluster B split");
   static_assert(!NSPLIT || (CL == 2 && Cfg::LN && NUM_B == 1), "NSPLIT: LayerNorm row split over a CTA pair");
   static_assert(BN % CH == 0 && (CH == 16 || CH == 32), "bad epilogue chunk");
   static_assert(!Cfg::TMA16 || BN % 64 == 0, "TMA16: both warpgroups take whole 32-column chunks");
+  static_assert(!Cfg::RESTMA || (Cfg::LN && Cfg::RESID && Cfg::OUT32 && Cfg::OUT16 && CH == 32 && BN % 64 == 0 &&
+                                 Cfg::RECOVER == 0 && !Cfg::TMA16), "RESTMA: LayerNorm + residual epilogue");
+  static_assert(SLAB_BYTES % 1024 == 0 || !Cfg::RESTMA, "SWIZZLE_128B tiles need 1024 B alignment");
   static_assert(!Cfg::TMA16 || (CH == 32 && !Cfg::LN && !Cfg::OUT32 && Cfg::RECOVER == 0), "TMA16: plain 16-bit output");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024 B alignment");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
@@ -120,6 +126,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   [[maybe_unused]] uint64_t* xfull_bar = bars + 24;     // [2] 128 remote arrivals (peer's row owners)
   [[maybe_unused]] uint64_t* xempty_bar = bars + 26;    // [2] 256 remote arrivals (peer's readers)
   [[maybe_unused]] float4* xch = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][128]
+  // RESTMA: residual tile of (epilogue warp, slot) has landed
+  [[maybe_unused]] uint64_t* rfull_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bars) + 256 + (Cfg::NSPLIT ? 2 * 128 * 16 : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -137,7 +145,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
-    if constexpr (Cfg::TMA16) tma_prefetch_desc(&tmOut);
+    if constexpr (Cfg::TMA16 || Cfg::RESTMA) tma_prefetch_desc(&tmOut);
     for (int s = 0; s < T::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], CL);     // one tcgen05.commit arrival per CTA of the cluster
@@ -146,6 +154,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], kEpiThreads);
       if constexpr (T::NSPLIT) { mbar_init(&xfull_bar[a], 128); mbar_init(&xempty_bar[a], kEpiThreads); }
+    }
+    if constexpr (Cfg::RESTMA) {
+      for (int i = 0; i < 8 * T::RES_SLOTS; ++i) mbar_init(&rfull_bar[i], 1);
     }
     fence_barrier_init();
   }
@@ -247,6 +258,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t acc_phase = 0;
     int loaded_n_blk = -1;
     [[maybe_unused]] int sbuf = 0;   // TMA16: slab parity, alternates across chunks AND tiles
+    [[maybe_unused]] int res_tiles = 0;   // RESTMA: tiles finished by this warp (residual barrier phase)
     for (int unit = unit0; unit < num_units; unit += unit_stride) {
       const int m_blk = unit_m(unit), n_blk = unit_n(unit);
       // ---- epilogue parameters of this n-block (uniform decision across the 8 warps; LN kernels: once)
@@ -323,6 +335,150 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_before();
         mbar_arrive(&tempty_bar[acc]);
         if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+
+      if constexpr (Cfg::RESTMA) {
+        // ------- LayerNorm + residual with the fp32 residual stream moved by TMA (natural token rows only).
+        // The warp owns RES_SLOTS tiles [32 rows x 32 fp32 columns] (SWIZZLE_128B, private smem): the residual
+        // of the NEXT tile is fetched into them while the mainloop of that tile runs, the result is formed in
+        // place and leaves with one TMA store per tile; no global load is ever waited for in this loop.
+        constexpr int NS = T::RES_SLOTS;
+        const int row0 = m_blk * BLOCK_M + quad * 32;
+        auto fetch_resid = [&](int mb, int nb) {      // lane 0: residual tiles of this warp for tile (mb, nb)
+#pragma unroll
+          for (int sl = 0; sl < NS; ++sl) {
+            mbar_arrive_expect_tx(&rfull_bar[wslot * NS + sl], 4096);
+            tma_load_2d(&tmOut, &rfull_bar[wslot * NS + sl], slab + sl * 4096, nb * BN + (half + 2 * sl) * 32, mb * BLOCK_M + quad * 32);
+          }
+        };
+        if (res_tiles == 0 && lane == 0) fetch_resid(m_blk, n_blk);      // first tile of this CTA
+        // 16-bit destination rows of this warp's 32 tokens
+        __syncwarp();
+        {
+          const int tok = row0 + lane < shape.M ? row0 + lane + ep.row_base : -1;
+          s_dst[lane] = (tok >= 0 && ep.dstmap == DM_TOK2WIN) ? token_to_win_row(geo, tok, ep.roll_out) : tok;
+        }
+        __syncwarp();
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        float mean = 0.f, rstd = 1.f;
+        {
+          // thread-local LayerNorm statistics over the row (shifted sums, packed fp32x2 math)
+          float shift = 0.f;
+          f32x2 s1 = pack2(0.f, 0.f), s2 = pack2(0.f, 0.f);
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c0, r);
+            tmem_ld_wait();
+            if (c0 == 0) shift = __uint_as_float(r[0]) + s_bias[0];
+            const f32x2 nshift = pack2(-shift, -shift);
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4];
+              const f32x2 v01 = add2(add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y)), nshift);
+              const f32x2 v23 = add2(add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w)), nshift);
+              s1 = add2(s1, add2(v01, v23));
+              s2 = fma2(v01, v01, s2);
+              s2 = fma2(v23, v23, s2);
+            }
+          }
+          float s1a, s1b, s2a, s2b;
+          unpack2(s1, s1a, s1b);
+          unpack2(s2, s2a, s2b);
+          if constexpr (T::NSPLIT) {
+            // exchange (sum, sum of squares, shift) of this half row with the peer CTA through DSMEM
+            const float my1 = s1a + s1b, my2 = s2a + s2b;
+            const uint32_t peer = uint32_t(cta_rank ^ 1);
+            if (half == 0) {
+              mbar_wait_cluster(&xempty_bar[acc], acc_phase ^ 1);  // peer has consumed my previous message in this slot
+              st_cluster_f4(mapa_u32(smem_u32(&xch[acc * 128 + quad * 32 + lane]), peer), my1, my2, shift, 0.f);
+              mbar_arrive_cluster(mapa_u32(smem_u32(&xfull_bar[acc]), peer));
+            }
+            mbar_wait_cluster(&xfull_bar[acc], acc_phase);
+            const float4 o = xch[acc * 128 + quad * 32 + lane];
+            mbar_arrive_cluster(mapa_u32(smem_u32(&xempty_bar[acc]), peer));
+            const float n = float(BN), inv_n2 = 1.0f / float(2 * BN);
+            const float mu = (my1 + n * shift + o.x + n * o.z) * inv_n2;
+            const float d0 = shift - mu, d1 = o.z - mu;
+            const float m2 = (my2 + 2.f * d0 * my1 + n * d0 * d0) + (o.y + 2.f * d1 * o.x + n * d1 * d1);
+            mean = mu;
+            rstd = rsqrtf(fmaxf(m2 * inv_n2, 0.f) + ep.eps);
+          } else {
+            const float inv_n = 1.0f / float(BN);
+            const float m = (s1a + s1b) * inv_n;
+            const float var = fmaxf((s2a + s2b) * inv_n - m * m, 0.f);
+            mean = shift + m;
+            rstd = rsqrtf(var + ep.eps);
+          }
+        }
+        const f32x2 ln_a = pack2(rstd * ep.res_scale, rstd * ep.res_scale), ln_b = pack2(-mean * rstd * ep.res_scale, -mean * rstd * ep.res_scale);
+        const f32x2 rs2 = pack2(ep.res_scale, ep.res_scale);
+#pragma unroll 1
+        for (int sl = 0; sl < NS; ++sl) {
+          const int c0 = (half + 2 * sl) * 32;
+          uint8_t* tile = slab + sl * 4096;
+          uint32_t r[32];
+          tmem_ld32(tacc + c0, r);
+          mbar_wait(&rfull_bar[wslot * NS + sl], res_tiles & 1);
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+          const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
+          const float4* e4 = reinterpret_cast<const float4*>(s_beta + c0);
+          // phase A (row per lane): x + s * ((acc + b - mean) * rstd * gamma + beta), formed in place in the residual tile
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            uint4* cell = reinterpret_cast<uint4*>(tile + lane * 128 + ((j4 ^ (lane & 7)) << 4));
+            const uint4 q = *cell;
+            const float4 bb = b4[j4], gg = g4[j4], ee = e4[j4];
+            f32x2 v01 = add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y));
+            f32x2 v23 = add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w));
+            // s * (v * rstd - mean * rstd) * gamma + s * beta + x
+            v01 = fma2(fma2(v01, ln_a, ln_b), pack2(gg.x, gg.y), fma2(rs2, pack2(ee.x, ee.y), pack2(__uint_as_float(q.x), __uint_as_float(q.y))));
+            v23 = fma2(fma2(v23, ln_a, ln_b), pack2(gg.z, gg.w), fma2(rs2, pack2(ee.z, ee.w), pack2(__uint_as_float(q.z), __uint_as_float(q.w))));
+            float v0, v1, v2, v3;
+            unpack2(v01, v0, v1);
+            unpack2(v23, v2, v3);
+            *cell = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+          }
+          if (sl == NS - 1) {        // accumulator drained by this thread
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          // fp32 stream: one TMA store of the [32 x 32] tile (rows beyond M are clipped)
+          if (lane == 0 && m_blk < shape.num_m_blocks) {
+            tma_store_2d(&tmOut, tile, n_blk * BN + c0, row0);
+            bulk_commit();
+          }
+          // phase B: 16-bit shadow, coalesced 64 B rows (4 lanes per row), optionally scattered to window order
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int id = it * 32 + lane;
+            const int rr = id >> 2, pc = id & 3;
+            const int dst = s_dst[rr];
+            if (dst < 0) continue;
+            const uint4 a0 = *reinterpret_cast<const uint4*>(tile + rr * 128 + (((2 * pc) ^ (rr & 7)) << 4));
+            const uint4 a1 = *reinterpret_cast<const uint4*>(tile + rr * 128 + (((2 * pc + 1) ^ (rr & 7)) << 4));
+            uint4 h;
+            h.x = pack16<kFp16>(__uint_as_float(a0.x), __uint_as_float(a0.y));
+            h.y = pack16<kFp16>(__uint_as_float(a0.z), __uint_as_float(a0.w));
+            h.z = pack16<kFp16>(__uint_as_float(a1.x), __uint_as_float(a1.y));
+            h.w = pack16<kFp16>(__uint_as_float(a1.z), __uint_as_float(a1.w));
+            stg16(reinterpret_cast<uint16_t*>(ep.out16) + size_t(dst) * ep.ld16 + n_blk * BN + c0 + pc * 8, h);
+          }
+        }
+        if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        ++res_tiles;
+        // residual tiles of this CTA's next work unit: the TMA stores above must have read the slots first
+        __syncwarp();
+        if (lane == 0 && unit + unit_stride < num_units) {
+          bulk_wait_read<0>();
+          fetch_resid(unit_m(unit + unit_stride), unit_n(unit + unit_stride));
+        }
         continue;
       }
 
@@ -538,7 +694,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
 
-  if constexpr (Cfg::TMA16) {
+  if constexpr (Cfg::TMA16 || Cfg::RESTMA) {
     if (warp >= 2 && lane == 0) bulk_wait_all();   // smem must outlive the bulk stores
   }
   tc_fence_before();
