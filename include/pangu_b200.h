@@ -141,9 +141,65 @@ int pangu_l1_loss(const float* out_upper, const float* out_surface, const float*
 /* Generic nn.Linear forward used by the stand-alone module API (EarthAttention3D.linear2,
  * Mlp.linear1/2 outside the fused block path) and by the unit tests of the tcgen05 GEMM engine:
  * out = a16 [M,K] * w16 [N,K]^T + bias.  gelu == 0: fp32 out32 and 16-bit out16 (both required),
- * N % 192 == 0.  gelu != 0: exact-erf GELU applied, 16-bit out16 only, N % 256 == 0.  K % 64 == 0. */
+ * N % 192 == 0.  gelu != 0: exact-erf GELU applied, 16-bit out16 only, N % 256 == 0.  K % 64 == 0.
+ * gelu == 0 with out32 == NULL: 16-bit out16 only, N % 256 == 0 (pre-activation recompute of the backward). */
 int pangu_linear(const void* a16, const void* w16, const float* bias, float* out32, void* out16,
                  int M, int N, int K, int gelu, int fp16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward pass.  The reference obtains these through autograd over
+ * models/layers.py (loss.backward(), models/pangu_sample.py:69); here every gradient is a hand-written
+ * kernel.  Parameter gradients are ACCUMULATED into caller-provided fp32 buffers (the .grad semantics).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* fp32 [rows, cols] -> 16-bit TRANSPOSED copy [cols_pad, rows_pad] (zero padded): the B operands
+ * (W^T) of the dgrad GEMMs, from the (out, in) weights of the state_dict. */
+int pangu_cast16_t(const float* src, void* dst, int rows, int cols, int rows_pad, int cols_pad, int fp16, void* stream);
+
+/* Data-gradient GEMM  out[M, N] = a16[M, K] * wt16[N, K]^T (+ bias),  wt16 = transposed weight copy:
+ *   kind 0: out32 = (resid32 ? resid32 : 0) + acc, identity rows                         (N % 192 == 0)
+ *   kind 1: out16 row-major                                                                (N % 256 == 0)
+ *   kind 2: a16 rows are in WINDOW order (roll state `roll`): out32[token] = resid32[token] + acc,
+ *           pad rows dropped -- backward of pad + roll + window partition (models/layers.py:188-221)
+ *   kind 3: a16 rows natural; out16 rows scattered to WINDOW order (pad rows are not written) --
+ *           backward of window reverse + un-roll + crop (models/layers.py:227-243)
+ * K % 64 == 0.  (Z, H, W) is the token grid of the row maps (kinds 2, 3). */
+int pangu_dgrad(const void* a16, const void* wt16, const float* bias, const float* resid32, float* out32, void* out16,
+                int M, int N, int K, int kind, int Z, int H, int W, int roll, int fp16, void* stream);
+
+/* Weight-gradient GEMM  dw[n, k_off + k] += alpha * sum_m dy16[m, n] * x16[m, k]  for n < N, k < K
+ * (autograd of F.linear w.r.t. the weight).  dy16 [M, ld_dy], x16 [M, ld_x] 16-bit; dw fp32 [N, ldw]. */
+int pangu_wgrad(const void* dy16, int ld_dy, const void* x16, int ld_x, float* dw, int ldw, int k_off,
+                int M, int N, int K, float alpha, int fp16, void* stream);
+
+/* Bias gradient: out[n] += alpha * sum_m src16[m, n], n < n_valid (N columns scanned, N % 8 == 0). */
+int pangu_colsum16(const void* src16, int ld, float* out, int M, int N, int n_valid, float alpha, int fp16, void* stream);
+
+/* LayerNorm backward (nn.LayerNorm, eps 1e-5; models/layers.py:141-142, 429, 472).  y: pre-norm values,
+ * g: fp32 gradient w.r.t. the normalised output [rows, C], scale: DropPath factor of the branch.
+ *   mode 0: y [rows, C], dx16 [rows, C]                                   (block norm1 / norm2; C 192 | 384)
+ *   mode 1: UpSample.norm: rows = high-res tokens, y = linear1 output [T2, 4C] before the pixel shuffle,
+ *           dx16 [T2, 4C] in the same layout (cropped positions are not written)        (C 192)
+ *   mode 2: DownSample.norm: rows = low-res tokens, y = high-res stream x [T, C/4] fp32 (2x2 merge + pad
+ *           recomputed), dx32 [T, C/4] is ADDED to                                      (C 768)
+ * dgamma / dbeta [C] are accumulated into. */
+int pangu_layernorm_bwd(const float* y, const float* g, const float* gamma, void* dx16, float* dx32,
+                        float* dgamma, float* dbeta, int rows, int C, int mode, int Z, int H, int W,
+                        float scale, int fp16, void* stream);
+
+/* GELU backward in place: dh16[i] *= gelu'(pre16[i]) (exact erf form, nn.GELU; models/layers.py:261). */
+int pangu_gelu_bwd(void* dh16, const void* pre16, long long n, int fp16, void* stream);
+
+/* Backward of pangu_window_attention (autograd of models/layers.py:368-415).  datt16w: [Tp, C] gradient of the
+ * merged-head attention output in WINDOW order (pad rows zero); dqkv16: [Tp, 3C] window order, column
+ * s*C + head*32 + d, gradient w.r.t. the un-scaled linear1 output; dbias [types, heads, 144, 144] accumulated. */
+int pangu_window_attention_bwd(const void* qkv16, const void* datt16w, const float* earth_bias, void* dqkv16,
+                               float* dbias, int Z, int H, int W, int C, int heads, int roll, int fp16, void* stream);
+
+/* Backward of the un-patchify + crop of PatchRecovery_pretrain (models/layers.py:519-545): output-field
+ * gradients -> dy_upper [7*Hh*Ww, 192] (features >= 160 zero), dy_surface [Hh*Ww, 128] (features >= 64 zero). */
+int pangu_recover_grad_gather(const float* d_upper, const float* d_surface, void* dy_upper, void* dy_surface,
+                              int lat, int lon, int fp16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -133,39 +133,41 @@ def window_attention(xw: Tensor, p: Dict[str, Tensor], pre: str, heads: int,
 
 
 def earth_block(x: Tensor, p: Dict[str, Tensor], pre: str, Z: int, H: int, W: int,
-                heads: int, roll: bool, drop_scale: float = 1.0) -> Tensor:
+                heads: int, roll: bool, drop_scale=1.0) -> Tensor:
     """``EarthSpecificBlock.forward`` (models/layers.py:183-253), eval-mode DropPath.
 
     ``x``: [1, Z*H*W, C].  ``drop_scale`` multiplies both residual branches (a DropPath
     draw for batch 1 is a single Bernoulli/keep scalar, so training-mode parity can be
-    exercised by passing 0 or 1/keep)."""
+    exercised by passing 0 or 1/keep; a pair ``(s1, s2)`` gives the two DropPath draws of
+    models/layers.py:250-251 separately)."""
+    s1, s2 = drop_scale if isinstance(drop_scale, (tuple, list)) else (drop_scale, drop_scale)
     C = x.shape[-1]
     src = window_source_index(Z, H, W, roll)           # [nLon,types,144]
     flat = src.reshape(-1)
     xt = x.reshape(-1, C)
-    xw = torch.zeros(flat.numel(), C, dtype=x.dtype)
     real = flat >= 0
-    xw[real] = xt[flat[real]]
+    xw = torch.zeros(flat.numel(), C, dtype=x.dtype).index_put((real.nonzero().squeeze(1),), xt[flat[real]])
     xw = xw.view(*src.shape, C)
     mask = shift_mask(Z, H) if roll else None
     aw = window_attention(xw, p, pre + "attention.", heads, mask).reshape(-1, C)
     # window reverse + un-roll + crop == scatter through the same map; pad rows dropped
-    y = torch.empty_like(xt)
-    y[flat[real]] = aw[real]
+    y = torch.zeros_like(xt).index_put((flat[real],), aw[real])
     y = F.layer_norm(y, (C,), p[pre + "norm1.weight"], p[pre + "norm1.bias"], 1e-5)
-    xt = xt + drop_scale * y
+    xt = xt + s1 * y
     h = F.linear(xt, p[pre + "linear.linear1.weight"], p[pre + "linear.linear1.bias"])
     h = F.gelu(h)                                       # exact erf GELU (nn.GELU default)
     h = F.linear(h, p[pre + "linear.linear2.weight"], p[pre + "linear.linear2.bias"])
     h = F.layer_norm(h, (C,), p[pre + "norm2.weight"], p[pre + "norm2.bias"], 1e-5)
-    return (xt + drop_scale * h).view(1, -1, C)
+    return (xt + s2 * h).view(1, -1, C)
 
 
-def earth_layer(x, p, layer: int, Z, H, W, depth: int, heads: int) -> Tensor:
-    """``EarthSpecificLayer.forward`` (models/layers.py:110-125): roll every odd block."""
+def earth_layer(x, p, layer: int, Z, H, W, depth: int, heads: int, drop_scales=None) -> Tensor:
+    """``EarthSpecificLayer.forward`` (models/layers.py:110-125): roll every odd block.
+    ``drop_scales``: optional per-block DropPath factors (train mode), else 1 (eval)."""
     for i in range(depth):
         pre = f"layers.EarthSpecificLayer{layer}.blocks.EarthSpecificBlock{i}."
-        x = earth_block(x, p, pre, Z, H, W, heads, roll=(i % 2 == 1))
+        x = earth_block(x, p, pre, Z, H, W, heads, roll=(i % 2 == 1),
+                        drop_scale=1.0 if drop_scales is None else drop_scales[i])
     return x
 
 
@@ -237,6 +239,15 @@ def forward(p: Dict[str, Tensor], upper, surface, statistics, maps, const_h,
     """``PanguModel.forward`` (models/pangu_model.py:50-87).  Generic in longitude: the
     number of longitude tokens ``lon/4`` must be a multiple of 24.  ``taps`` (optional
     dict) receives the residual stream after every stage."""
+    with torch.no_grad():
+        return forward_train(p, upper, surface, statistics, maps, const_h, taps=taps)
+
+
+def forward_train(p: Dict[str, Tensor], upper, surface, statistics, maps, const_h,
+                  drop_scales=None, taps: Optional[dict] = None) -> Tuple[Tensor, Tensor]:
+    """Differentiable ``PanguModel.forward`` (autograd records it when ``p`` holds leaves that
+    require grad): the training path of models/pangu_sample.py:52.  ``drop_scales``: 16 pairs
+    ``(s1, s2)`` of DropPath factors in block order (None = eval mode)."""
     lat, lon = surface.shape[-2], surface.shape[-1]
     Z, H, W = 8, (lat + 3) // 4, lon // 4
     H2, W2 = (H + 1) // 2, W // 2
@@ -245,17 +256,29 @@ def forward(p: Dict[str, Tensor], upper, surface, statistics, maps, const_h,
         if taps is not None:
             taps[name] = t
 
-    with torch.no_grad():
-        x = patch_embed(upper, surface, statistics, maps, const_h, p); tap("embed", x)
-        x = earth_layer(x, p, 0, Z, H, W, DEPTHS[0], HEADS[0]); tap("layer0", x)
-        skip = x
-        x = down_sample(x, p, Z, H, W); tap("down", x)
-        x = earth_layer(x, p, 1, Z, H2, W2, DEPTHS[1], HEADS[1]); tap("layer1", x)
-        x = earth_layer(x, p, 2, Z, H2, W2, DEPTHS[2], HEADS[2]); tap("layer2", x)
-        x = up_sample(x, p, Z, H2, W2, H); tap("up", x)
-        x = earth_layer(x, p, 3, Z, H, W, DEPTHS[3], HEADS[3]); tap("layer3", x)
-        x = torch.cat((skip, x), dim=-1)
-        return patch_recover(x, p, Z, H, W, lat)
+    ds = [None] * 4 if drop_scales is None else [drop_scales[0:2], drop_scales[2:8], drop_scales[8:14], drop_scales[14:16]]
+    x = patch_embed(upper, surface, statistics, maps, const_h, p); tap("embed", x)
+    x = earth_layer(x, p, 0, Z, H, W, DEPTHS[0], HEADS[0], ds[0]); tap("layer0", x)
+    skip = x
+    x = down_sample(x, p, Z, H, W); tap("down", x)
+    x = earth_layer(x, p, 1, Z, H2, W2, DEPTHS[1], HEADS[1], ds[1]); tap("layer1", x)
+    x = earth_layer(x, p, 2, Z, H2, W2, DEPTHS[2], HEADS[2], ds[2]); tap("layer2", x)
+    x = up_sample(x, p, Z, H2, W2, H); tap("up", x)
+    x = earth_layer(x, p, 3, Z, H, W, DEPTHS[3], HEADS[3], ds[3]); tap("layer3", x)
+    x = torch.cat((skip, x), dim=-1)
+    return patch_recover(x, p, Z, H, W, lat)
+
+
+def loss_and_grads(p: Dict[str, Tensor], upper, surface, statistics, maps, const_h, tgt_upper, tgt_surface,
+                   drop_scales=None):
+    """One training step's loss and parameter gradients (models/pangu_sample.py:52-69): forward,
+    ``normData`` of the physical targets, weighted L1, ``loss.backward()``.  Returns (loss, {name: grad})."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    ou, os_ = forward_train(leaves, upper, surface, statistics, maps, const_h, drop_scales)
+    tu, ts = norm_data(tgt_upper, tgt_surface, output_statistics(statistics))
+    loss = weighted_l1_loss(ou, os_, tu, ts)
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in leaves.items()}
 
 
 # --------------------------------------------------------------------------------------

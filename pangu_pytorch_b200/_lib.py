@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes
 import os
 import re
-from ctypes import c_char_p, c_float, c_int, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpangu_b200.so")
@@ -32,6 +32,14 @@ SIGNATURES = {
     "pangu_linear": [_P] * 5 + [_I, _I, _I, _I, _I, _P],
     "pangu_denorm_fields": [_P] * 6 + [_I, _I, _P],
     "pangu_l1_loss": [_P] * 14 + [_I, _I, _P],
+    "pangu_cast16_t": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "pangu_dgrad": [_P] * 6 + [_I] * 9 + [_P],
+    "pangu_wgrad": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    "pangu_colsum16": [_P, _I, _P, _I, _I, _I, _F, _I, _P],
+    "pangu_layernorm_bwd": [_P] * 7 + [_I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "pangu_gelu_bwd": [_P, _P, c_longlong, _I, _P],
+    "pangu_window_attention_bwd": [_P] * 5 + [_I] * 7 + [_P],
+    "pangu_recover_grad_gather": [_P] * 4 + [_I, _I, _I, _P],
 }
 
 _lib = None

@@ -1,0 +1,227 @@
+// Memory-bound kernels of the backward pass (reference: autograd through models/layers.py,
+// driven by models/pangu_sample.py:57-71):
+//   * ln_bwd_kernel     LayerNorm backward (dx, d gamma, d beta) with the row maps of the plain block
+//                       LayerNorms, UpSample.norm (pixel-shuffle rows) and DownSample.norm (2x2 merge rows)
+//   * gelu_bwd_kernel   d pre = d hidden * gelu'(pre)       (exact erf GELU, models/layers.py:261)
+//   * colsum16_kernel   bias gradients: column sums of a 16-bit [M, N] gradient matrix
+//   * cast16_t_kernel   fp32 [R, C] -> 16-bit [C, R_pad] transposed weight copies (B operands of the dgrad GEMMs)
+#pragma once
+#include "common.cuh"
+#include "geometry.cuh"
+
+namespace pg {
+
+enum LnBwdMode { LNB_IDENT = 0, LNB_UP = 1, LNB_DOWN = 2 };
+
+struct LnBwdArgs {
+  const float* y;       // pre-LayerNorm values.  IDENT: [rows, C]; UP: upsample.linear1 output [T2, 4C]; DOWN: x_hi [T, C/4]
+  const float* g;       // gradient w.r.t. the LayerNorm output, [rows, C] fp32
+  const float* gamma;   // [C]
+  void* dx16;           // IDENT: [rows, C] 16-bit; UP: [T2, 4C] 16-bit (cropped positions are never written)
+  float* dx32;          // DOWN: [T, C/4] fp32, read-modify-write (+=)
+  float* dgamma;        // [C] += scale * sum_rows g * xhat
+  float* dbeta;         // [C] += scale * sum_rows g
+  int rows, C;
+  int Z, H, W;          // UP / DOWN: HIGH-resolution token grid
+  float scale;          // DropPath factor of the branch (1 in eval)
+  float eps;
+};
+
+// One warp per row, grid-stride over rows; lane owns float4 pieces q = lane + 32*i of the row.
+// dx = rstd * (gh - mean(gh) - xhat * mean(gh * xhat)),  gh = scale * g * gamma,  xhat = (y - mean) * rstd
+template <bool kFp16, int kMode, int kC>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
+  constexpr int NP = (kC / 4 + 31) / 32;           // float4 pieces per lane
+  __shared__ float s_dg[kC], s_db[kC];
+  for (int i = threadIdx.x; i < kC; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  float4 gam[NP], adg[NP], adb[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int q = lane + 32 * i;
+    gam[i] = q < kC / 4 ? *reinterpret_cast<const float4*>(a.gamma + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    adg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    adb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int W2 = a.W / 2, H2 = (a.H + 1) / 2;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.rows; row += warps_total) {
+    // ---- addressing of this row
+    const float* ysrc = nullptr;
+    size_t out_off = 0;          // element offset of the row in dx16 (IDENT / UP)
+    int z = 0, h2 = 0, w2 = 0;
+    if constexpr (kMode == LNB_IDENT) {
+      ysrc = a.y + size_t(row) * kC;
+      out_off = size_t(row) * kC;
+    } else if constexpr (kMode == LNB_UP) {
+      const int w = row % a.W, h = (row / a.W) % a.H, zz = row / (a.W * a.H);
+      const size_t tok2 = size_t(zz * H2 + (h >> 1)) * W2 + (w >> 1);
+      const int grp = (h & 1) * 2 + (w & 1);
+      out_off = tok2 * (4 * kC) + grp * kC;
+      ysrc = a.y + out_off;
+    } else {
+      w2 = row % W2; h2 = (row / W2) % H2; z = row / (W2 * H2);
+    }
+    float4 yv[NP], gv[NP];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int q = lane + 32 * i;
+      yv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < kC / 4) {
+        if constexpr (kMode == LNB_DOWN) {
+          constexpr int QH = kC / 8;               // float4 pieces per dh half-row (two adjacent tokens)
+          const int dh = q / QH, r = q % QH;
+          const int h = 2 * h2 + dh;
+          if (h < a.H) yv[i] = *reinterpret_cast<const float4*>(a.y + (size_t(z * a.H + h) * a.W + 2 * w2) * (kC / 4) + r * 4);
+        } else {
+          yv[i] = *reinterpret_cast<const float4*>(ysrc + q * 4);
+        }
+        gv[i] = *reinterpret_cast<const float4*>(a.g + size_t(row) * kC + q * 4);
+      }
+      s += (yv[i].x + yv[i].y) + (yv[i].z + yv[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / kC);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int q = lane + 32 * i;
+      if (q < kC / 4) {
+        yv[i].x -= mean; yv[i].y -= mean; yv[i].z -= mean; yv[i].w -= mean;
+        ss += (yv[i].x * yv[i].x + yv[i].y * yv[i].y) + (yv[i].z * yv[i].z + yv[i].w * yv[i].w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * (1.0f / kC) + a.eps);
+    float m1 = 0.f, m2 = 0.f;      // sum gh, sum gh * xhat
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      // xhat in yv, scaled upstream gradient in gv, gh = g * gamma
+      yv[i].x *= rstd; yv[i].y *= rstd; yv[i].z *= rstd; yv[i].w *= rstd;
+      gv[i].x *= a.scale; gv[i].y *= a.scale; gv[i].z *= a.scale; gv[i].w *= a.scale;
+      adg[i].x += gv[i].x * yv[i].x; adg[i].y += gv[i].y * yv[i].y; adg[i].z += gv[i].z * yv[i].z; adg[i].w += gv[i].w * yv[i].w;
+      adb[i].x += gv[i].x; adb[i].y += gv[i].y; adb[i].z += gv[i].z; adb[i].w += gv[i].w;
+      gv[i].x *= gam[i].x; gv[i].y *= gam[i].y; gv[i].z *= gam[i].z; gv[i].w *= gam[i].w;
+      m1 += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+      m2 += (gv[i].x * yv[i].x + gv[i].y * yv[i].y) + (gv[i].z * yv[i].z + gv[i].w * yv[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    }
+    m1 *= (1.0f / kC); m2 *= (1.0f / kC);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int q = lane + 32 * i;
+      if (q >= kC / 4) continue;
+      const float d0 = rstd * (gv[i].x - m1 - yv[i].x * m2), d1 = rstd * (gv[i].y - m1 - yv[i].y * m2);
+      const float d2 = rstd * (gv[i].z - m1 - yv[i].z * m2), d3 = rstd * (gv[i].w - m1 - yv[i].w * m2);
+      if constexpr (kMode == LNB_DOWN) {
+        constexpr int QH = kC / 8;
+        const int dh = q / QH, r = q % QH;
+        const int h = 2 * h2 + dh;
+        if (h < a.H) {
+          float4* p = reinterpret_cast<float4*>(a.dx32 + (size_t(z * a.H + h) * a.W + 2 * w2) * (kC / 4) + r * 4);
+          float4 o = *p;
+          o.x += d0; o.y += d1; o.z += d2; o.w += d3;
+          *p = o;
+        }
+      } else {
+        reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.dx16) + out_off)[q] =
+            make_uint2(pack16<kFp16>(d0, d1), pack16<kFp16>(d2, d3));
+      }
+    }
+  }
+  // ---- parameter gradients: lanes of every warp own the same columns -> shared atomics, then one global atomic per column
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int q = lane + 32 * i;
+    if (q >= kC / 4) continue;
+    atomicAdd(&s_dg[q * 4 + 0], adg[i].x); atomicAdd(&s_dg[q * 4 + 1], adg[i].y);
+    atomicAdd(&s_dg[q * 4 + 2], adg[i].z); atomicAdd(&s_dg[q * 4 + 3], adg[i].w);
+    atomicAdd(&s_db[q * 4 + 0], adb[i].x); atomicAdd(&s_db[q * 4 + 1], adb[i].y);
+    atomicAdd(&s_db[q * 4 + 2], adb[i].z); atomicAdd(&s_db[q * 4 + 3], adb[i].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kC; i += blockDim.x) {
+    if (a.dgamma) atomicAdd(a.dgamma + i, s_dg[i]);
+    if (a.dbeta) atomicAdd(a.dbeta + i, s_db[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// d pre = d hidden * gelu'(pre),  gelu'(x) = Phi(x) + x phi(x)   (in place on dh); 8 elements per thread
+template <bool kFp16>
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(uint16_t* __restrict__ dh, const uint16_t* __restrict__ pre, size_t n8) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
+    uint4 d = reinterpret_cast<const uint4*>(dh)[i];
+    const uint4 p = ldg_nc16(reinterpret_cast<const uint4*>(pre) + i);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(&d);
+    const uint32_t* pw = reinterpret_cast<const uint32_t*>(&p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float x0 = unpack16_lo<kFp16>(pw[k]), x1 = unpack16_hi<kFp16>(pw[k]);
+      float g0 = unpack16_lo<kFp16>(dw[k]), g1 = unpack16_hi<kFp16>(dw[k]);
+      const float c0 = 0.5f * (1.0f + erff(x0 * 0.70710678118654752440f)) + x0 * 0.3989422804014327f * __expf(-0.5f * x0 * x0);
+      const float c1 = 0.5f * (1.0f + erff(x1 * 0.70710678118654752440f)) + x1 * 0.3989422804014327f * __expf(-0.5f * x1 * x1);
+      dw[k] = pack16<kFp16>(g0 * c0, g1 * c1);
+    }
+    reinterpret_cast<uint4*>(dh)[i] = d;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// out[n] += alpha * sum_m src[m][n] for n < n_valid.  src: 16-bit [M, ld]; N = columns scanned (multiple of 8).
+template <bool kFp16>
+__global__ void __launch_bounds__(256) colsum16_kernel(const uint16_t* __restrict__ src, float* __restrict__ out, int M, int N,
+                                                       int ld, int n_valid, float alpha) {
+  extern __shared__ float s_acc[];               // [N]
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int tpr = N / 8;                         // threads per row
+  const int rpi = blockDim.x / tpr;              // rows per iteration of this block
+  const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < rpi) {
+    for (int m = blockIdx.x * rpi + rl; m < M; m += gridDim.x * rpi) {
+      const uint4 v = ldg_nc16(src + size_t(m) * ld + cg * 8);
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[2 * k] += unpack16_lo<kFp16>(w[k]);
+        acc[2 * k + 1] += unpack16_hi<kFp16>(w[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_acc[cg * 8 + k], acc[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_valid; i += blockDim.x) atomicAdd(out + i, alpha * s_acc[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// dst[c][r] = cast(src[r][c]) for r < R, c < C; dst is [C_pad rows][R_pad] with zero padding.
+template <bool kFp16>
+__global__ void __launch_bounds__(256) cast16_t_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int R, int C,
+                                                       int R_pad, int C_pad) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + tx;
+    tile[k][tx] = (r < R && c < C) ? src[size_t(r) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k, r = r0 + tx;
+    if (c < C_pad && r < R_pad) dst[size_t(c) * R_pad + r] = cvt16<kFp16>(tile[tx][k]);
+  }
+}
+
+}  // namespace pg

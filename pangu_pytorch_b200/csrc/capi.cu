@@ -10,9 +10,12 @@
 
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "attention_bwd.cuh"
+#include "backward.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "mlp_fused.cuh"
+#include "wgrad.cuh"
 
 using namespace pg;
 
@@ -155,6 +158,20 @@ struct CfgRecU : CfgBase {     // _output_layer.conv: bias + un-patchify + crop 
 struct CfgRecS : CfgBase {     // _output_layer.conv_surface
   static constexpr int BN = 64, UN = 64, STAGES = 4;
   static constexpr int RECOVER = RC_SURFACE;
+};
+
+struct CfgLin16 : CfgBase {    // (bias) -> 16-bit row-major (pre-activation recompute, d hidden)
+  static constexpr int BN = 256, UN = 256, STAGES = 3;
+  static constexpr bool OUT16 = true, TMA16 = true;
+  static constexpr int CLUSTER = 2;
+};
+struct CfgAcc192 : CfgBase {   // fp32 out = residual + acc (dgrad accumulating into the gradient stream), row maps
+  static constexpr int BN = 192, UN = 192, STAGES = 4;
+  static constexpr bool RESID = true, OUT32 = true;
+};
+struct CfgOut16Map : CfgBase { // 16-bit out, destination row map (dgrad scattered into window order)
+  static constexpr int BN = 192, UN = 192, STAGES = 4;
+  static constexpr bool OUT16 = true;
 };
 
 struct GemmOperands {
@@ -622,6 +639,208 @@ extern "C" int pangu_linear(const void* a16, const void* w16, const float* bias,
     PG_REQUIRE(out16 != nullptr && N % 256 == 0, "pangu_linear(gelu): needs a 16-bit output and N %% 256 == 0");
     return launch_gemm<CfgMLP1>(o, ep, fp16, s);
   }
+  if (out32 == nullptr) {
+    PG_REQUIRE(out16 != nullptr && N % 256 == 0, "pangu_linear(16-bit only): needs a 16-bit output and N %% 256 == 0");
+    return launch_gemm<CfgLin16>(o, ep, fp16, s);
+  }
   PG_REQUIRE(out32 != nullptr && out16 != nullptr && N % 192 == 0, "pangu_linear: needs both outputs and N %% 192 == 0");
   return launch_gemm<CfgPlain192>(o, ep, fp16, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// backward pass
+// ---------------------------------------------------------------------------------------
+extern "C" int pangu_cast16_t(const float* src, void* dst, int rows, int cols, int rows_pad, int cols_pad, int fp16,
+                              void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(rows > 0 && cols > 0 && rows_pad >= rows && cols_pad >= cols, "bad cast16_t shape");
+  dim3 grid((cols_pad + 31) / 32, (rows_pad + 31) / 32);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (fp16) cast16_t_kernel<true><<<grid, 256, 0, s>>>(src, static_cast<uint16_t*>(dst), rows, cols, rows_pad, cols_pad);
+  else cast16_t_kernel<false><<<grid, 256, 0, s>>>(src, static_cast<uint16_t*>(dst), rows, cols, rows_pad, cols_pad);
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pangu_dgrad(const void* a16, const void* wt16, const float* bias, const float* resid32, float* out32,
+                           void* out16, int M, int N, int K, int kind, int Z, int H, int W, int roll, int fp16,
+                           void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(kind >= 0 && kind <= 3, "dgrad: kind must be 0..3");
+  GemmOperands o{a16, uint64_t(K), nullptr, 0, K, 0, wt16, uint64_t(K), M, N};
+  EpiArgs ep = epi_defaults();
+  ep.bias = bias;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (kind == 1) {
+    PG_REQUIRE(out16 != nullptr && N % 256 == 0, "dgrad(kind 1): needs a 16-bit output and N %% 256 == 0");
+    ep.out16 = out16; ep.ld16 = N;
+    return launch_gemm<CfgLin16>(o, ep, fp16, s);
+  }
+  PG_REQUIRE(N % 192 == 0, "dgrad: N must be a multiple of 192");
+  if (kind == 3) {
+    PG_REQUIRE(out16 != nullptr, "dgrad(kind 3): needs a 16-bit output");
+    PG_TRY(check_grid(Z, H, W, N, 0));
+    PG_REQUIRE(M == Z * H * W, "dgrad(kind 3): M must be the token count");
+    ep.Z = Z; ep.H = H; ep.W = W;
+    ep.out16 = out16; ep.ld16 = N;
+    ep.dstmap = DM_TOK2WIN; ep.roll_out = roll ? 1 : 0;
+    return launch_gemm<CfgOut16Map>(o, ep, fp16, s);
+  }
+  PG_REQUIRE(out32 != nullptr, "dgrad: needs an fp32 output");
+  ep.out32 = out32; ep.ld32 = N; ep.resid = resid32;
+  if (resid32 == nullptr) ep.debug |= 1;      // no residual: plain fp32 store
+  if (kind == 2) {
+    PG_TRY(check_grid(Z, H, W, N, 0));
+    const Geo g = make_geo(Z, H, W);
+    PG_REQUIRE(M == g.nLon * g.types * 144, "dgrad(kind 2): M must be the window-padded row count");
+    ep.Z = Z; ep.H = H; ep.W = W;
+    ep.rowmap = RM_WIN2TOK; ep.roll_in = roll ? 1 : 0;
+  }
+  return launch_gemm<CfgAcc192>(o, ep, fp16, s);
+}
+
+static int make_map_cols(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems) {
+  PG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (pitch_elems * 2) % 16 == 0 && cols % 8 == 0,
+             "wgrad operand not TMA-addressable (base %p, pitch %llu)", base, (unsigned long long)pitch_elems);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {64, WG_TOK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled(wgrad) failed (%d)", int(r));
+  return 0;
+}
+
+extern "C" int pangu_wgrad(const void* dy16, int ld_dy, const void* x16, int ld_x, float* dw, int ldw, int k_off,
+                           int M, int N, int K, float alpha, int fp16, void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(M > 0 && N > 0 && K > 0 && N % 8 == 0 && K % 4 == 0, "wgrad: bad shape (M=%d N=%d K=%d)", M, N, K);
+  PG_REQUIRE((reinterpret_cast<uintptr_t>(dw) & 15) == 0 && ldw % 4 == 0 && k_off % 4 == 0, "wgrad: dW not 16 B aligned");
+  CUtensorMap mdy, mx;
+  PG_TRY(make_map_cols(&mdy, dy16, M, uint64_t((N + 7) / 8 * 8), ld_dy));
+  PG_TRY(make_map_cols(&mx, x16, M, uint64_t((K + 7) / 8 * 8), ld_x));
+  WgradArgs a;
+  a.dw = dw; a.ldw = ldw; a.k_off = k_off; a.N = N; a.K = K; a.alpha = alpha;
+  const int Kp = (K + 63) / 64 * 64;
+  a.KB = Kp % 192 == 0 ? 192 : (Kp % 256 == 0 ? 256 : (Kp % 128 == 0 ? 128 : 64));
+  a.n_tiles = (N + 127) / 128;
+  a.k_tiles = Kp / a.KB;
+  a.chunks = (M + WG_TOK - 1) / WG_TOK;
+  int splits = (2 * g_num_sms) / (a.n_tiles * a.k_tiles);
+  if (splits > a.chunks / 4) splits = a.chunks / 4;
+  if (splits < 1) splits = 1;
+  a.splits = splits;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = a.n_tiles * a.k_tiles * a.splits;
+  static bool attr_done[2] = {false, false};
+  if (fp16) {
+    if (!attr_done[1]) { PG_CUDA(cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES)); attr_done[1] = true; }
+    wgrad_kernel<true><<<grid, WG_THREADS, WG_SMEM_BYTES, s>>>(mdy, mx, a);
+  } else {
+    if (!attr_done[0]) { PG_CUDA(cudaFuncSetAttribute(wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES)); attr_done[0] = true; }
+    wgrad_kernel<false><<<grid, WG_THREADS, WG_SMEM_BYTES, s>>>(mdy, mx, a);
+  }
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pangu_colsum16(const void* src16, int ld, float* out, int M, int N, int n_valid, float alpha, int fp16,
+                              void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && N <= 2048 && n_valid <= N && ld % 8 == 0, "colsum16: bad shape");
+  PG_REQUIRE((reinterpret_cast<uintptr_t>(src16) & 15) == 0, "colsum16: source not 16 B aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rpi = 256 / (N / 8);
+  int grid = (M + rpi * 64 - 1) / (rpi * 64);
+  if (grid > 4 * g_num_sms) grid = 4 * g_num_sms;
+  if (grid < 1) grid = 1;
+  if (fp16) colsum16_kernel<true><<<grid, 256, N * sizeof(float), s>>>(static_cast<const uint16_t*>(src16), out, M, N, ld, n_valid, alpha);
+  else colsum16_kernel<false><<<grid, 256, N * sizeof(float), s>>>(static_cast<const uint16_t*>(src16), out, M, N, ld, n_valid, alpha);
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <bool kFp16>
+static int launch_ln_bwd(const LnBwdArgs& a, int mode, cudaStream_t s) {
+  int grid = (a.rows + 7) / 8;                 // 8 warps (rows) per block, grid-stride
+  if (grid > 8 * g_num_sms) grid = 8 * g_num_sms;
+  if (mode == LNB_IDENT && a.C == 192) ln_bwd_kernel<kFp16, LNB_IDENT, 192><<<grid, 256, 0, s>>>(a);
+  else if (mode == LNB_IDENT && a.C == 384) ln_bwd_kernel<kFp16, LNB_IDENT, 384><<<grid, 256, 0, s>>>(a);
+  else if (mode == LNB_UP && a.C == 192) ln_bwd_kernel<kFp16, LNB_UP, 192><<<grid, 256, 0, s>>>(a);
+  else if (mode == LNB_DOWN && a.C == 768) ln_bwd_kernel<kFp16, LNB_DOWN, 768><<<grid, 256, 0, s>>>(a);
+  else return fail(-1, "layernorm_bwd: unsupported (mode %d, C %d)", mode, a.C);
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pangu_layernorm_bwd(const float* y, const float* g, const float* gamma, void* dx16, float* dx32,
+                                   float* dgamma, float* dbeta, int rows, int C, int mode, int Z, int H, int W,
+                                   float scale, int fp16, void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(rows > 0 && y && g && gamma, "layernorm_bwd: null argument");
+  PG_REQUIRE(mode == LNB_DOWN ? dx32 != nullptr : dx16 != nullptr, "layernorm_bwd: missing output");
+  if (mode == LNB_UP) PG_REQUIRE(rows == Z * H * W && W % 2 == 0, "layernorm_bwd(up): rows must be the high-res token count");
+  if (mode == LNB_DOWN) PG_REQUIRE(rows == Z * ((H + 1) / 2) * (W / 2), "layernorm_bwd(down): rows must be the low-res token count");
+  LnBwdArgs a;
+  a.y = y; a.g = g; a.gamma = gamma; a.dx16 = dx16; a.dx32 = dx32; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.rows = rows; a.C = C; a.Z = Z; a.H = H; a.W = W; a.scale = scale; a.eps = 1e-5f;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return fp16 ? launch_ln_bwd<true>(a, mode, s) : launch_ln_bwd<false>(a, mode, s);
+}
+
+extern "C" int pangu_gelu_bwd(void* dh16, const void* pre16, long long n, int fp16, void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(n > 0 && n % 8 == 0, "gelu_bwd: element count must be a positive multiple of 8");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n8 = size_t(n) / 8;
+  const int grid = int((n8 + 255) / 256 < size_t(16 * g_num_sms) ? (n8 + 255) / 256 : size_t(16 * g_num_sms));
+  if (fp16) gelu_bwd_kernel<true><<<grid, 256, 0, s>>>(static_cast<uint16_t*>(dh16), static_cast<const uint16_t*>(pre16), n8);
+  else gelu_bwd_kernel<false><<<grid, 256, 0, s>>>(static_cast<uint16_t*>(dh16), static_cast<const uint16_t*>(pre16), n8);
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pangu_window_attention_bwd(const void* qkv16, const void* datt16w, const float* earth_bias, void* dqkv16,
+                                          float* dbias, int Z, int H, int W, int C, int heads, int roll, int fp16,
+                                          void* stream) {
+  PG_TRY(ensure_init());
+  PG_TRY(check_grid(Z, H, W, C, heads));
+  const Geo g = make_geo(Z, H, W);
+  AttnBwdArgs a;
+  a.qkv = qkv16; a.datt = datt16w; a.bias = earth_bias; a.dqkv = dqkv16; a.dbias = dbias;
+  a.C = C; a.heads = heads; a.types = g.types; a.nLon = g.nLon; a.nH = g.nH; a.roll = roll ? 1 : 0;
+  a.plane_rows = sh_rows_padded(g.nLon * g.types * 144);
+  a.q_scale = 0.17677669529663687f;
+  PG_REQUIRE((reinterpret_cast<uintptr_t>(qkv16) & 15) == 0 && (reinterpret_cast<uintptr_t>(datt16w) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(earth_bias) & 7) == 0 && (reinterpret_cast<uintptr_t>(dqkv16) & 3) == 0,
+             "attention_bwd: misaligned argument");
+  const long long units = (long long)g.types * heads * g.nLon;
+  const int grid = int(units < g_num_sms ? units : g_num_sms);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static bool attr_done[2] = {false, false};
+  if (fp16) {
+    if (!attr_done[1]) { PG_CUDA(cudaFuncSetAttribute(window_attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_SMEM_BYTES)); attr_done[1] = true; }
+    window_attention_bwd_kernel<true><<<grid, ATB_THREADS, ATB_SMEM_BYTES, s>>>(a);
+  } else {
+    if (!attr_done[0]) { PG_CUDA(cudaFuncSetAttribute(window_attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_SMEM_BYTES)); attr_done[0] = true; }
+    window_attention_bwd_kernel<false><<<grid, ATB_THREADS, ATB_SMEM_BYTES, s>>>(a);
+  }
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pangu_recover_grad_gather(const float* d_upper, const float* d_surface, void* dy_upper, void* dy_surface,
+                                         int lat, int lon, int fp16, void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(lon % 48 == 0 && lon > 0, "lon must be a positive multiple of 48 (got %d)", lon);
+  const int Hh = (lat + 3) / 4, Ww = lon / 4;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  EmbedArgs ea{d_upper, d_surface, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dy_upper, dy_surface, lat, lon, Hh, Ww};
+  dim3 grid((Ww + EMB_TT - 1) / EMB_TT, Hh, 8);
+  if (fp16) embed_im2col_kernel<true><<<grid, EMB_THREADS, 0, s>>>(ea);
+  else embed_im2col_kernel<false><<<grid, EMB_THREADS, 0, s>>>(ea);
+  PG_CUDA(cudaGetLastError());
+  return 0;
 }

@@ -18,8 +18,8 @@ struct EmbedArgs {
   const float* surface;   // [4][lat][lon]
   const float* s_mean; const float* s_std;   // [4]
   const float* u_mean; const float* u_std;   // [13][5]  (level axis reversed w.r.t. data, layers.py:73-76)
-  const float* maps;      // [3][4*Hh][lon]
-  const float* const_h;   // [13][lat][lon]
+  const float* maps;      // [3][4*Hh][lon]          (nullptr: zeros -- gradient patchify mode)
+  const float* const_h;   // [13][lat][lon]          (nullptr: zeros; s_mean / u_mean nullptr: no normalisation)
   void* a_upper;          // [7*Hh*Ww][192] 16-bit, feature ((c*2+dz)*4+dh)*4+dw
   void* a_surface;        // [Hh*Ww][128]   16-bit, feature (c*4+dh)*4+dw, zero for f >= 112
   int lat, lon, Hh, Ww;
@@ -52,10 +52,12 @@ __global__ void __launch_bounds__(EMB_THREADS) embed_im2col_kernel(const EmbedAr
       if (c < 4) {
         if (la < a.lat) {
           v = *reinterpret_cast<const float4*>(a.surface + c * plane + size_t(la) * a.lon + lo);
-          const float m = a.s_mean[c], s = a.s_std[c];
-          v.x = (v.x - m) / s; v.y = (v.y - m) / s; v.z = (v.z - m) / s; v.w = (v.w - m) / s;
+          if (a.s_mean) {
+            const float m = a.s_mean[c], s = a.s_std[c];
+            v.x = (v.x - m) / s; v.y = (v.y - m) / s; v.z = (v.z - m) / s; v.w = (v.w - m) / s;
+          }
         }
-      } else {
+      } else if (a.maps) {
         v = *reinterpret_cast<const float4*>(a.maps + (size_t(c - 4) * (4 * a.Hh) + la) * a.lon + lo);
       }
     } else {
@@ -64,9 +66,11 @@ __global__ void __launch_bounds__(EMB_THREADS) embed_im2col_kernel(const EmbedAr
       if (lev < 13 && la < a.lat) {
         if (c < 5) {
           v = *reinterpret_cast<const float4*>(a.upper + (size_t(c) * 13 + lev) * plane + size_t(la) * a.lon + lo);
-          const float m = a.u_mean[(12 - lev) * 5 + c], s = a.u_std[(12 - lev) * 5 + c];
-          v.x = (v.x - m) / s; v.y = (v.y - m) / s; v.z = (v.z - m) / s; v.w = (v.w - m) / s;
-        } else {
+          if (a.u_mean) {
+            const float m = a.u_mean[(12 - lev) * 5 + c], s = a.u_std[(12 - lev) * 5 + c];
+            v.x = (v.x - m) / s; v.y = (v.y - m) / s; v.z = (v.z - m) / s; v.w = (v.w - m) / s;
+          }
+        } else if (a.const_h) {
           v = *reinterpret_cast<const float4*>(a.const_h + size_t(lev) * plane + size_t(la) * a.lon + lo);
         }
       }

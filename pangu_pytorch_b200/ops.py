@@ -21,6 +21,8 @@ _KERNELS_PER_CALL = {
     "pangu_cast16": 1, "pangu_to_window16": 1, "pangu_patch_embed": 3, "pangu_qkv": 1,
     "pangu_window_attention": 1, "pangu_proj_ln_residual": 1, "pangu_mlp_ln_residual": 2,
     "pangu_downsample": 2, "pangu_upsample": 2, "pangu_patch_recover": 2, "pangu_linear": 1, "pangu_denorm_fields": 1, "pangu_l1_loss": 2,
+    "pangu_cast16_t": 1, "pangu_dgrad": 1, "pangu_wgrad": 1, "pangu_colsum16": 1, "pangu_layernorm_bwd": 1, "pangu_gelu_bwd": 1,
+    "pangu_window_attention_bwd": 1, "pangu_recover_grad_gather": 1,
 }
 
 
@@ -213,3 +215,80 @@ def l1_loss(out_upper, out_surface, tgt_upper, tgt_surface, s_mean, s_std, u_mea
           _p(s_std, f), _p(u_mean, f), _p(u_std, f), ctypes.cast(wu, c_void_p), ctypes.cast(ws, c_void_p), _p(loss, f),
           _p(acc, torch.float64), _p(gu, f), _p(gs, f), lat, lon, _stream())
     return loss, gu, gs
+
+
+# ----------------------------------------------------------------------------------------------
+# backward pass (include/pangu_b200.h, "Backward pass")
+# ----------------------------------------------------------------------------------------------
+def cast16_t(src: Tensor, fp16: bool, rows_pad: Optional[int] = None, cols_pad: Optional[int] = None) -> Tensor:
+    """fp32 [R, C] -> 16-bit transposed copy [C_pad, R_pad] (zero padded)."""
+    src = src.detach().reshape(src.shape[0], -1).contiguous()
+    R, C = src.shape
+    rp, cp = rows_pad or R, cols_pad or C
+    out = torch.empty(cp, rp, dtype=dtype16(fp16), device=src.device)
+    _call("pangu_cast16_t", _p(src, torch.float32, "src"), _p(out), R, C, rp, cp, int(fp16), _stream())
+    return out
+
+
+def dgrad(a16: Tensor, wt16: Tensor, kind: int, fp16: bool, out32: Optional[Tensor] = None,
+          out16: Optional[Tensor] = None, resid32: Optional[Tensor] = None, bias: Optional[Tensor] = None,
+          grid=(8, 1, 12), roll: bool = False) -> None:
+    """out[M, N] = a16[M, K] @ wt16[N, K].T (+bias); see ``pangu_dgrad`` for the four output kinds."""
+    h, f = dtype16(fp16), torch.float32
+    M, K = a16.shape
+    N = wt16.shape[0]
+    if wt16.shape[1] != K:
+        raise ValueError(f"dgrad: reduction extents differ ({K} vs {wt16.shape[1]})")
+    Z, H, W = grid
+    _call("pangu_dgrad", _p(a16, h, "a16"), _p(wt16, h, "wt16"), _p(bias, f), _p(resid32, f), _p(out32, f), _p(out16, h),
+          M, N, K, int(kind), Z, H, W, int(bool(roll)), int(fp16), _stream())
+
+
+def wgrad(dy16: Tensor, x16: Tensor, dw: Tensor, fp16: bool, n_valid: Optional[int] = None,
+          k_valid: Optional[int] = None, k_off: int = 0, alpha: float = 1.0) -> None:
+    """dw[n, k_off + k] += alpha * sum_m dy16[m, n] * x16[m, k]; dw: fp32 2-D (row pitch = dw.stride(0))."""
+    h = dtype16(fp16)
+    M = dy16.shape[0]
+    if x16.shape[0] != M:
+        raise ValueError("wgrad: row counts differ")
+    if dw.dim() != 2 or dw.stride(1) != 1 or dw.dtype != torch.float32 or not dw.is_cuda:
+        raise ValueError("wgrad: dw must be a 2-D fp32 CUDA tensor with unit column stride")
+    N = dy16.shape[1] if n_valid is None else n_valid
+    K = x16.shape[1] if k_valid is None else k_valid
+    _call("pangu_wgrad", _p(dy16, h, "dy16"), dy16.stride(0), _p(x16, h, "x16"), x16.stride(0), c_void_p(dw.data_ptr()),
+          dw.stride(0), int(k_off), M, N, K, float(alpha), int(fp16), _stream())
+
+
+def colsum16(src16: Tensor, out: Tensor, fp16: bool, n_valid: Optional[int] = None, alpha: float = 1.0) -> None:
+    """out[n] += alpha * sum_m src16[m, n] (bias gradients)."""
+    M, N = src16.shape
+    _call("pangu_colsum16", _p(src16, dtype16(fp16), "src16"), src16.stride(0), _p(out, torch.float32, "out"), M, N,
+          N if n_valid is None else n_valid, float(alpha), int(fp16), _stream())
+
+
+def layernorm_bwd(y: Tensor, g: Tensor, gamma: Tensor, dgamma: Optional[Tensor], dbeta: Optional[Tensor], rows: int,
+                  C: int, mode: int, fp16: bool, dx16: Optional[Tensor] = None, dx32: Optional[Tensor] = None,
+                  grid=(8, 1, 12), scale: float = 1.0) -> None:
+    f = torch.float32
+    Z, H, W = grid
+    _call("pangu_layernorm_bwd", _p(y, f, "y"), _p(g, f, "g"), _p(gamma, f, "gamma"), _p(dx16, dtype16(fp16)), _p(dx32, f),
+          _p(dgamma, f), _p(dbeta, f), rows, C, int(mode), Z, H, W, float(scale), int(fp16), _stream())
+
+
+def gelu_bwd(dh16: Tensor, pre16: Tensor, fp16: bool) -> None:
+    """dh16 *= gelu'(pre16) in place."""
+    from ctypes import c_longlong
+    h = dtype16(fp16)
+    _call("pangu_gelu_bwd", _p(dh16, h, "dh16"), _p(pre16, h, "pre16"), c_longlong(dh16.numel()), int(fp16), _stream())
+
+
+def window_attention_bwd(qkv16, datt16w, earth_bias, dqkv16, dbias, Z, H, W, C, heads, roll: bool, fp16: bool) -> None:
+    h, f = dtype16(fp16), torch.float32
+    _call("pangu_window_attention_bwd", _p(qkv16, h, "qkv"), _p(datt16w, h, "datt"), _p(earth_bias, f, "earth_specific_bias"),
+          _p(dqkv16, h, "dqkv"), _p(dbias, f, "dbias"), Z, H, W, C, heads, int(bool(roll)), int(fp16), _stream())
+
+
+def recover_grad_gather(d_upper, d_surface, dy_upper, dy_surface, lat, lon, fp16: bool) -> None:
+    h, f = dtype16(fp16), torch.float32
+    _call("pangu_recover_grad_gather", _p(d_upper, f, "d_upper"), _p(d_surface, f, "d_surface"), _p(dy_upper, h),
+          _p(dy_surface, h), lat, lon, int(fp16), _stream())
