@@ -272,13 +272,15 @@ def forward_train(p: Dict[str, Tensor], upper, surface, statistics, maps, const_
 def loss_and_grads(p: Dict[str, Tensor], upper, surface, statistics, maps, const_h, tgt_upper, tgt_surface,
                    drop_scales=None):
     """One training step's loss and parameter gradients (models/pangu_sample.py:52-69): forward,
-    ``normData`` of the physical targets, weighted L1, ``loss.backward()``.  Returns (loss, {name: grad})."""
+    ``normData`` of the physical targets, weighted L1, ``loss.backward()``.
+    Returns (loss, {name: grad}, (dL/d output, dL/d output_surface))."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
     ou, os_ = forward_train(leaves, upper, surface, statistics, maps, const_h, drop_scales)
+    ou.retain_grad(); os_.retain_grad()
     tu, ts = norm_data(tgt_upper, tgt_surface, output_statistics(statistics))
     loss = weighted_l1_loss(ou, os_, tu, ts)
     loss.backward()
-    return loss.detach(), {k: v.grad for k, v in leaves.items()}
+    return loss.detach(), {k: v.grad for k, v in leaves.items()}, (ou.grad, os_.grad)
 
 
 # --------------------------------------------------------------------------------------

@@ -34,6 +34,7 @@ struct AttnBwdArgs {
   float* dbias;         // [types][heads][144][144] fp32, accumulated into
   int C, heads, types, nLon, nH, roll, plane_rows;
   float q_scale;
+  float palpha;         // factor on the bias gradient (1 / loss scale)
 };
 
 template <bool kFp16>
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) window_attention_bwd_kernel(co
       for (int i = threadIdx.x; i < ATT_TOK * ATT_TOK; i += ATB_THREADS) {
         const int r = i / ATT_TOK, c = i % ATT_TOK;
         float* p = s_db + r * ATB_DB_PITCH + c;
-        atomicAdd(g + i, *p);
+        atomicAdd(g + i, a.palpha * *p);
         *p = 0.f;
       }
       __syncthreads();

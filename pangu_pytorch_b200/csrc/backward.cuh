@@ -24,6 +24,7 @@ struct LnBwdArgs {
   int rows, C;
   int Z, H, W;          // UP / DOWN: HIGH-resolution token grid
   float scale;          // DropPath factor of the branch (1 in eval)
+  float palpha;         // factor on the parameter gradients (1 / loss scale)
   float eps;
 };
 
@@ -150,8 +151,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kC; i += blockDim.x) {
-    if (a.dgamma) atomicAdd(a.dgamma + i, s_dg[i]);
-    if (a.dbeta) atomicAdd(a.dbeta + i, s_db[i]);
+    if (a.dgamma) atomicAdd(a.dgamma + i, a.palpha * s_dg[i]);
+    if (a.dbeta) atomicAdd(a.dbeta + i, a.palpha * s_db[i]);
   }
 }
 

@@ -352,7 +352,7 @@ extern "C" int pangu_patch_embed(const float* upper, const float* surface, const
   PG_TRY(check_grid(8, Hh, Ww, 192, 0));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   EmbedArgs ea{upper, surface, surface_mean, surface_std, upper_mean, upper_std, maps, const_h,
-               ws_a_upper, ws_a_surface, lat, lon, Hh, Ww};
+               ws_a_upper, ws_a_surface, lat, lon, Hh, Ww, 1.f};
   dim3 grid((Ww + EMB_TT - 1) / EMB_TT, Hh, 8);
   if (fp16) embed_im2col_kernel<true><<<grid, EMB_THREADS, 0, s>>>(ea);
   else embed_im2col_kernel<false><<<grid, EMB_THREADS, 0, s>>>(ea);
@@ -777,7 +777,7 @@ static int launch_ln_bwd(const LnBwdArgs& a, int mode, cudaStream_t s) {
 
 extern "C" int pangu_layernorm_bwd(const float* y, const float* g, const float* gamma, void* dx16, float* dx32,
                                    float* dgamma, float* dbeta, int rows, int C, int mode, int Z, int H, int W,
-                                   float scale, int fp16, void* stream) {
+                                   float scale, float palpha, int fp16, void* stream) {
   PG_TRY(ensure_init());
   PG_REQUIRE(rows > 0 && y && g && gamma, "layernorm_bwd: null argument");
   PG_REQUIRE(mode == LNB_DOWN ? dx32 != nullptr : dx16 != nullptr, "layernorm_bwd: missing output");
@@ -785,7 +785,7 @@ extern "C" int pangu_layernorm_bwd(const float* y, const float* g, const float* 
   if (mode == LNB_DOWN) PG_REQUIRE(rows == Z * ((H + 1) / 2) * (W / 2), "layernorm_bwd(down): rows must be the low-res token count");
   LnBwdArgs a;
   a.y = y; a.g = g; a.gamma = gamma; a.dx16 = dx16; a.dx32 = dx32; a.dgamma = dgamma; a.dbeta = dbeta;
-  a.rows = rows; a.C = C; a.Z = Z; a.H = H; a.W = W; a.scale = scale; a.eps = 1e-5f;
+  a.rows = rows; a.C = C; a.Z = Z; a.H = H; a.W = W; a.scale = scale; a.palpha = palpha; a.eps = 1e-5f;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return fp16 ? launch_ln_bwd<true>(a, mode, s) : launch_ln_bwd<false>(a, mode, s);
 }
@@ -803,8 +803,8 @@ extern "C" int pangu_gelu_bwd(void* dh16, const void* pre16, long long n, int fp
 }
 
 extern "C" int pangu_window_attention_bwd(const void* qkv16, const void* datt16w, const float* earth_bias, void* dqkv16,
-                                          float* dbias, int Z, int H, int W, int C, int heads, int roll, int fp16,
-                                          void* stream) {
+                                          float* dbias, int Z, int H, int W, int C, int heads, int roll, float palpha,
+                                          int fp16, void* stream) {
   PG_TRY(ensure_init());
   PG_TRY(check_grid(Z, H, W, C, heads));
   const Geo g = make_geo(Z, H, W);
@@ -813,6 +813,7 @@ extern "C" int pangu_window_attention_bwd(const void* qkv16, const void* datt16w
   a.C = C; a.heads = heads; a.types = g.types; a.nLon = g.nLon; a.nH = g.nH; a.roll = roll ? 1 : 0;
   a.plane_rows = sh_rows_padded(g.nLon * g.types * 144);
   a.q_scale = 0.17677669529663687f;
+  a.palpha = palpha;
   PG_REQUIRE((reinterpret_cast<uintptr_t>(qkv16) & 15) == 0 && (reinterpret_cast<uintptr_t>(datt16w) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(earth_bias) & 7) == 0 && (reinterpret_cast<uintptr_t>(dqkv16) & 3) == 0,
              "attention_bwd: misaligned argument");
@@ -832,12 +833,12 @@ extern "C" int pangu_window_attention_bwd(const void* qkv16, const void* datt16w
 }
 
 extern "C" int pangu_recover_grad_gather(const float* d_upper, const float* d_surface, void* dy_upper, void* dy_surface,
-                                         int lat, int lon, int fp16, void* stream) {
+                                         int lat, int lon, float scale, int fp16, void* stream) {
   PG_TRY(ensure_init());
   PG_REQUIRE(lon % 48 == 0 && lon > 0, "lon must be a positive multiple of 48 (got %d)", lon);
   const int Hh = (lat + 3) / 4, Ww = lon / 4;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  EmbedArgs ea{d_upper, d_surface, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dy_upper, dy_surface, lat, lon, Hh, Ww};
+  EmbedArgs ea{d_upper, d_surface, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dy_upper, dy_surface, lat, lon, Hh, Ww, scale};
   dim3 grid((Ww + EMB_TT - 1) / EMB_TT, Hh, 8);
   if (fp16) embed_im2col_kernel<true><<<grid, EMB_THREADS, 0, s>>>(ea);
   else embed_im2col_kernel<false><<<grid, EMB_THREADS, 0, s>>>(ea);

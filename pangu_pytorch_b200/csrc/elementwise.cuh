@@ -23,6 +23,7 @@ struct EmbedArgs {
   void* a_upper;          // [7*Hh*Ww][192] 16-bit, feature ((c*2+dz)*4+dh)*4+dw
   void* a_surface;        // [Hh*Ww][128]   16-bit, feature (c*4+dh)*4+dw, zero for f >= 112
   int lat, lon, Hh, Ww;
+  float gscale;           // gradient patchify mode: factor on the values (loss scale); unused otherwise
 };
 
 template <bool kFp16>
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(EMB_THREADS) embed_im2col_kernel(const EmbedAr
         }
       }
     }
+    if (a.s_mean == nullptr) { v.x *= a.gscale; v.y *= a.gscale; v.z *= a.gscale; v.w *= a.gscale; }
     *reinterpret_cast<uint2*>(tile + tk * EMB_PITCH + grp * 8) =
         make_uint2(pack16<kFp16>(v.x, v.y), pack16<kFp16>(v.z, v.w));
   }

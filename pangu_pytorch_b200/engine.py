@@ -103,6 +103,23 @@ class Weight16:
         return self._val
 
 
+class Weight16T:
+    """Lazily maintained TRANSPOSED 16-bit copy [in, out_pad] of an fp32 (out, in[, 1]) weight: the B operand
+    of the weight's data-gradient GEMM (re-cast when the parameter changes)."""
+
+    def __init__(self, rows_pad=None):
+        self.rows_pad = rows_pad
+        self._key = None
+        self._val = None
+
+    def get(self, param: torch.Tensor) -> torch.Tensor:
+        key = (param.data_ptr(), param._version, use_fp16(), str(param.device))
+        if key != self._key:
+            self._val = ops.cast16_t(param, use_fp16(), rows_pad=self.rows_pad)
+            self._key = key
+        return self._val
+
+
 def f32(t: torch.Tensor, device) -> torch.Tensor:
     """Contiguous fp32 view/copy of a small tensor on ``device`` (statistics, biases)."""
     return t.detach().to(device=device, dtype=torch.float32).contiguous()

@@ -231,6 +231,7 @@ class EarthSpecificBlock(nn.Module):
                             mlp._w2.get(mlp.linear2.weight), mlp.linear2.bias, self.norm2.weight, self.norm2.bias,
                             ws.hidden, ws.x32, target, Z, H, W, C, roll_out, s2, fp16)
         ops.set_tag("")
+        return s1, s2
 
     def forward(self, x, Z, H, W, roll):
         C = x.shape[-1]

@@ -50,10 +50,12 @@ class PanguModel(nn.Module):
             nn.init.constant_(m.weight, 1.0)
 
     def forward(self, input, input_surface, statistics, maps, const_h):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError(
-                "pangu_pytorch_b200: the hand-written backward kernels are not built yet; run the forward "
-                "under torch.no_grad() / model.eval() (see DESIGN.md, scope row a15)")
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            # training step (models/pangu_sample.py:52-71): activations are kept on a tape, the backward is
+            # the hand-written kernel chain of pangu_pytorch_b200/training.py
+            from ..training import PanguTrainFunction
+            return PanguTrainFunction.apply(self, input, input_surface, statistics, maps, const_h,
+                                            *self.parameters())
         dev = self._input_layer.conv.weight.device
         lat, lon = input_surface.shape[-2], input_surface.shape[-1]
         Z, H, W = 8, (lat + 3) // 4, lon // 4

@@ -268,11 +268,11 @@ def colsum16(src16: Tensor, out: Tensor, fp16: bool, n_valid: Optional[int] = No
 
 def layernorm_bwd(y: Tensor, g: Tensor, gamma: Tensor, dgamma: Optional[Tensor], dbeta: Optional[Tensor], rows: int,
                   C: int, mode: int, fp16: bool, dx16: Optional[Tensor] = None, dx32: Optional[Tensor] = None,
-                  grid=(8, 1, 12), scale: float = 1.0) -> None:
+                  grid=(8, 1, 12), scale: float = 1.0, palpha: float = 1.0) -> None:
     f = torch.float32
     Z, H, W = grid
     _call("pangu_layernorm_bwd", _p(y, f, "y"), _p(g, f, "g"), _p(gamma, f, "gamma"), _p(dx16, dtype16(fp16)), _p(dx32, f),
-          _p(dgamma, f), _p(dbeta, f), rows, C, int(mode), Z, H, W, float(scale), int(fp16), _stream())
+          _p(dgamma, f), _p(dbeta, f), rows, C, int(mode), Z, H, W, float(scale), float(palpha), int(fp16), _stream())
 
 
 def gelu_bwd(dh16: Tensor, pre16: Tensor, fp16: bool) -> None:
@@ -282,13 +282,14 @@ def gelu_bwd(dh16: Tensor, pre16: Tensor, fp16: bool) -> None:
     _call("pangu_gelu_bwd", _p(dh16, h, "dh16"), _p(pre16, h, "pre16"), c_longlong(dh16.numel()), int(fp16), _stream())
 
 
-def window_attention_bwd(qkv16, datt16w, earth_bias, dqkv16, dbias, Z, H, W, C, heads, roll: bool, fp16: bool) -> None:
+def window_attention_bwd(qkv16, datt16w, earth_bias, dqkv16, dbias, Z, H, W, C, heads, roll: bool, fp16: bool,
+                         palpha: float = 1.0) -> None:
     h, f = dtype16(fp16), torch.float32
     _call("pangu_window_attention_bwd", _p(qkv16, h, "qkv"), _p(datt16w, h, "datt"), _p(earth_bias, f, "earth_specific_bias"),
-          _p(dqkv16, h, "dqkv"), _p(dbias, f, "dbias"), Z, H, W, C, heads, int(bool(roll)), int(fp16), _stream())
+          _p(dqkv16, h, "dqkv"), _p(dbias, f, "dbias"), Z, H, W, C, heads, int(bool(roll)), float(palpha), int(fp16), _stream())
 
 
-def recover_grad_gather(d_upper, d_surface, dy_upper, dy_surface, lat, lon, fp16: bool) -> None:
+def recover_grad_gather(d_upper, d_surface, dy_upper, dy_surface, lat, lon, fp16: bool, scale: float = 1.0) -> None:
     h, f = dtype16(fp16), torch.float32
     _call("pangu_recover_grad_gather", _p(d_upper, f, "d_upper"), _p(d_surface, f, "d_surface"), _p(dy_upper, h),
-          _p(dy_surface, h), lat, lon, int(fp16), _stream())
+          _p(dy_surface, h), lat, lon, float(scale), int(fp16), _stream())
