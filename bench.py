@@ -318,6 +318,92 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------
+# training workload (BASELINE.json configs[3]: finetune_fully forward+backward, batch 1 per GPU, DDP gradient mean)
+# ----------------------------------------------------------------------------------------------
+def run_train_arm(args):
+    import torch
+    import torch.distributed as dist
+    import pangu_pytorch_b200 as pb
+    from pangu_pytorch_b200 import ops, training
+    from pangu_pytorch_b200.dist import GradReducer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pb.set_operand_dtype(args.operands)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    torch.manual_seed(0)
+    model = pb.PanguModel(device=dev).to(dev).train()
+    if world > 1:
+        model.grad_reducer = GradReducer()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-6, weight_decay=3e-6, fused=True)   # finetune/finetune_fully.py:119
+    g = torch.Generator(device=dev).manual_seed(1)
+    maps = torch.randn(1, 3, 724, LON, device=dev, generator=g)
+    const_h = torch.randn(1, 1, 1, 13, LAT, LON, device=dev, generator=g)
+    stats = [torch.zeros(4, device=dev), torch.ones(4, device=dev),
+             torch.zeros(13, 1, 1, 5, device=dev), torch.ones(13, 1, 1, 5, device=dev)]
+    gk = torch.Generator(device=dev).manual_seed(100 + rank)
+    up = torch.randn(1, 5, 13, LAT, LON, device=dev, generator=gk)
+    sf = torch.randn(1, 4, LAT, LON, device=dev, generator=gk)
+    tu = torch.randn(1, 5, 13, LAT, LON, device=dev, generator=gk)
+    ts = torch.randn(1, 4, LAT, LON, device=dev, generator=gk)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = training.train_step(model, up, sf, stats, maps, const_h, tu, ts)
+        opt.step()
+        return loss
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ops.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launches() - l0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    times = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_max = float(times[0])
+    if rank == 0:
+        pk = peaks()
+        per = ms_max / args.steps
+        tfl = 3 * FLOPS_PER_STEP / (per * 1e-3) / 1e12
+        line = {"metric": "finetune steps/s @0.25deg (fwd + weighted-L1 + bwd + grad mean + Adam)", "value": round(world * args.steps / (ms_max / 1e3), 3),
+                "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": round(per, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.operands, "data": "synthetic",
+                "config": {"workload": "finetune_fully step, PanguModel 0.25deg, batch 1 per GPU, random-init weights",
+                           "parallelism": f"data parallel over {world} GPU(s); gradient mean (1.1 GB fp32) all-reduced per block "
+                                          "on a side stream under the backward", "optimizer": "torch.optim.Adam(fused), as the reference"},
+                "clocks": clocks, "gpu_launches": launches, "loss": float(loss),
+                "roofline": {"bound": "tensor", "achieved": round(tfl, 1), "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                             "frac": round(tfl / pk["tflops_sustained"], 4), "algorithmic_flops_per_step": 3 * FLOPS_PER_STEP,
+                             "peak_source": pk["source"]}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -326,9 +412,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--operands", default=os.environ.get("PANGU_B200_OPERANDS", "bf16"), choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="forecast", choices=["forecast", "train"],
+                    help="forecast: the BASELINE.json headline (default); train: finetune_fully step (configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "train":
+        run_train_arm(args)
     else:
         run_gpu_arm(args)
 

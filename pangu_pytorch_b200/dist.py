@@ -64,3 +64,72 @@ def gather_grad(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 
         return finish
     finish()
     return []
+
+
+class GradReducer:
+    """Gradient mean overlapped with the backward pass ("bucket = one bias table, launched as
+    each block's backward finishes").
+
+    ``training.backward`` calls ``ready(grads)`` whenever a group of parameter gradients is final (one
+    block, or the recovery / up-sample / down-sample / embedding stage).  On CUDA the group is all-reduced
+    on a side stream behind an event, so NCCL traffic over NVLink runs under the remaining backward kernels;
+    ``finish()`` makes the compute stream wait for the exchange and unpacks the packed small tensors.
+    Same arithmetic as ``gather_grad`` (sum over ranks, divide by the world size)."""
+
+    def __init__(self, bucket_bytes: int = 64 << 20):
+        self.bucket_bytes = bucket_bytes
+        self._pending = []
+        self._stream = None
+
+    @staticmethod
+    def active() -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def ready(self, grads: List[torch.Tensor]) -> None:
+        grads = [g for g in grads if g is not None]
+        if not grads or not self.active():
+            return
+        cuda = grads[0].is_cuda
+        if cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream()
+            ev = torch.cuda.Event()
+            ev.record()
+            self._stream.wait_event(ev)
+        ctx = torch.cuda.stream(self._stream) if cuda else _NullCtx()
+        with ctx:
+            for bucket in _buckets(grads, self.bucket_bytes):
+                if len(bucket) == 1 and bucket[0].is_contiguous():
+                    flat, members = bucket[0].view(-1), None
+                else:
+                    flat, members = torch.cat([g.reshape(-1) for g in bucket]), bucket
+                work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
+                self._pending.append((work, flat, members))
+
+    def finish(self) -> None:
+        if not self._pending:
+            return
+        world = dist.get_world_size()
+        cuda = self._pending[0][1].is_cuda
+        ctx = torch.cuda.stream(self._stream) if cuda else _NullCtx()
+        with ctx:
+            for work, flat, members in self._pending:
+                work.wait()
+                flat.div_(world)
+                if members is not None:
+                    off = 0
+                    for g in members:
+                        n = g.numel()
+                        g.copy_(flat[off:off + n].view_as(g))
+                        off += n
+        if cuda:
+            torch.cuda.current_stream().wait_stream(self._stream)
+        self._pending = []
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

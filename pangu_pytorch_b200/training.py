@@ -247,13 +247,18 @@ def _block_backward(blk, ws, roll, t: BlockTape, sc: Scratch, g32, G, fp16):
     ops.set_tag("")
 
 
-def backward(model, tape: Tape, g_upper: torch.Tensor, g_surface: torch.Tensor) -> List[Optional[torch.Tensor]]:
+def backward(model, tape: Tape, g_upper: torch.Tensor, g_surface: torch.Tensor, reducer=None) -> List[Optional[torch.Tensor]]:
     """Gradients of all parameters (in ``model.parameters()`` order; None where requires_grad is False)
-    given dL/d(output), dL/d(output_surface)."""
+    given dL/d(output), dL/d(output_surface).  ``reducer`` (``dist.GradReducer``): data-parallel gradient mean
+    (era5_data/utils_dist.py:125-134), started group by group as the gradients become final."""
     hi, lo, fp16 = tape.hi, tape.lo, tape.fp16
     lat, lon = tape.lat, tape.lon
     plane = hi.H * hi.W
     G = _Grads()
+
+    def done(module):          # every gradient of `module` is final: hand the group to the exchange
+        if reducer is not None:
+            reducer.ready([G.g.get(id(p)) for p in module.parameters()])
     sh, sl = tape.scr[id(hi)], tape.scr[id(lo)]
     f = torch.float32
     g_upper = g_upper.detach().to(f).contiguous()
@@ -275,11 +280,13 @@ def backward(model, tape: Tape, g_upper: torch.Tensor, g_surface: torch.Tensor) 
     ops.dgrad(tape.dys, wst[:192], 0, fp16, out32=g_skip[:plane])
     ops.dgrad(tape.dyu, wut[192:], 0, fp16, out32=g_hi[plane:])
     ops.dgrad(tape.dys, wst[192:], 0, fp16, out32=g_hi[:plane])
+    done(rec)
 
     order, bt = tape.order, tape.blocks
     for b in (15, 14):
         blk, ws, roll = order[b]
         _block_backward(blk, ws, roll, bt[b], sh, g_hi, G, fp16)
+        done(blk)
 
     # ---------------- UpSample                              (models/layers.py:474-499)
     up = model.upsample
@@ -293,10 +300,12 @@ def backward(model, tape: Tape, g_upper: torch.Tensor, g_surface: torch.Tensor) 
     _linear_bwd(tape.du16, tape.lo_out16, up.linear1.weight, None, G, fp16)
     g_lo = sl.g32
     ops.dgrad(tape.du16, _wt(up, "w1", up.linear1.weight, fp16), 0, fp16, out32=g_lo)
+    done(up)
 
     for b in range(13, 1, -1):
         blk, ws, roll = order[b]
         _block_backward(blk, ws, roll, bt[b], sl, g_lo, G, fp16)
+        done(blk)
 
     # ---------------- DownSample                            (models/layers.py:432-459)
     down = model.downsample
@@ -305,16 +314,21 @@ def backward(model, tape: Tape, g_upper: torch.Tensor, g_surface: torch.Tensor) 
     ops.dgrad(sl.dy16, _wt(down, "w", down.linear.weight, fp16), 0, fp16, out32=tape.u32)
     ops.layernorm_bwd(tape.x32_skip, tape.u32, down.norm.weight, G(down.norm.weight), G(down.norm.bias), lo.T,
                       4 * hi.C, LNB_DOWN, fp16, dx32=g_skip, grid=(hi.Z, hi.H, hi.W), palpha=pa)
+    done(down)
 
     for b in (1, 0):
         blk, ws, roll = order[b]
         _block_backward(blk, ws, roll, bt[b], sh, g_skip, G, fp16)
+        done(blk)
 
     # ---------------- PatchEmbedding                        (models/layers.py:40-93; inputs need no gradient)
     emb = model._input_layer
     ops.cast_rows(g_skip, sh.dy16, fp16)
     _linear_bwd(sh.dy16[plane:], tape.a_u, emb.conv.weight, emb.conv.bias, G, fp16)
     _linear_bwd(sh.dy16[:plane], tape.a_s, emb.conv_surface.weight, emb.conv_surface.bias, G, fp16, k_valid=112)
+    done(emb)
+    if reducer is not None:
+        reducer.finish()
     return [G.g.get(id(p)) for p in model.parameters()]
 
 
@@ -330,7 +344,7 @@ class PanguTrainFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_upper, g_surface):
-        grads = backward(ctx.model, ctx.tape, g_upper, g_surface)
+        grads = backward(ctx.model, ctx.tape, g_upper, g_surface, getattr(ctx.model, "grad_reducer", None))
         return (None,) * 6 + tuple(grads)
 
 

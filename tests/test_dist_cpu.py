@@ -36,6 +36,12 @@ def _worker(rank, world, port, q):
         frozen = torch.nn.Parameter(torch.zeros(3))          # no grad: must be skipped
         mine = [p.grad.clone() for p in params]
         pdist.gather_grad(params + [frozen], bucket_bytes=4096)
+        # --- overlapped reducer: the same gradients handed over in three groups (one with a None = frozen parameter)
+        red = pdist.GradReducer(bucket_bytes=4096)
+        again = [t.clone() for t in mine]
+        red.ready(again[0:2] + [None]); red.ready(again[2:3]); red.ready(again[3:])
+        red.finish()
+        assert all(torch.equal(a, p.grad) for a, p in zip(again, params)), "GradReducer != gather_grad"
         # --- ensemble sharding + metadata gather
         idx = ensemble.member_indices(11, rank, world)
         meta = ensemble.gather_metadata({k: float(k) * 2 for k in idx})
