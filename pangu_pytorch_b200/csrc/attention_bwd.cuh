@@ -31,7 +31,7 @@ struct AttnBwdArgs {
   const void* datt;     // [Tp][C] 16-bit, window order (pad rows zero): gradient w.r.t. the merged-head attention output
   const float* bias;    // [types][heads][144][144] fp32
   void* dqkv;           // [Tp][3C] 16-bit, window order, column s*C + head*32 + d; dq is w.r.t. the UNscaled q
-  float* dbias;         // [types][heads][144][144] fp32, accumulated into
+  float* dbias;         // [types][heads][144][144] fp32, accumulated into (nullptr: frozen table, skipped)
   int C, heads, types, nLon, nH, roll, plane_rows;
   float q_scale;
   float palpha;         // factor on the bias gradient (1 / loss scale)
@@ -165,12 +165,14 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) window_attention_bwd_kernel(co
       for (int j = 0; j < 18; ++j) {
         dp[j][0] = s[j][0] * (dp[j][0] - d0); dp[j][1] = s[j][1] * (dp[j][1] - d0);
         dp[j][2] = s[j][2] * (dp[j][2] - d1); dp[j][3] = s[j][3] * (dp[j][3] - d1);
-        float2 x = *reinterpret_cast<float2*>(db0 + 8 * j);
-        x.x += dp[j][0]; x.y += dp[j][1];
-        *reinterpret_cast<float2*>(db0 + 8 * j) = x;
-        float2 y = *reinterpret_cast<float2*>(db1 + 8 * j);
-        y.x += dp[j][2]; y.y += dp[j][3];
-        *reinterpret_cast<float2*>(db1 + 8 * j) = y;
+        if (a.dbias) {
+          float2 x = *reinterpret_cast<float2*>(db0 + 8 * j);
+          x.x += dp[j][0]; x.y += dp[j][1];
+          *reinterpret_cast<float2*>(db0 + 8 * j) = x;
+          float2 y = *reinterpret_cast<float2*>(db1 + 8 * j);
+          y.x += dp[j][2]; y.y += dp[j][3];
+          *reinterpret_cast<float2*>(db1 + 8 * j) = y;
+        }
         *reinterpret_cast<uint32_t*>(p0 + 16 * j) = pack16<kFp16>(s[j][0], s[j][1]);
         *reinterpret_cast<uint32_t*>(p1 + 16 * j) = pack16<kFp16>(s[j][2], s[j][3]);
         *reinterpret_cast<uint32_t*>(e0 + 16 * j) = pack16<kFp16>(dp[j][0], dp[j][1]);
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) window_attention_bwd_kernel(co
     __syncthreads();     // tiles and P / dS are free again
 
     // ---- end of a (type, head) segment (or of this CTA's range): flush the bias gradient
-    if (lw == a.nLon - 1 || u + 1 == u_end) {
+    if (a.dbias && (lw == a.nLon - 1 || u + 1 == u_end)) {
       float* g = a.dbias + size_t(th) * ATT_TOK * ATT_TOK;
       for (int i = threadIdx.x; i < ATT_TOK * ATT_TOK; i += ATB_THREADS) {
         const int r = i / ATT_TOK, c = i % ATT_TOK;

@@ -71,3 +71,89 @@ def load_lora_checkpoint(model, path: str, map_location=None, lora_alpha: float 
     state = ckpt["model"] if isinstance(ckpt, dict) and "model" in ckpt else ckpt
     model.load_state_dict(merge_lora_state_dict(state, lora_alpha=lora_alpha), strict=True)
     return model
+
+
+# ----------------------------------------------------------------------------------------------
+# LoRA finetuning on the B200 path (reference finetune/lora_tune.py:124-139)
+# ----------------------------------------------------------------------------------------------
+import math
+
+from torch import nn
+
+
+class LoraLinear(nn.Module):
+    """Stand-in for peft's ``lora.Linear`` wrapper with the same child names (``base_layer``,
+    ``lora_A.<adapter>``, ``lora_B.<adapter>``), so ``state_dict()`` keys match peft's.
+
+    peft would wrap the ``nn.Linear`` children and add the adapter branch inside their ``forward`` -- but on
+    this path the children only HOLD parameters (the kernels read the weights directly), so a peft wrap would
+    silently do nothing.  Here the adapter is folded into the operand instead: the kernels see
+    ``weight = W + (alpha / r) B A`` (re-formed from the current A, B at every step; exact, since the branch
+    is linear), and the backward projects the dense weight gradient onto the adapters:
+    ``dA = (alpha/r) B^T dW``, ``dB = (alpha/r) dW A^T``.  This is exact for ``lora_dropout == 0`` and in
+    eval mode; a non-zero dropout on the adapter input cannot be folded and is rejected in training mode."""
+
+    def __init__(self, base: nn.Linear, r: int = 16, lora_alpha: float = 16.0, lora_dropout: float = 0.0,
+                 adapter: str = "default"):
+        super().__init__()
+        self.base_layer = base
+        self.r, self.lora_alpha, self.scaling, self.adapter = r, lora_alpha, lora_alpha / r, adapter
+        self.in_features, self.out_features = base.in_features, base.out_features
+        self.lora_dropout = nn.ModuleDict({adapter: nn.Dropout(lora_dropout) if lora_dropout > 0 else nn.Identity()})
+        dev = base.weight.device
+        self.lora_A = nn.ModuleDict({adapter: nn.Linear(base.in_features, r, bias=False, device=dev)})
+        self.lora_B = nn.ModuleDict({adapter: nn.Linear(r, base.out_features, bias=False, device=dev)})
+        nn.init.kaiming_uniform_(self.lora_A[adapter].weight, a=math.sqrt(5))     # peft's default init
+        nn.init.zeros_(self.lora_B[adapter].weight)
+        for p in base.parameters():
+            p.requires_grad_(False)
+
+    @property
+    def A(self) -> torch.Tensor:
+        return self.lora_A[self.adapter].weight
+
+    @property
+    def B(self) -> torch.Tensor:
+        return self.lora_B[self.adapter].weight
+
+    @property
+    def weight(self) -> torch.Tensor:
+        """Effective dense weight seen by the kernels (a fresh fp32 tensor, parameter-space arithmetic only)."""
+        drop = self.lora_dropout[self.adapter]
+        if self.training and isinstance(drop, nn.Dropout) and drop.p > 0:
+            raise NotImplementedError("pangu_pytorch_b200: lora_dropout > 0 cannot be folded into the weight; "
+                                      "train with lora_dropout=0 (eval / inference accept any value)")
+        with torch.no_grad():
+            return torch.addmm(self.base_layer.weight, self.B, self.A, alpha=self.scaling)
+
+    @property
+    def bias(self):
+        return self.base_layer.bias
+
+    def forward(self, x):           # plain-torch semantics of peft (never used by the B200 hot path)
+        y = self.base_layer(x)
+        return y + self.scaling * self.lora_B[self.adapter](self.lora_A[self.adapter](self.lora_dropout[self.adapter](x)))
+
+
+def add_lora(model, r: int = 16, lora_alpha: float = 16.0, lora_dropout: float = 0.0,
+             modules_to_save=("_output_layer.conv_surface", "_output_layer.conv")):
+    """``get_peft_model(model, LoraConfig(r, lora_alpha, target_modules=<every nn.Linear>, lora_dropout,
+    modules_to_save))`` of finetune/lora_tune.py:124-139: freezes the base model, puts a rank-``r`` adapter on
+    each of the 67 ``nn.Linear`` modules (4 per block + downsample.linear + upsample.linear1/2; the Conv1d
+    layers get none) and keeps ``modules_to_save`` fully trainable.  Returns the model (modified in place)."""
+    for p in model.parameters():
+        p.requires_grad_(False)
+    targets = [(name, m) for name, m in model.named_modules() if isinstance(m, nn.Linear)]
+    for name, lin in targets:
+        parent = model.get_submodule(name.rsplit(".", 1)[0]) if "." in name else model
+        setattr(parent, name.rsplit(".", 1)[-1], LoraLinear(lin, r, lora_alpha, lora_dropout))
+    for name in modules_to_save:
+        for p in model.get_submodule(name).parameters():
+            p.requires_grad_(True)
+    return model
+
+
+def peft_state_dict(model, prefix: str = "base_model.model.") -> Dict[str, torch.Tensor]:
+    """``state_dict`` with peft's key prefix, i.e. what the reference saves for a LoRA run
+    (models/pangu_sample.py:94-98); ``merge_lora_state_dict`` reads it back."""
+    return {prefix + k: v for k, v in model.state_dict().items()}

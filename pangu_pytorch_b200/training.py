@@ -21,6 +21,7 @@ import torch
 
 from . import engine, ops
 from .engine import Weight16T
+from .lora import LoraLinear
 
 LNB_IDENT, LNB_UP, LNB_DOWN = 0, 1, 2
 # Loss scale of the backward pass.  dL/d(output) of the weighted L1 loss is ~1e-8 at 0.25 degrees: below the fp16
@@ -201,16 +202,28 @@ def _wt(mod, name: str, weight: torch.Tensor, fp16: bool, rows_pad=None) -> torc
     return c.get(weight)
 
 
-def _linear_bwd(dy16, x16, lin_w, lin_b, G, fp16, n_valid=None, k_valid=None, k_off=0, gw2d=None):
+def _linear_bwd(dy16, x16, lin, G, fp16, n_valid=None, k_valid=None, k_off=0, with_bias=True):
+    """Parameter gradients of y = x W^T + b from dy (16-bit) and the saved operand x (16-bit).
+    ``lin``: nn.Linear / nn.Conv1d(k=1) holding (weight, bias), or a LoraLinear (dense gradient projected
+    onto the adapters: dA = s B^T dW, dB = s dW A^T -- parameter-space products of rank 16)."""
     pa = 1.0 / LOSS_SCALE[fp16]
-    """Parameter gradients of y = x W^T + b from dy (16-bit) and the saved operand x (16-bit)."""
-    gb = G(lin_b)
+    if isinstance(lin, LoraLinear):
+        gA, gB = G(lin.A), G(lin.B)
+        if gA is None and gB is None:
+            return
+        dw = torch.zeros(lin.out_features, lin.in_features, dtype=torch.float32, device=dy16.device)
+        ops.wgrad(dy16, x16, dw, fp16, alpha=pa)
+        if gA is not None:
+            gA.addmm_(lin.B.detach().t(), dw, alpha=lin.scaling)
+        if gB is not None:
+            gB.addmm_(dw, lin.A.detach().t(), alpha=lin.scaling)
+        return
+    gb = G(lin.bias) if with_bias else None
     if gb is not None:
         ops.colsum16(dy16, gb, fp16, n_valid=n_valid, alpha=pa)
-    gw = G(lin_w)
+    gw = G(lin.weight)
     if gw is not None:
-        g2 = gw.view(gw.shape[0], -1) if gw2d is None else gw2d(gw)
-        ops.wgrad(dy16, x16, g2, fp16, n_valid=n_valid, k_valid=k_valid, k_off=k_off, alpha=pa)
+        ops.wgrad(dy16, x16, gw.view(gw.shape[0], -1), fp16, n_valid=n_valid, k_valid=k_valid, k_off=k_off, alpha=pa)
 
 
 def _block_backward(blk, ws, roll, t: BlockTape, sc: Scratch, g32, G, fp16):
@@ -224,25 +237,23 @@ def _block_backward(blk, ws, roll, t: BlockTape, sc: Scratch, g32, G, fp16):
     ops.linear(t.hidden, mlp._w2.get(mlp.linear2.weight), mlp.linear2.bias, sc.y32, sc.tmp16, False, fp16)
     ops.layernorm_bwd(sc.y32, g32, blk.norm2.weight, G(blk.norm2.weight), G(blk.norm2.bias), T, C, LNB_IDENT, fp16,
                       dx16=sc.dy16, scale=t.s2, palpha=pa)
-    _linear_bwd(sc.dy16, t.hidden, mlp.linear2.weight, mlp.linear2.bias, G, fp16)
+    _linear_bwd(sc.dy16, t.hidden, mlp.linear2, G, fp16)
     ops.dgrad(sc.dy16, _wt(mlp, "w2", mlp.linear2.weight, fp16), 1, fp16, out16=sc.dh16)
     ops.linear(t.xmid16, mlp._w1.get(mlp.linear1.weight), mlp.linear1.bias, None, sc.pre16, False, fp16)
     ops.gelu_bwd(sc.dh16, sc.pre16, fp16)
-    _linear_bwd(sc.dh16, t.xmid16, mlp.linear1.weight, mlp.linear1.bias, G, fp16)
+    _linear_bwd(sc.dh16, t.xmid16, mlp.linear1, G, fp16)
     ops.dgrad(sc.dh16, _wt(mlp, "w1", mlp.linear1.weight, fp16), 0, fp16, out32=g32, resid32=g32)
     # ---------------- x = shortcut + s1 * LN1(window_reverse(attention(window_partition(x))))   (:185-250)
     ops.linear(t.att, att._w2.get(att.linear2.weight), att.linear2.bias, sc.y32, sc.tmp16, False, fp16)
     ops.layernorm_bwd(sc.y32, g32, blk.norm1.weight, G(blk.norm1.weight), G(blk.norm1.bias), T, C, LNB_IDENT, fp16,
                       dx16=sc.dy16, scale=t.s1, palpha=pa)
-    _linear_bwd(sc.dy16, t.att, att.linear2.weight, att.linear2.bias, G, fp16)
+    _linear_bwd(sc.dy16, t.att, att.linear2, G, fp16)
     dattw = sc.dattw[int(roll)]
     ops.dgrad(sc.dy16, _wt(att, "w2", att.linear2.weight, fp16), 3, fp16, out16=dattw, grid=grid, roll=roll)
-    gbias = G(att.earth_specific_bias)
-    if gbias is None:          # frozen bias table (LoRA): the kernel still needs somewhere to accumulate
-        gbias = sc.__dict__.setdefault("dbias_sink", torch.zeros_like(att.earth_specific_bias))
+    gbias = G(att.earth_specific_bias)       # None (frozen table, LoRA): the kernel skips the accumulation
     ops.window_attention_bwd(t.qkv, dattw, att.earth_specific_bias, sc.dqkv, gbias, Z, H, W, C, att.head_number,
                              roll, fp16, palpha=pa)
-    _linear_bwd(sc.dqkv, t.xw, att.linear1.weight, att.linear1.bias, G, fp16)
+    _linear_bwd(sc.dqkv, t.xw, att.linear1, G, fp16)
     ops.dgrad(sc.dqkv, _wt(att, "w1", att.linear1.weight, fp16), 2, fp16, out32=g32, resid32=g32, grid=grid, roll=roll)
     ops.set_tag("")
 
@@ -269,10 +280,8 @@ def backward(model, tape: Tape, g_upper: torch.Tensor, g_surface: torch.Tensor, 
     pa = 1.0 / LOSS_SCALE[fp16]
     ops.recover_grad_gather(g_upper, g_surface, tape.dyu, tape.dys, lat, lon, fp16, scale=LOSS_SCALE[fp16])
     for src, k_off in ((tape.skip16, 0), (tape.final16, 192)):
-        _linear_bwd(tape.dyu, src[plane:], rec.conv.weight, rec.conv.bias if k_off == 0 else None, G, fp16,
-                    n_valid=160, k_off=k_off)
-        _linear_bwd(tape.dys, src[:plane], rec.conv_surface.weight, rec.conv_surface.bias if k_off == 0 else None, G,
-                    fp16, n_valid=64, k_off=k_off)
+        _linear_bwd(tape.dyu, src[plane:], rec.conv, G, fp16, n_valid=160, k_off=k_off, with_bias=k_off == 0)
+        _linear_bwd(tape.dys, src[:plane], rec.conv_surface, G, fp16, n_valid=64, k_off=k_off, with_bias=k_off == 0)
     wut = _wt(rec, "conv", rec.conv.weight, fp16, rows_pad=192)                   # [384, 192]
     wst = _wt(rec, "conv_surface", rec.conv_surface.weight, fp16, rows_pad=128)   # [384, 128]
     g_hi, g_skip = sh.g32, tape.g_skip
@@ -291,13 +300,13 @@ def backward(model, tape: Tape, g_upper: torch.Tensor, g_surface: torch.Tensor, 
     # ---------------- UpSample                              (models/layers.py:474-499)
     up = model.upsample
     ops.cast_rows(g_hi, sh.dy16, fp16)
-    _linear_bwd(sh.dy16, tape.up_a, up.linear2.weight, None, G, fp16)
+    _linear_bwd(sh.dy16, tape.up_a, up.linear2, G, fp16)
     ops.dgrad(sh.dy16, _wt(up, "w2", up.linear2.weight, fp16), 0, fp16, out32=sh.y32)
     ops.linear(tape.lo_out16, up._w1.get(up.linear1.weight), None, tape.u32, tape.u16, False, fp16)
     tape.du16.zero_()                                       # cropped positions (lat row 181) get no gradient
     ops.layernorm_bwd(tape.u32, sh.y32, up.norm.weight, G(up.norm.weight), G(up.norm.bias), hi.T, hi.C, LNB_UP, fp16,
                       dx16=tape.du16, grid=(hi.Z, hi.H, hi.W), palpha=pa)
-    _linear_bwd(tape.du16, tape.lo_out16, up.linear1.weight, None, G, fp16)
+    _linear_bwd(tape.du16, tape.lo_out16, up.linear1, G, fp16)
     g_lo = sl.g32
     ops.dgrad(tape.du16, _wt(up, "w1", up.linear1.weight, fp16), 0, fp16, out32=g_lo)
     done(up)
@@ -310,7 +319,7 @@ def backward(model, tape: Tape, g_upper: torch.Tensor, g_surface: torch.Tensor, 
     # ---------------- DownSample                            (models/layers.py:432-459)
     down = model.downsample
     ops.cast_rows(g_lo, sl.dy16, fp16)
-    _linear_bwd(sl.dy16, tape.down_a, down.linear.weight, None, G, fp16)
+    _linear_bwd(sl.dy16, tape.down_a, down.linear, G, fp16)
     ops.dgrad(sl.dy16, _wt(down, "w", down.linear.weight, fp16), 0, fp16, out32=tape.u32)
     ops.layernorm_bwd(tape.x32_skip, tape.u32, down.norm.weight, G(down.norm.weight), G(down.norm.bias), lo.T,
                       4 * hi.C, LNB_DOWN, fp16, dx32=g_skip, grid=(hi.Z, hi.H, hi.W), palpha=pa)
@@ -324,8 +333,8 @@ def backward(model, tape: Tape, g_upper: torch.Tensor, g_surface: torch.Tensor, 
     # ---------------- PatchEmbedding                        (models/layers.py:40-93; inputs need no gradient)
     emb = model._input_layer
     ops.cast_rows(g_skip, sh.dy16, fp16)
-    _linear_bwd(sh.dy16[plane:], tape.a_u, emb.conv.weight, emb.conv.bias, G, fp16)
-    _linear_bwd(sh.dy16[:plane], tape.a_s, emb.conv_surface.weight, emb.conv_surface.bias, G, fp16, k_valid=112)
+    _linear_bwd(sh.dy16[plane:], tape.a_u, emb.conv, G, fp16)
+    _linear_bwd(sh.dy16[:plane], tape.a_s, emb.conv_surface, G, fp16, k_valid=112)
     done(emb)
     if reducer is not None:
         reducer.finish()

@@ -104,3 +104,50 @@ def test_gradients_accumulate_and_frozen_parameters_are_skipped():
         else:
             assert rel_l2(q.grad, 2 * g1[n]) < 1e-3, n           # .grad accumulates (fp32 atomics: order varies)
     training.release_tape(model)
+
+
+def test_lora_training_gradients():
+    """lora_tune: frozen base, rank-16 adapters on the 67 nn.Linear modules, the two output
+    convs trained in full.  Gradients of the adapters and of modules_to_save against oracle autograd through
+    ``W + (alpha/r) B A`` (peft semantics, lora_dropout = 0)."""
+    pb, p, model, (up, sf, stats, maps, ch), (tu, ts) = _setup("bf16")
+    from pangu_pytorch_b200 import lora, training
+    lora.add_lora(model, r=16, lora_alpha=16.0, lora_dropout=0.0)
+    model.to(DEV).train()
+    loras = {n: m for n, m in model.named_modules() if isinstance(m, lora.LoraLinear)}
+    assert len(loras) == 67
+    g = torch.Generator().manual_seed(11)
+    for m in loras.values():                      # peft starts B at zero; give the adapters something to do
+        m.B.data.copy_(0.02 * torch.randn(m.B.shape, generator=g))
+    trainable = [n for n, q in model.named_parameters() if q.requires_grad]
+    assert len(trainable) == 2 * 67 + 4
+    for blk in [m for m in model.modules() if hasattr(m, "drop_path")]:
+        blk.drop_path.drop_prob = 0.0
+    dstats = [s.to(DEV) for s in stats]
+    out, out_s = model(up.to(DEV), sf.to(DEV), dstats, maps.to(DEV), ch.to(DEV))
+    # oracle: autograd through the merged weights
+    leaves, eff = {}, dict(p)
+    for n, m in loras.items():
+        a = m.A.detach().cpu().clone().requires_grad_(True)
+        b = m.B.detach().cpu().clone().requires_grad_(True)
+        leaves[n + ".lora_A.default.weight"], leaves[n + ".lora_B.default.weight"] = a, b
+        eff[n + ".weight"] = p[n + ".weight"] + m.scaling * (b @ a)
+    for n in ("_output_layer.conv.weight", "_output_layer.conv.bias", "_output_layer.conv_surface.weight",
+              "_output_layer.conv_surface.bias"):
+        leaves[n] = eff[n] = p[n].clone().requires_grad_(True)
+    ou, os_ = O.forward_train(eff, up, sf, stats, maps, ch)
+    ou.retain_grad(); os_.retain_grad()
+    tun, tsn = O.norm_data(tu, ts, O.output_statistics(stats))
+    O.weighted_l1_loss(ou, os_, tun, tsn).backward()
+    torch.autograd.backward((out, out_s), (ou.grad.to(DEV), os_.grad.to(DEV)))
+    torch.cuda.synchronize()
+    named = dict(model.named_parameters())
+    worst = sorted(((rel_l2(named[n].grad, leaves[n].grad), n) for n in trainable), reverse=True)
+    print("[lora] worst gradient rel-L2:", worst[:4])
+    assert worst[0][0] < 5e-2, worst[:4]
+    assert all(q.grad is None for n, q in named.items() if n not in trainable)
+    # checkpoint round trip: peft-style keys -> merged plain weights == the effective weights the kernels used
+    merged = lora.merge_lora_state_dict(lora.peft_state_dict(model))
+    n0 = "layers.EarthSpecificLayer1.blocks.EarthSpecificBlock2.attention.linear1"
+    assert torch.allclose(merged[n0 + ".weight"].cpu(), eff[n0 + ".weight"].detach(), atol=1e-6)
+    training.release_tape(model)
