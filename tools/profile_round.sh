@@ -14,3 +14,11 @@ cap attention_lo window_attention_tc 2
 cap CfgQKV_lo CfgQKV 2
 cap CfgLNRes192_mlp2 CfgLNRes192 1
 ls -la gpurun_out
+# backward kernels (training step workload)
+T="python tools/train_times.py"
+capt() {
+  timeout 500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" --launch-skip $3 -c 1 -f -o gpurun_out/prof_${TAG}_$1 $T > gpurun_out/prof_${TAG}_$1.log 2>&1
+}
+capt attention_bwd_lo window_attention_bwd 6
+capt wgrad_lo wgrad_kernel 20
+ls -la gpurun_out
