@@ -157,23 +157,53 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// d pre = d hidden * gelu'(pre),  gelu'(x) = Phi(x) + x phi(x)   (in place on dh); 8 elements per thread
+// d pre = d hidden * gelu'(pre),  gelu'(x) = Phi(x) + x phi(x)   (in place on dh); 8 elements per thread.
+// Phi through the same degree-7 fit of log2(erfc(t))/t as the forward GELU (common.cuh): erfc(t) = 2^(t P7(t)),
+// Phi(x) = 1 - erfc(|x|/sqrt 2)/2 for x >= 0, erfc(|x|/sqrt 2)/2 for x < 0; phi through one more ex2.approx.
+// max |error| of gelu' ~ 6e-7, far below the 16-bit rounding of the result.
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float ax = fabsf(x);
+  const float t = fminf(ax * 0.70710678118654752440f, 4.0f);
+  float p = -5.904116739e-06f;
+  p = fmaf(p, t, 6.987359289e-05f);
+  p = fmaf(p, t, -6.779016748e-05f);
+  p = fmaf(p, t, -3.477876114e-03f);
+  p = fmaf(p, t, 3.092580434e-02f);
+  p = fmaf(p, t, -1.497507845e-01f);
+  p = fmaf(p, t, -9.181910519e-01f);
+  p = fmaf(p, t, -1.627914489e+00f);
+  const float half_erfc = 0.5f * ex2_approx(p * t);
+  const float cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+  const float pdf = 0.3989422804014327f * ex2_approx(-0.72134752044448170368f * x * x);   // exp(-x^2/2) = 2^(-x^2 log2(e)/2)
+  return fmaf(x, pdf, cdf);
+}
+
 template <bool kFp16>
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(uint16_t* __restrict__ dh, const uint16_t* __restrict__ pre, size_t n8) {
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
-    uint4 d = reinterpret_cast<const uint4*>(dh)[i];
-    const uint4 p = ldg_nc16(reinterpret_cast<const uint4*>(pre) + i);
-    uint32_t* dw = reinterpret_cast<uint32_t*>(&d);
-    const uint32_t* pw = reinterpret_cast<const uint32_t*>(&p);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float x0 = unpack16_lo<kFp16>(pw[k]), x1 = unpack16_hi<kFp16>(pw[k]);
-      float g0 = unpack16_lo<kFp16>(dw[k]), g1 = unpack16_hi<kFp16>(dw[k]);
-      const float c0 = 0.5f * (1.0f + erff(x0 * 0.70710678118654752440f)) + x0 * 0.3989422804014327f * __expf(-0.5f * x0 * x0);
-      const float c1 = 0.5f * (1.0f + erff(x1 * 0.70710678118654752440f)) + x1 * 0.3989422804014327f * __expf(-0.5f * x1 * x1);
-      dw[k] = pack16<kFp16>(g0 * c0, g1 * c1);
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < n8; i0 += 2 * stride) {
+    const size_t i1 = i0 + stride;
+    const bool two = i1 < n8;
+    uint4 d[2], p[2];
+    d[0] = ldg16(reinterpret_cast<const uint4*>(dh) + i0);      // coherent: dh is rewritten in place
+    p[0] = ldg_nc16(reinterpret_cast<const uint4*>(pre) + i0);
+    if (two) {
+      d[1] = ldg16(reinterpret_cast<const uint4*>(dh) + i1);
+      p[1] = ldg_nc16(reinterpret_cast<const uint4*>(pre) + i1);
     }
-    reinterpret_cast<uint4*>(dh)[i] = d;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      uint32_t* dw = reinterpret_cast<uint32_t*>(&d[u]);
+      const uint32_t* pw = reinterpret_cast<const uint32_t*>(&p[u]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x0 = unpack16_lo<kFp16>(pw[k]), x1 = unpack16_hi<kFp16>(pw[k]);
+        const float g0 = unpack16_lo<kFp16>(dw[k]), g1 = unpack16_hi<kFp16>(dw[k]);
+        dw[k] = pack16<kFp16>(g0 * gelu_grad(x0), g1 * gelu_grad(x1));
+      }
+      reinterpret_cast<uint4*>(dh)[u == 0 ? i0 : i1] = d[u];
+    }
   }
 }
 
@@ -190,13 +220,22 @@ __global__ void __launch_bounds__(256) colsum16_kernel(const uint16_t* __restric
   const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (rl < rpi) {
-    for (int m = blockIdx.x * rpi + rl; m < M; m += gridDim.x * rpi) {
-      const uint4 v = ldg_nc16(src + size_t(m) * ld + cg * 8);
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+    const int step = gridDim.x * rpi;
+    for (int m = blockIdx.x * rpi + rl; m < M; m += 4 * step) {
+      uint4 v[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        acc[2 * k] += unpack16_lo<kFp16>(w[k]);
-        acc[2 * k + 1] += unpack16_hi<kFp16>(w[k]);
+      for (int u = 0; u < 4; ++u) {          // four independent 16 B loads in flight per thread
+        const int mm = m + u * step;
+        v[u] = mm < M ? ldg_nc16(src + size_t(mm) * ld + cg * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[u]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[2 * k] += unpack16_lo<kFp16>(w[k]);
+          acc[2 * k + 1] += unpack16_hi<kFp16>(w[k]);
+        }
       }
     }
 #pragma unroll
