@@ -34,6 +34,14 @@ FLOPS_PER_STEP = 8.4212e12          # dense-contraction FLOPs of
 FLOPS_BLOCKS = 8.1325e12            # attention + MLP of the 16 blocks
 LAT, LON = 721, 1440
 STRIP = 96                          # CPU sample: full-depth forward on a 96-column strip (1/15 of the grid)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels behind each entry point, from the committed
+# `ncu --set full` captures (profiles/r01c_*.md; an entry point = the sum of its kernels)
+NCU_TRAFFIC_BYTES = {
+    "pangu_mlp_ln_residual[lo]": (102.0e6 + 352.3e6) + (628.9e6 + 246.0e6),     # CfgMLP1 + CfgLNRes384
+    "pangu_mlp_ln_residual[hi]": None,
+    "pangu_window_attention[lo]": 405.9e6 + 92.6e6,
+    "pangu_qkv[lo]": 107.1e6 + 270.3e6,
+}
 
 
 def peaks():
@@ -291,7 +299,8 @@ def run_gpu_arm(args):
     dom_ms = kern[dom][0] / kern[dom][1]
     achieved = algo_flops[dom] / (dom_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 1), "peak": pk["tflops_sustained"],
-                "unit": "TFLOP/s", "frac": round(achieved / pk["tflops_sustained"], 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(achieved / pk["tflops_sustained"], 4),
+                "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "ncu --set full, profiles/r01c_*.md (bytes per launch)",
                 "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "avg_launch_ms": round(dom_ms, 4), "algorithmic_flops_per_launch": algo_flops[dom],
                 "step_tflops": round(FLOPS_PER_STEP / (ms_per_step * 1e-3) / 1e12, 1),

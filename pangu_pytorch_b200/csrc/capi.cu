@@ -111,6 +111,12 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t k,
 // ---------------------------------------------------------------------------------------
 // GEMM configurations (epilogue variants)
 // ---------------------------------------------------------------------------------------
+#ifndef PANGU_EPI_WARPS_MLP1
+#define PANGU_EPI_WARPS_MLP1 16     // BN 256: 4 column groups x 2 chunks
+#endif
+#ifndef PANGU_EPI_WARPS_QKV
+#define PANGU_EPI_WARPS_QKV 8       // BN 192: measured no gain from 12 warps (HBM / MMA bound)
+#endif
 struct CfgBase {
   static constexpr bool LN = false, GELU = false, SCALEQ = false, RESID = false, OUT32 = false, OUT16 = false,
                         GROUPCOL = false;
@@ -121,16 +127,19 @@ struct CfgBase {
   static constexpr bool NSPLIT = false;  // CTA pair splits the LayerNorm row (N) instead of M; stats via DSMEM
   static constexpr bool HEADMAJOR = false;  // TMA16: output stored as [N/32 planes][plane_rows][32]
   static constexpr bool RESTMA = false;  // LN + residual epilogue whose fp32 stream moves by TMA (identity row map)
+  static constexpr int EPI_WARPS = 8;    // 4 x column groups (TMA16 configs may use 12 / 16: latency-bound epilogues)
 };
 struct CfgQKV : CfgBase {      // linear1 of attention: bias, q-scale, 16-bit out
   static constexpr int BN = 192, UN = 192, STAGES = 4;
   static constexpr bool SCALEQ = true, OUT16 = true, TMA16 = true, HEADMAJOR = true;
   static constexpr int CLUSTER = 2;
+  static constexpr int EPI_WARPS = PANGU_EPI_WARPS_QKV;
 };
 struct CfgMLP1 : CfgBase {     // Mlp.linear1: bias + exact GELU, 16-bit out
   static constexpr int BN = 256, UN = 256, STAGES = 3;
   static constexpr bool GELU = true, OUT16 = true, TMA16 = true;
   static constexpr int CLUSTER = 2;
+  static constexpr int EPI_WARPS = PANGU_EPI_WARPS_MLP1;
 };
 struct CfgLNRes192 : CfgBase { // bias + LayerNorm(192) + residual, fp32 + 16-bit out
   static constexpr int BN = 192, UN = 192, STAGES = 3;
@@ -164,6 +173,7 @@ struct CfgLin16 : CfgBase {    // (bias) -> 16-bit row-major (pre-activation rec
   static constexpr int BN = 256, UN = 256, STAGES = 3;
   static constexpr bool OUT16 = true, TMA16 = true;
   static constexpr int CLUSTER = 2;
+  static constexpr int EPI_WARPS = PANGU_EPI_WARPS_MLP1;
 };
 struct CfgAcc192 : CfgBase {   // fp32 out = residual + acc (dgrad accumulating into the gradient stream), row maps
   static constexpr int BN = 192, UN = 192, STAGES = 4;
@@ -239,7 +249,7 @@ static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t 
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kNumThreads);
+  cfg.blockDim = dim3(T::THREADS);
   cfg.dynamicSmemBytes = T::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

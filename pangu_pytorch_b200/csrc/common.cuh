@@ -122,6 +122,17 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t raddr, float a, float b, 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t rbar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
 }
+// "slot free" style signal to a peer CTA: the reads it covers have already been consumed by this thread, so no
+// release fence (the .release form costs a CCTL.IVALL + ERRBAR pair per arrive)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t rbar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+// 16-byte store into a peer CTA's shared memory that signals complete_tx(16) on the peer's mbarrier when it lands:
+// data and notification travel together, no fence on either side
+__device__ __forceinline__ void st_async_cluster_f4(uint32_t raddr, float a, float b, float c, float d, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(rbar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0, ok = 0;
   while (true) {

@@ -82,8 +82,15 @@ struct GemmTraits {
   static constexpr int RES_SLOTS = BN / 64;          // chunks of 32 columns per epilogue warp and tile
   static constexpr int SLAB_BYTES = Cfg::RESTMA ? RES_SLOTS * 4096 : Cfg::TMA16 ? 4096 : ((32 * STG_PITCH + 511) / 512) * 512;
   static constexpr int PAR_BYTES = 3 * BN * 4;       // bias / gamma / beta (shared by the 8 epilogue warps)
-  static constexpr int TAB_BYTES = 8 * 64 * 4;       // per warp: row -> token, row -> 16-bit destination row
-  static constexpr int EPI_BYTES = ((8 * SLAB_BYTES + PAR_BYTES + TAB_BYTES + 1023) / 1024) * 1024;
+  // Epilogue warps: 4 per column group (one per TMEM lane quadrant).  The plain 16-bit (TMA16) epilogues are bound by
+  // instruction latency, not issue slots (ncu: 2 warps per scheduler at ~0.2 IPC each), so those configs may ask for
+  // 3 or 4 column groups; the LayerNorm / row-mapped epilogues keep 2.
+  static constexpr int EPI_WARPS = Cfg::EPI_WARPS;
+  static constexpr int GROUPS = EPI_WARPS / 4;
+  static constexpr int EPI_THREADS = 32 * EPI_WARPS;
+  static constexpr int THREADS = 64 + EPI_THREADS;   // warp 0 TMA, warp 1 MMA, then the epilogue warps
+  static constexpr int TAB_BYTES = EPI_WARPS * 64 * 4;   // per warp: row -> token, row -> 16-bit destination row
+  static constexpr int EPI_BYTES = ((EPI_WARPS * SLAB_BYTES + PAR_BYTES + TAB_BYTES + 1023) / 1024) * 1024;
   static constexpr int BAR_BYTES = 256 + (Cfg::NSPLIT ? 2 * 128 * 16 : 0)    // + LN partial-stat mailboxes
                                    + (Cfg::RESTMA ? 8 * RES_SLOTS * 8 : 0);   // + per-warp residual-landed barriers
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
@@ -91,7 +98,8 @@ struct GemmTraits {
   static_assert(CL == 1 || (CL == 2 && (BN / 2) % 8 == 0 && BN / 2 <= 256), "bad cluster B split");
   static_assert(!NSPLIT || (CL == 2 && Cfg::LN && NUM_B == 1), "NSPLIT: LayerNorm row split over a CTA pair");
   static_assert(BN % CH == 0 && (CH == 16 || CH == 32), "bad epilogue chunk");
-  static_assert(!Cfg::TMA16 || BN % 64 == 0, "TMA16: both warpgroups take whole 32-column chunks");
+  static_assert(EPI_WARPS % 4 == 0 && (EPI_WARPS == 8 || Cfg::TMA16), "more than 8 epilogue warps: TMA16 epilogue only");
+  static_assert(!Cfg::TMA16 || BN % (32 * GROUPS) == 0, "TMA16: every column group takes whole 32-column chunks");
   static_assert(!Cfg::RESTMA || (Cfg::LN && Cfg::RESID && Cfg::OUT32 && Cfg::OUT16 && CH == 32 && BN % 64 == 0 &&
                                  Cfg::RECOVER == 0 && !Cfg::TMA16), "RESTMA: LayerNorm + residual epilogue");
   static_assert(SLAB_BYTES % 1024 == 0 || !Cfg::RESTMA, "SWIZZLE_128B tiles need 1024 B alignment");
@@ -100,16 +108,14 @@ struct GemmTraits {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
 
-constexpr int kNumThreads = 320;      // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-constexpr int kEpiThreads = 256;
-
 template <class Cfg, bool kFp16>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(GemmTraits<Cfg>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
             const GemmShape shape, const EpiArgs ep) {
   using T = GemmTraits<Cfg>;
   constexpr int BN = T::BN, UN = T::UN, CH = T::CH;
+  constexpr int kEpiThreads = T::EPI_THREADS;
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for SWIZZLE_128B; offset arithmetic (not an int->pointer cast) so that the
   // compiler keeps the shared address space and emits LDS/STS instead of generic LD/ST
@@ -123,7 +129,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tempty_bar = tfull_bar + T::ACC_STAGES;  // [ACC_STAGES]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + T::ACC_STAGES);
   // NSPLIT: LayerNorm partial statistics of the peer CTA arrive here (one float4 per row and accumulator stage)
-  [[maybe_unused]] uint64_t* xfull_bar = bars + 24;     // [2] 128 remote arrivals (peer's row owners)
+  [[maybe_unused]] uint64_t* xfull_bar = bars + 24;     // [2] one local arrive.expect_tx + 128 x 16 B of st.async from the peer's row owners
   [[maybe_unused]] uint64_t* xempty_bar = bars + 26;    // [2] 256 remote arrivals (peer's readers)
   [[maybe_unused]] float4* xch = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][128]
   // RESTMA: residual tile of (epilogue warp, slot) has landed
@@ -153,7 +159,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int a = 0; a < T::ACC_STAGES; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], kEpiThreads);
-      if constexpr (T::NSPLIT) { mbar_init(&xfull_bar[a], 128); mbar_init(&xempty_bar[a], kEpiThreads); }
+      if constexpr (T::NSPLIT) { mbar_init(&xfull_bar[a], 1); mbar_init(&xempty_bar[a], kEpiThreads); }
     }
     if constexpr (Cfg::RESTMA) {
       for (int i = 0; i < 8 * T::RES_SLOTS; ++i) mbar_init(&rfull_bar[i], 1);
@@ -244,10 +250,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // the two warps of a lane quadrant take alternate column chunks.  No cross-warp barrier is needed in
     // the steady state: tables, staging slab and output stores are all per warp (__syncwarp only).
     const int quad = warp & 3;                 // TMEM lane quadrant
-    const int half = (warp - 2) >> 2;          // 0 / 1: which column chunks
-    const int wslot = warp - 2;                // 0..7
+    const int half = (warp - 2) >> 2;          // column group 0 .. GROUPS-1: which column chunks
+    const int wslot = warp - 2;                // 0 .. EPI_WARPS-1
     uint8_t* slab = wg_area + wslot * T::SLAB_BYTES;                       // [32 rows][STG_PITCH] or 2 x 2 KB (TMA16)
-    float* s_bias = reinterpret_cast<float*>(wg_area + 8 * T::SLAB_BYTES); // shared by the 8 warps
+    float* s_bias = reinterpret_cast<float*>(wg_area + T::EPI_WARPS * T::SLAB_BYTES); // shared by the epilogue warps
     float* s_gamma = s_bias + BN;
     float* s_beta = s_gamma + BN;
     int* s_tok = reinterpret_cast<int*>(s_beta + BN) + wslot * 64;         // per warp: row -> token
@@ -282,15 +288,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // flight while the current one is being converted.
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        constexpr int NCH = BN / 64;               // chunks of 32 columns per warp
+        constexpr int CSTEP = 32 * T::GROUPS;      // column distance between consecutive chunks of one warp
+        constexpr int NCH = BN / CSTEP;            // chunks of 32 columns per warp
         uint32_t rb[2][32];
         tmem_ld32(tacc + half * 32, rb[0]);
         tmem_ld_wait();
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
-          const int c0 = half * 32 + 64 * ci;
+          const int c0 = half * 32 + CSTEP * ci;
           uint32_t (&r)[32] = rb[ci & 1];
-          if (ci + 1 < NCH) tmem_ld32(tacc + c0 + 64, rb[(ci + 1) & 1]);
+          if (ci + 1 < NCH) tmem_ld32(tacc + c0 + CSTEP, rb[(ci + 1) & 1]);
           if (lane == 0) bulk_wait_read<1>();      // the store issued two chunks ago has read this slab
           __syncwarp();
           const int ncol0 = n_blk * BN + c0;
@@ -393,13 +400,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const float my1 = s1a + s1b, my2 = s2a + s2b;
             const uint32_t peer = uint32_t(cta_rank ^ 1);
             if (half == 0) {
+              if (wslot == 0 && lane == 0) mbar_arrive_expect_tx(&xfull_bar[acc], 128 * 16);   // this CTA's inbox: 128 rows x 16 B
               mbar_wait_cluster(&xempty_bar[acc], acc_phase ^ 1);  // peer has consumed my previous message in this slot
-              st_cluster_f4(mapa_u32(smem_u32(&xch[acc * 128 + quad * 32 + lane]), peer), my1, my2, shift, 0.f);
-              mbar_arrive_cluster(mapa_u32(smem_u32(&xfull_bar[acc]), peer));
+              st_async_cluster_f4(mapa_u32(smem_u32(&xch[acc * 128 + quad * 32 + lane]), peer), my1, my2, shift, 0.f,
+                                  mapa_u32(smem_u32(&xfull_bar[acc]), peer));
             }
             mbar_wait_cluster(&xfull_bar[acc], acc_phase);
             const float4 o = xch[acc * 128 + quad * 32 + lane];
-            mbar_arrive_cluster(mapa_u32(smem_u32(&xempty_bar[acc]), peer));
+            mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&xempty_bar[acc]), peer));
             const float n = float(BN), inv_n2 = 1.0f / float(2 * BN);
             const float mu = (my1 + n * shift + o.x + n * o.z) * inv_n2;
             const float d0 = shift - mu, d1 = o.z - mu;
@@ -553,13 +561,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const float my1 = s1a + s1b, my2 = s2a + s2b;
           const uint32_t peer = uint32_t(cta_rank ^ 1);
           if (half == 0) {
+            if (wslot == 0 && lane == 0) mbar_arrive_expect_tx(&xfull_bar[acc], 128 * 16);   // this CTA's inbox: 128 rows x 16 B
             mbar_wait_cluster(&xempty_bar[acc], acc_phase ^ 1);  // peer has consumed my previous message in this slot
-            st_cluster_f4(mapa_u32(smem_u32(&xch[acc * 128 + quad * 32 + lane]), peer), my1, my2, shift, 0.f);
-            mbar_arrive_cluster(mapa_u32(smem_u32(&xfull_bar[acc]), peer));
+            st_async_cluster_f4(mapa_u32(smem_u32(&xch[acc * 128 + quad * 32 + lane]), peer), my1, my2, shift, 0.f,
+                                mapa_u32(smem_u32(&xfull_bar[acc]), peer));
           }
           mbar_wait_cluster(&xfull_bar[acc], acc_phase);
           const float4 o = xch[acc * 128 + quad * 32 + lane];
-          mbar_arrive_cluster(mapa_u32(smem_u32(&xempty_bar[acc]), peer));
+          mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&xempty_bar[acc]), peer));
           const float n = float(BN), inv_n2 = 1.0f / float(2 * BN);
           const float mu = (my1 + n * shift + o.x + n * o.z) * inv_n2;
           const float d0 = shift - mu, d1 = o.z - mu;
