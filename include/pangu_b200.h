@@ -138,6 +138,18 @@ int pangu_l1_loss(const float* out_upper, const float* out_surface, const float*
                   const float* upper_weights_host, const float* surface_weights_host, float* loss, double* ws_acc,
                   float* grad_upper, float* grad_surface, int lat, int lon, void* stream);
 
+/* Evaluation scores of the reference's test loop (models/pangu_sample.py:236-270): latitude-weighted RMSE
+ * (era5_data/score.py:92-105) and ACC (era5_data/score.py:123-135) per plane, p = var*13 + level for the 65
+ * upper-air planes, 65 + var for the 4 surface planes; anomalies are taken against the scalar statistics mean of
+ * the plane, as the reference does.  normalised != 0: out_* are the model's normalised outputs (normBackData is
+ * applied on the fly); 0: physical fields.  tgt_* are physical.  lat_weights[lat]: the weights of
+ * latitude_weighting_factor_torch (host-computed, caller-owned device array).  ws_acc: double[276] scratch.
+ * rmse / acc: float[69]. */
+int pangu_scores(const float* out_upper, const float* out_surface, const float* tgt_upper, const float* tgt_surface,
+                 const float* surface_mean, const float* surface_std, const float* upper_mean, const float* upper_std,
+                 const float* lat_weights, double* ws_acc, float* rmse, float* acc, int lat, int lon, int normalised,
+                 void* stream);
+
 /* Generic nn.Linear forward used by the stand-alone module API (EarthAttention3D.linear2,
  * Mlp.linear1/2 outside the fused block path) and by the unit tests of the tcgen05 GEMM engine:
  * out = a16 [M,K] * w16 [N,K]^T + bias.  gelu == 0: fp32 out32 and 16-bit out16 (both required),

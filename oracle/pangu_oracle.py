@@ -20,6 +20,8 @@ What it restates (all citations relative to the reference checkout):
 * ``era5_data/utils_data.py:315-330`` normData / normBackData     -> ``norm_data`` / ``norm_back_data``
 * ``era5_data/utils_dist.py:125-134`` gather_grad                 -> ``mean_of_grads``
 * ``finetune/lora_tune.py:124-139`` peft LoRA (third party, unpinned) -> ``lora_linear``
+* ``era5_data/score.py:83-135`` latitude-weighted RMSE / ACC    -> ``weighted_rmse_channels`` / ``weighted_acc_channels``
+* ``models/pangu_sample.py:203-270`` evaluation loop scores       -> ``evaluation_scores``
 
 Unlike the reference (which chains view/permute/roll/pad and hard-codes 181x360 in
 three places) the oracle is written against *closed-form index maps* (SURVEY.md
@@ -314,6 +316,39 @@ def weighted_l1_loss(out_u, out_s, tgt_u, tgt_s) -> Tensor:
     wu = torch.tensor(UPPER_WEIGHTS, dtype=out_u.dtype).view(1, 5, 1, 1, 1)
     ws = torch.tensor(SURFACE_WEIGHTS, dtype=out_s.dtype).view(1, 4, 1, 1)
     return ((out_u - tgt_u).abs() * wu).mean() + 0.25 * ((out_s - tgt_s).abs() * ws).mean()
+
+
+def latitude_weights(num_lat: int) -> Tensor:
+    """``latitude_weighting_factor_torch`` (era5_data/score.py:83-90; the reference writes 3.1416 for pi)."""
+    j = torch.arange(num_lat, dtype=torch.float64)
+    c = torch.cos(3.1416 / 180.0 * (90.0 - j * 180.0 / float(num_lat - 1)))
+    return num_lat * c / c.sum()
+
+
+def weighted_rmse_channels(pred: Tensor, target: Tensor) -> Tensor:
+    """``weighted_rmse_torch_channels`` (era5_data/score.py:92-105): ``[..., lat, lon]`` -> ``[...]``."""
+    w = latitude_weights(pred.shape[-2]).to(pred.dtype).view(-1, 1)
+    return torch.sqrt(torch.mean(w * (pred - target) ** 2.0, dim=(-1, -2)))
+
+
+def weighted_acc_channels(pred: Tensor, target: Tensor) -> Tensor:
+    """``weighted_acc_torch_channels`` (era5_data/score.py:123-135) on anomalies."""
+    w = latitude_weights(pred.shape[-2]).to(pred.dtype).view(-1, 1)
+    return torch.sum(w * pred * target, dim=(-1, -2)) / torch.sqrt(
+        torch.sum(w * pred * pred, dim=(-1, -2)) * torch.sum(w * target * target, dim=(-1, -2)))
+
+
+def evaluation_scores(out_u, out_s, tgt_u, tgt_s, statistics):
+    """Scores of the reference's test loop (models/pangu_sample.py:203-270): ``normBackData`` of the model outputs,
+    RMSE per (variable, level), ACC on anomalies against the scalar statistics means.  Returns
+    (rmse_upper [5,13], rmse_surface [4], acc_upper [5,13], acc_surface [4])."""
+    ostats = output_statistics(statistics)
+    pu, ps = norm_back_data(out_u, out_s, ostats)
+    s_mean, _, u_mean, _ = ostats
+    ru, rs = weighted_rmse_channels(pu[0], tgt_u[0]), weighted_rmse_channels(ps[0], tgt_s[0])
+    au = weighted_acc_channels(pu[0] - u_mean[0], tgt_u[0] - u_mean[0])
+    as_ = weighted_acc_channels(ps[0] - s_mean[0], tgt_s[0] - s_mean[0])
+    return ru, rs, au, as_
 
 
 def rollout(p, upper, surface, statistics, maps, const_h, steps: int):

@@ -32,6 +32,7 @@ SIGNATURES = {
     "pangu_linear": [_P] * 5 + [_I, _I, _I, _I, _I, _P],
     "pangu_denorm_fields": [_P] * 6 + [_I, _I, _P],
     "pangu_l1_loss": [_P] * 14 + [_I, _I, _P],
+    "pangu_scores": [_P] * 12 + [_I, _I, _I, _P],
     "pangu_cast16_t": [_P, _P, _I, _I, _I, _I, _I, _P],
     "pangu_dgrad": [_P] * 6 + [_I] * 9 + [_P],
     "pangu_wgrad": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P],

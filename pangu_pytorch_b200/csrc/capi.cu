@@ -638,6 +638,24 @@ extern "C" int pangu_l1_loss(const float* out_upper, const float* out_surface, c
   return 0;
 }
 
+extern "C" int pangu_scores(const float* out_upper, const float* out_surface, const float* tgt_upper,
+                            const float* tgt_surface, const float* surface_mean, const float* surface_std,
+                            const float* upper_mean, const float* upper_std, const float* lat_weights, double* ws_acc,
+                            float* rmse, float* acc, int lat, int lon, int normalised, void* stream) {
+  PG_TRY(ensure_init());
+  PG_REQUIRE(lat > 0 && lon > 0 && lon % 4 == 0, "scores: lon must be a positive multiple of 4");
+  PG_REQUIRE(out_upper && out_surface && tgt_upper && tgt_surface && lat_weights && ws_acc && rmse && acc, "scores: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ScoreArgs a{out_upper, out_surface, tgt_upper, tgt_surface, surface_mean, surface_std, upper_mean, upper_std,
+              lat_weights, ws_acc, lat, lon, normalised};
+  PG_CUDA(cudaMemsetAsync(ws_acc, 0, 69 * 4 * sizeof(double), s));
+  dim3 grid(lat < 32 ? lat : 32, 69);
+  scores_kernel<<<grid, 256, 0, s>>>(a);
+  scores_finalize_kernel<<<1, 96, 0, s>>>(ws_acc, rmse, acc, 1.0 / (double(lat) * lon));
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int pangu_linear(const void* a16, const void* w16, const float* bias, float* out32, void* out16, int M,
                             int N, int K, int gelu, int fp16, void* stream) {
   PG_TRY(ensure_init());

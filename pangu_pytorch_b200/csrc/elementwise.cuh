@@ -260,6 +260,78 @@ __global__ void l1_finalize_kernel(const double* acc, float* loss, double inv_nu
 }
 
 // ---------------------------------------------------------------------------------------
+// Latitude-weighted RMSE and ACC of the reference's evaluation loop (era5_data/score.py:92-105, 123-135 as called
+// from models/pangu_sample.py:236-270), one value per plane p (65 upper-air (variable, level) planes, 4 surface):
+//   w_j   = num_lat * cos(3.1416/180 * lat_j) / sum_j cos(3.1416/180 * lat_j),   lat_j = 90 - j * 180 / (num_lat - 1)
+//   rmse  = sqrt(mean_{lat,lon} w (pred - tgt)^2)
+//   acc   = sum w a b / sqrt(sum w a^2 * sum w b^2),   a = pred - mean_p, b = tgt - mean_p   (mean_p: the scalar
+//           statistics mean of the plane, models/pangu_sample.py:250-254)
+// pred may be the model's NORMALISED output (normalised != 0): pred_phys = out * std_p + mean_p is formed on the
+// fly, so the scores need no separate normBackData pass.  Partial sums in fp64 (4 per plane).
+struct ScoreArgs {
+  const float* out_u; const float* out_s; const float* tgt_u; const float* tgt_s;
+  const float* s_mean; const float* s_std; const float* u_mean; const float* u_std;
+  const float* wlat;      // [lat] latitude weights
+  double* acc;            // [69][4] zero-initialised: sum w d^2, sum w a b, sum w a^2, sum w b^2
+  int lat, lon, normalised;
+};
+__global__ void __launch_bounds__(256) scores_kernel(const ScoreArgs a) {
+  const int p = blockIdx.y;
+  float m, s;
+  const float *o, *t;
+  const size_t plane = size_t(a.lat) * a.lon;
+  if (p < 65) {
+    const int c = p / 13, l = p % 13;
+    m = a.u_mean[(12 - l) * 5 + c]; s = a.u_std[(12 - l) * 5 + c];
+    o = a.out_u + size_t(p) * plane; t = a.tgt_u + size_t(p) * plane;
+  } else {
+    m = a.s_mean[p - 65]; s = a.s_std[p - 65];
+    o = a.out_s + size_t(p - 65) * plane; t = a.tgt_s + size_t(p - 65) * plane;
+  }
+  const float ps = a.normalised ? s : 1.f, pm = a.normalised ? 0.f : m;   // anomaly a = out * std (normalised) or pred - mean
+  float sd = 0.f, sab = 0.f, saa = 0.f, sbb = 0.f;
+  const int lon4 = a.lon / 4;
+  for (int row = blockIdx.x; row < a.lat; row += gridDim.x) {
+    const float w = a.wlat[row];
+    const float4* o4 = reinterpret_cast<const float4*>(o + size_t(row) * a.lon);
+    const float4* t4 = reinterpret_cast<const float4*>(t + size_t(row) * a.lon);
+    float rd = 0.f, rab = 0.f, raa = 0.f, rbb = 0.f;
+    for (int i = threadIdx.x; i < lon4; i += blockDim.x) {
+      const float4 ov = o4[i], tv = t4[i];
+      const float av[4] = {ov.x * ps - pm, ov.y * ps - pm, ov.z * ps - pm, ov.w * ps - pm};
+      const float bv[4] = {tv.x - m, tv.y - m, tv.z - m, tv.w - m};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float d = av[k] - bv[k];
+        rd = fmaf(d, d, rd); rab = fmaf(av[k], bv[k], rab); raa = fmaf(av[k], av[k], raa); rbb = fmaf(bv[k], bv[k], rbb);
+      }
+    }
+    sd = fmaf(w, rd, sd); sab = fmaf(w, rab, sab); saa = fmaf(w, raa, saa); sbb = fmaf(w, rbb, sbb);
+  }
+  __shared__ float part[8][4];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sd += __shfl_xor_sync(0xffffffffu, sd, off); sab += __shfl_xor_sync(0xffffffffu, sab, off);
+    saa += __shfl_xor_sync(0xffffffffu, saa, off); sbb += __shfl_xor_sync(0xffffffffu, sbb, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    part[threadIdx.x >> 5][0] = sd; part[threadIdx.x >> 5][1] = sab; part[threadIdx.x >> 5][2] = saa; part[threadIdx.x >> 5][3] = sbb;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) tot += double(part[k][threadIdx.x]);
+    atomicAdd(a.acc + p * 4 + threadIdx.x, tot);
+  }
+}
+__global__ void scores_finalize_kernel(const double* acc, float* rmse, float* accs, double inv_n) {
+  const int p = threadIdx.x;
+  if (p >= 69) return;
+  rmse[p] = float(sqrt(acc[p * 4] * inv_n));
+  accs[p] = float(acc[p * 4 + 1] / sqrt(acc[p * 4 + 2] * acc[p * 4 + 3]));
+}
+
+// ---------------------------------------------------------------------------------------
 // dst[r][0..kd) = cast(src[r][0..ks)), zero for columns ks..kd (K padding of conv_surface)
 template <bool kFp16>
 __global__ void cast16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int rows, int ks, int kd) {

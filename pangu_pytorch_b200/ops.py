@@ -22,7 +22,7 @@ _KERNELS_PER_CALL = {
     "pangu_window_attention": 1, "pangu_proj_ln_residual": 1, "pangu_mlp_ln_residual": 2,
     "pangu_downsample": 2, "pangu_upsample": 2, "pangu_patch_recover": 2, "pangu_linear": 1, "pangu_denorm_fields": 1, "pangu_l1_loss": 2,
     "pangu_cast16_t": 1, "pangu_dgrad": 1, "pangu_wgrad": 1, "pangu_colsum16": 1, "pangu_layernorm_bwd": 1, "pangu_gelu_bwd": 1,
-    "pangu_window_attention_bwd": 1, "pangu_recover_grad_gather": 1,
+    "pangu_window_attention_bwd": 1, "pangu_recover_grad_gather": 1, "pangu_scores": 2,
 }
 
 
@@ -293,3 +293,30 @@ def recover_grad_gather(d_upper, d_surface, dy_upper, dy_surface, lat, lon, fp16
     h, f = dtype16(fp16), torch.float32
     _call("pangu_recover_grad_gather", _p(d_upper, f, "d_upper"), _p(d_surface, f, "d_surface"), _p(dy_upper, h),
           _p(dy_surface, h), lat, lon, float(scale), int(fp16), _stream())
+
+
+# ----------------------------------------------------------------------------------------------
+# evaluation scores (reference era5_data/score.py, models/pangu_sample.py:236-270)
+# ----------------------------------------------------------------------------------------------
+def latitude_weights(num_lat: int, device) -> Tensor:
+    """``latitude_weighting_factor_torch`` of era5_data/score.py:88-90 (note the reference's 3.1416)."""
+    j = torch.arange(num_lat, dtype=torch.float64)
+    c = torch.cos(3.1416 / 180.0 * (90.0 - j * 180.0 / float(num_lat - 1)))
+    return (num_lat * c / c.sum()).to(dtype=torch.float32, device=device)
+
+
+def scores(out_upper, out_surface, tgt_upper, tgt_surface, s_mean, s_std, u_mean, u_std, normalised: bool = True):
+    """Latitude-weighted RMSE and ACC per plane: returns (rmse_upper [5,13], rmse_surface [4], acc_upper [5,13],
+    acc_surface [4]) device tensors.  ``out_*``: model outputs (normalised=True) or physical fields; targets physical;
+    statistics in the input order the model takes."""
+    f = torch.float32
+    dev = out_upper.device
+    lat, lon = out_surface.shape[-2], out_surface.shape[-1]
+    w = latitude_weights(lat, dev)
+    acc_ws = torch.empty(69 * 4, dtype=torch.float64, device=dev)
+    rmse = torch.empty(69, dtype=f, device=dev)
+    acc = torch.empty(69, dtype=f, device=dev)
+    _call("pangu_scores", _p(out_upper, f, "out_upper"), _p(out_surface, f, "out_surface"), _p(tgt_upper, f, "tgt_upper"),
+          _p(tgt_surface, f, "tgt_surface"), _p(s_mean, f), _p(s_std, f), _p(u_mean, f), _p(u_std, f), _p(w, f),
+          _p(acc_ws, torch.float64), _p(rmse, f), _p(acc, f), lat, lon, int(bool(normalised)), _stream())
+    return rmse[:65].view(5, 13), rmse[65:], acc[:65].view(5, 13), acc[65:]

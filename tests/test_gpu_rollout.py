@@ -100,3 +100,40 @@ def test_weighted_l1_loss_and_output_gradient():
     for got, want, o, t in ((gu, ou_r.grad, ou, O.norm_data(tu, ts, ostats)[0]), (gs, os_r.grad, os_, O.norm_data(tu, ts, ostats)[1])):
         mask = (o - t).abs() > 1e-4
         assert torch.allclose(got.cpu()[mask], want[mask], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("normalised", [True, False])
+def test_evaluation_scores_match_oracle(normalised):
+    """pangu_scores (latitude-weighted RMSE / ACC per plane, models/pangu_sample.py:236-270) against the oracle's
+    restatement of era5_data/score.py; with normalised=True the kernel applies normBackData on the fly."""
+    from pangu_pytorch_b200 import ops
+    _, _, stats, _, _ = O.synthetic_inputs(seed=1, lat=721, lon=96)
+    g = torch.Generator().manual_seed(9)
+    ou, os_ = torch.randn(1, 5, 13, 721, 96, generator=g), torch.randn(1, 4, 721, 96, generator=g)
+    tu, ts = torch.randn(1, 5, 13, 721, 96, generator=g) * 2 + 1, torch.randn(1, 4, 721, 96, generator=g) * 2 + 1
+    ref = O.evaluation_scores(ou.double(), os_.double(), tu.double(), ts.double(), [s.double() for s in stats])
+    d = lambda t: t.to(DEV)
+    s_mean, s_std = d(stats[0]).reshape(4), d(stats[1]).reshape(4)
+    u_mean, u_std = d(stats[2]).reshape(13, 5).contiguous(), d(stats[3]).reshape(13, 5).contiguous()
+    if normalised:
+        pu, ps = d(ou), d(os_)
+    else:
+        pu, ps = (d(t.float()) for t in O.norm_back_data(ou, os_, O.output_statistics(stats)))
+    got = ops.scores(pu.contiguous(), ps.contiguous(), d(tu), d(ts), s_mean, s_std, u_mean, u_std, normalised=normalised)
+    for a, b in zip(got, ref):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert torch.allclose(a.cpu().double(), b, rtol=2e-5, atol=1e-6)
+
+
+def test_graphed_rollout_is_bit_identical_to_eager():
+    """The CUDA-graph step replays exactly the eager kernels: 3 chained steps must agree bit for bit."""
+    from pangu_pytorch_b200.rollout import rollout, rollout_graphed
+    p = O.reference_like_weights(seed=0)
+    m = _model(p, "bf16")
+    up, sf, stats, maps, ch = O.synthetic_inputs(seed=1, lat=721, lon=96)
+    d = lambda t: t.to(DEV)
+    args = (m, d(up), d(sf), [d(s) for s in stats], d(maps), d(ch))
+    eager = rollout(*args, steps=3)
+    graphed = rollout_graphed(*args, steps=3)
+    for (eu, es), (gu, gs) in zip(eager, graphed):
+        assert torch.equal(eu, gu) and torch.equal(es, gs)

@@ -120,3 +120,20 @@ def test_block_against_live_reference():
             assert float((mine - ref).norm() / ref.norm()) < 2e-6
     for m in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
         del sys.modules[m]
+
+
+@pytest.mark.reference
+def test_scores_against_live_reference():
+    """oracle RMSE / ACC == era5_data/score.py (imported unmodified; it needs only numpy + torch)."""
+    ref_root = os.environ.get("PANGU_REFERENCE", "/root/reference")
+    sys.path.insert(0, ref_root)
+    try:
+        from era5_data import score
+    finally:
+        sys.path.remove(ref_root)
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(13, 721, 48, generator=g), torch.randn(13, 721, 48, generator=g)
+    assert torch.allclose(O.weighted_rmse_channels(a, b), score.weighted_rmse_torch_channels(a, b), rtol=1e-5)
+    assert torch.allclose(O.weighted_acc_channels(a, b), score.weighted_acc_torch_channels(a, b), rtol=1e-5, atol=1e-7)
+    a4, b4 = a.unsqueeze(0), b.unsqueeze(0)
+    assert torch.allclose(O.weighted_rmse_channels(a4, b4), score.weighted_rmse_torch_channels(a4, b4), rtol=1e-5)
