@@ -95,7 +95,8 @@ struct GemmTraits {
                                    + (Cfg::RESTMA ? 8 * RES_SLOTS * 8 : 0);   // + per-warp residual-landed barriers
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
   static_assert(BN % UN == 0 && UN % 16 == 0 && UN <= 256, "bad N tiling");
-  static_assert(CL == 1 || (CL == 2 && (BN / 2) % 8 == 0 && BN / 2 <= 256), "bad cluster B split");
+  static_assert(CL == 1 || ((CL == 2 || CL == 4) && (BN / CL) % 8 == 0 && BN / CL <= 256), "bad cluster B split");
+  static_assert(!NSPLIT || CL == 2, "NSPLIT: a CTA pair");
   static_assert(!NSPLIT || (CL == 2 && Cfg::LN && NUM_B == 1), "NSPLIT: LayerNorm row split over a CTA pair");
   static_assert(BN % CH == 0 && (CH == 16 || CH == 32), "bad epilogue chunk");
   static_assert(EPI_WARPS % 4 == 0 && (EPI_WARPS == 8 || Cfg::TMA16), "more than 8 epilogue warps: TMA16 epilogue only");
@@ -352,7 +353,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // place and leaves with one TMA store per tile; no global load is ever waited for in this loop.
         constexpr int NS = T::RES_SLOTS;
         const int row0 = m_blk * BLOCK_M + quad * 32;
+        if (ep.debug & 4) {          // development ablation: mainloop only (no epilogue work at all)
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[acc]);
+          if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         auto fetch_resid = [&](int mb, int nb) {      // lane 0: residual tiles of this warp for tile (mb, nb)
+          if (ep.debug & 1) return;                   // development ablation: no residual traffic
 #pragma unroll
           for (int sl = 0; sl < NS; ++sl) {
             mbar_arrive_expect_tx(&rfull_bar[wslot * NS + sl], 4096);
@@ -430,7 +440,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* tile = slab + sl * 4096;
           uint32_t r[32];
           tmem_ld32(tacc + c0, r);
-          mbar_wait(&rfull_bar[wslot * NS + sl], res_tiles & 1);
+          if (!(ep.debug & 1)) mbar_wait(&rfull_bar[wslot * NS + sl], res_tiles & 1);
           tmem_ld_wait();
           const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
           const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
@@ -458,7 +468,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           fence_proxy_async_smem();
           __syncwarp();
           // fp32 stream: one TMA store of the [32 x 32] tile (rows beyond M are clipped)
-          if (lane == 0 && m_blk < shape.num_m_blocks) {
+          if (lane == 0 && m_blk < shape.num_m_blocks && !(ep.debug & 2)) {
             tma_store_2d(&tmOut, tile, n_blk * BN + c0, row0);
             bulk_commit();
           }
@@ -468,7 +478,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int id = it * 32 + lane;
             const int rr = id >> 2, pc = id & 3;
             const int dst = s_dst[rr];
-            if (dst < 0) continue;
+            if (dst < 0 || (ep.debug & 2)) continue;
             const uint4 a0 = *reinterpret_cast<const uint4*>(tile + rr * 128 + (((2 * pc) ^ (rr & 7)) << 4));
             const uint4 a1 = *reinterpret_cast<const uint4*>(tile + rr * 128 + (((2 * pc + 1) ^ (rr & 7)) << 4));
             uint4 h;
