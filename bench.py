@@ -305,6 +305,8 @@ def run_gpu_arm(args):
                 "avg_launch_ms": round(dom_ms, 4), "algorithmic_flops_per_launch": algo_flops[dom],
                 "step_tflops": round(FLOPS_PER_STEP / (ms_per_step * 1e-3) / 1e12, 1),
                 "step_frac_of_peak": round(FLOPS_PER_STEP / (ms_per_step * 1e-3) / 1e12 / pk["tflops_sustained"], 4),
+                "attn_mlp_frac_of_peak": round(FLOPS_BLOCKS / (sum(v[0] for k, v in kern.items() if k in algo_flops) / args.steps * 1e-3)
+                                               / 1e12 / pk["tflops_sustained"], 4),
                 "kernel_time_shares": shares}
     line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
