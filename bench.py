@@ -355,9 +355,15 @@ def run_train_arm(args):
 
     torch.manual_seed(0)
     model = pb.PanguModel(device=dev).to(dev).train()
+    lora_mode = args.workload == "lora"
+    if lora_mode:          # finetune/lora_tune.py:124-139 (lora_dropout 0 on this path)
+        from pangu_pytorch_b200 import lora
+        lora.add_lora(model, r=16, lora_alpha=16.0, lora_dropout=0.0)
+        model.to(dev).train()
     if world > 1:
         model.grad_reducer = GradReducer()
-    opt = torch.optim.Adam(model.parameters(), lr=5e-6, weight_decay=3e-6, fused=True)   # finetune/finetune_fully.py:119
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=5e-6, weight_decay=3e-6,
+                           fused=True)                                                   # finetune/finetune_fully.py:119
     g = torch.Generator(device=dev).manual_seed(1)
     maps = torch.randn(1, 3, 724, LON, device=dev, generator=g)
     const_h = torch.randn(1, 1, 1, 13, LAT, LON, device=dev, generator=g)
@@ -399,11 +405,12 @@ def run_train_arm(args):
         pk = peaks()
         per = ms_max / args.steps
         tfl = 3 * FLOPS_PER_STEP / (per * 1e-3) / 1e12
-        line = {"metric": "finetune steps/s @0.25deg (fwd + weighted-L1 + bwd + grad mean + Adam)", "value": round(world * args.steps / (ms_max / 1e3), 3),
+        line = {"metric": ("lora_tune" if lora_mode else "finetune") + " steps/s @0.25deg (fwd + weighted-L1 + bwd + grad mean + Adam)", "value": round(world * args.steps / (ms_max / 1e3), 3),
                 "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": round(per, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.operands, "data": "synthetic",
-                "config": {"workload": "finetune_fully step, PanguModel 0.25deg, batch 1 per GPU, random-init weights",
+                "config": {"workload": ("lora_tune step (r=16 adapters on 67 nn.Linear, output convs trained in full)" if lora_mode else "finetune_fully step")
+                                       + ", PanguModel 0.25deg, batch 1 per GPU, random-init weights",
                            "parallelism": f"data parallel over {world} GPU(s); gradient mean (1.1 GB fp32) all-reduced per block "
                                           "on a side stream under the backward", "optimizer": "torch.optim.Adam(fused), as the reference"},
                 "clocks": clocks, "gpu_launches": launches, "loss": float(loss),
@@ -423,12 +430,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--operands", default=os.environ.get("PANGU_B200_OPERANDS", "bf16"), choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="forecast", choices=["forecast", "train"],
-                    help="forecast: the BASELINE.json headline (default); train: finetune_fully step (configs[3])")
+    ap.add_argument("--workload", default="forecast", choices=["forecast", "train", "lora"],
+                    help="forecast: the BASELINE.json headline (default); train: finetune_fully step (configs[3]); "
+                         "lora: lora_tune step (configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
-    elif args.workload == "train":
+    elif args.workload in ("train", "lora"):
         run_train_arm(args)
     else:
         run_gpu_arm(args)
