@@ -194,20 +194,23 @@ int pangu_colsum16(const void* src16, int ld, float* out, int M, int N, int n_va
  *           dx16 [T2, 4C] in the same layout (cropped positions are not written)        (C 192)
  *   mode 2: DownSample.norm: rows = low-res tokens, y = high-res stream x [T, C/4] fp32 (2x2 merge + pad
  *           recomputed), dx32 [T, C/4] is ADDED to                                      (C 768)
- * dgamma / dbeta [C] are accumulated into, multiplied by palpha (1 / loss scale; 1 for bf16). */
+ * dgamma / dbeta [C] are accumulated into, multiplied by palpha (1 / loss scale; 1 for bf16).  dbias (nullable, mode 0):
+ * [C] += palpha * sum_rows dx, the bias gradient of the linear layer that produced y (saves a pass over dx). */
 int pangu_layernorm_bwd(const float* y, const float* g, const float* gamma, void* dx16, float* dx32,
-                        float* dgamma, float* dbeta, int rows, int C, int mode, int Z, int H, int W,
+                        float* dgamma, float* dbeta, float* dbias, int rows, int C, int mode, int Z, int H, int W,
                         float scale, float palpha, int fp16, void* stream);
 
-/* GELU backward in place: dh16[i] *= gelu'(pre16[i]) (exact erf form, nn.GELU; models/layers.py:261). */
-int pangu_gelu_bwd(void* dh16, const void* pre16, long long n, int fp16, void* stream);
+/* GELU backward in place: dh16[m, n] *= gelu'(pre16[m, n]) (exact erf form, nn.GELU; models/layers.py:261), [M, N] 16-bit.
+ * dbias (nullable): [N] += alpha * column sums of the result, the bias gradient of Mlp.linear1. */
+int pangu_gelu_bwd(void* dh16, const void* pre16, int M, int N, float* dbias, float alpha, int fp16, void* stream);
 
 /* Backward of pangu_window_attention (autograd of models/layers.py:368-415).  datt16w: [Tp, C] gradient of the
  * merged-head attention output in WINDOW order (pad rows zero); dqkv16: [Tp, 3C] window order, column
- * s*C + head*32 + d, gradient w.r.t. the un-scaled linear1 output; dbias [types, heads, 144, 144] += palpha * dS. */
+ * s*C + head*32 + d, gradient w.r.t. the un-scaled linear1 output; dbias [types, heads, 144, 144] += palpha * dS (nullable);
+ * dbqkv [3C] += palpha * column sums of dqkv, the gradient of attention.linear1.bias (nullable). */
 int pangu_window_attention_bwd(const void* qkv16, const void* datt16w, const float* earth_bias, void* dqkv16,
-                               float* dbias, int Z, int H, int W, int C, int heads, int roll, float palpha, int fp16,
-                               void* stream);
+                               float* dbias, float* dbqkv, int Z, int H, int W, int C, int heads, int roll, float palpha,
+                               int fp16, void* stream);
 
 /* Backward of the un-patchify + crop of PatchRecovery_pretrain (models/layers.py:519-545): output-field
  * gradients * scale (loss scale for fp16 operands) -> dy_upper [7*Hh*Ww, 192] (features >= 160 zero),

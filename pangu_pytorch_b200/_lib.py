@@ -37,9 +37,9 @@ SIGNATURES = {
     "pangu_dgrad": [_P] * 6 + [_I] * 9 + [_P],
     "pangu_wgrad": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     "pangu_colsum16": [_P, _I, _P, _I, _I, _I, _F, _I, _P],
-    "pangu_layernorm_bwd": [_P] * 7 + [_I, _I, _I, _I, _I, _I, _F, _F, _I, _P],
-    "pangu_gelu_bwd": [_P, _P, c_longlong, _I, _P],
-    "pangu_window_attention_bwd": [_P] * 5 + [_I] * 6 + [_F, _I, _P],
+    "pangu_layernorm_bwd": [_P] * 8 + [_I, _I, _I, _I, _I, _I, _F, _F, _I, _P],
+    "pangu_gelu_bwd": [_P, _P, _I, _I, _P, _F, _I, _P],
+    "pangu_window_attention_bwd": [_P] * 6 + [_I] * 6 + [_F, _I, _P],
     "pangu_recover_grad_gather": [_P] * 4 + [_I, _I, _F, _I, _P],
 }
 

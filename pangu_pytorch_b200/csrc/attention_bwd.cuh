@@ -23,7 +23,8 @@ constexpr int ATB_DB_PITCH = 152;                   // floats per row of the dBi
 constexpr int ATB_TILES_BYTES = 4 * ATT_TILE_BYTES; // q, k, v, dO
 constexpr int ATB_P_BYTES = ATT_TOK * ATB_P_PITCH;
 constexpr int ATB_DB_BYTES = ATT_TOK * ATB_DB_PITCH * 4;
-constexpr int ATB_SMEM_BYTES = ATB_TILES_BYTES + 2 * ATB_P_BYTES + ATB_DB_BYTES;
+constexpr int ATB_CS_BYTES = 3 * 32 * 4;              // column sums of dq / dk / dv of the current head (linear1.bias gradient)
+constexpr int ATB_SMEM_BYTES = ATB_TILES_BYTES + 2 * ATB_P_BYTES + ATB_DB_BYTES + ATB_CS_BYTES;
 static_assert(ATB_SMEM_BYTES <= 232448, "attention backward shared memory budget");
 
 struct AttnBwdArgs {
@@ -32,6 +33,7 @@ struct AttnBwdArgs {
   const float* bias;    // [types][heads][144][144] fp32
   void* dqkv;           // [Tp][3C] 16-bit, window order, column s*C + head*32 + d; dq is w.r.t. the UNscaled q
   float* dbias;         // [types][heads][144][144] fp32, accumulated into (nullptr: frozen table, skipped)
+  float* dbqkv;         // [3C] fp32 += palpha * column sums of dqkv: bias gradient of attention.linear1 (nullable)
   int C, heads, types, nLon, nH, roll, plane_rows;
   float q_scale;
   float palpha;         // factor on the bias gradient (1 / loss scale)
@@ -47,6 +49,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) window_attention_bwd_kernel(co
   uint8_t* s_p = atb_smem + ATB_TILES_BYTES;
   uint8_t* s_ds = s_p + ATB_P_BYTES;
   float* s_db = reinterpret_cast<float*>(s_ds + ATB_P_BYTES);
+  float* s_cs = s_db + ATT_TOK * ATB_DB_PITCH;       // [3][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, q4 = lane & 3;
@@ -57,6 +60,13 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) window_attention_bwd_kernel(co
   const int u_end = int(total * (blockIdx.x + 1) / gridDim.x);
 
   for (int i = threadIdx.x; i < ATT_TOK * ATB_DB_PITCH; i += ATB_THREADS) s_db[i] = 0.f;
+  if (threadIdx.x < 96) s_cs[threadIdx.x] = 0.f;
+  // column sums of a 16-row fragment block: reduce over the 8 row groups of the warp, one shared atomic per column
+  auto add_cols = [&](int x, int n, float c0, float c1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, 4); c0 += __shfl_xor_sync(0xffffffffu, c0, 8); c0 += __shfl_xor_sync(0xffffffffu, c0, 16);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, 4); c1 += __shfl_xor_sync(0xffffffffu, c1, 8); c1 += __shfl_xor_sync(0xffffffffu, c1, 16);
+    if (gq == 0) { atomicAdd(&s_cs[x * 32 + 8 * n + 2 * q4], c0); atomicAdd(&s_cs[x * 32 + 8 * n + 2 * q4 + 1], c1); }
+  };
   __syncthreads();
 
   const uint32_t sq = smem_u32(tq), sk = smem_u32(tk), sv = smem_u32(tv), sdo = smem_u32(tdo);
@@ -207,6 +217,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) window_attention_bwd_kernel(co
       for (int n = 0; n < 4; ++n) {
         *reinterpret_cast<uint32_t*>(r0p + 8 * n) = pack16<kFp16>(o[n][0] * a.q_scale, o[n][1] * a.q_scale);
         *reinterpret_cast<uint32_t*>(r1p + 8 * n) = pack16<kFp16>(o[n][2] * a.q_scale, o[n][3] * a.q_scale);
+        if (a.dbqkv) add_cols(0, n, (o[n][0] + o[n][2]) * a.q_scale, (o[n][1] + o[n][3]) * a.q_scale);
       }
     }
     __syncthreads();
@@ -246,11 +257,23 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) window_attention_bwd_kernel(co
         *reinterpret_cast<uint32_t*>(k1p + 8 * n) = pack16<kFp16>(dk[n][2], dk[n][3]);
         *reinterpret_cast<uint32_t*>(k0p + a.C + 8 * n) = pack16<kFp16>(dv[n][0], dv[n][1]);
         *reinterpret_cast<uint32_t*>(k1p + a.C + 8 * n) = pack16<kFp16>(dv[n][2], dv[n][3]);
+        if (a.dbqkv) {
+          add_cols(1, n, dk[n][0] + dk[n][2], dk[n][1] + dk[n][3]);
+          add_cols(2, n, dv[n][0] + dv[n][2], dv[n][1] + dv[n][3]);
+        }
       }
     }
     __syncthreads();     // tiles and P / dS are free again
 
-    // ---- end of a (type, head) segment (or of this CTA's range): flush the bias gradient
+    // ---- end of a (type, head) segment (or of this CTA's range): flush the column sums (linear1.bias gradient) ...
+    if (a.dbqkv && (lw == a.nLon - 1 || u + 1 == u_end)) {     // (the trailing __syncthreads of phase 2 ordered the shared atomics)
+      if (threadIdx.x < 96) {
+        atomicAdd(a.dbqkv + (threadIdx.x >> 5) * a.C + head * 32 + (threadIdx.x & 31), a.palpha * s_cs[threadIdx.x]);
+        s_cs[threadIdx.x] = 0.f;
+      }
+      __syncthreads();
+    }
+    // ... and the earth_specific_bias gradient
     if (a.dbias && (lw == a.nLon - 1 || u + 1 == u_end)) {
       float* g = a.dbias + size_t(th) * ATT_TOK * ATT_TOK;
       for (int i = threadIdx.x; i < ATT_TOK * ATT_TOK; i += ATB_THREADS) {

@@ -21,6 +21,7 @@ struct LnBwdArgs {
   float* dx32;          // DOWN: [T, C/4] fp32, read-modify-write (+=)
   float* dgamma;        // [C] += scale * sum_rows g * xhat
   float* dbeta;         // [C] += scale * sum_rows g
+  float* dbias;         // [C] += sum_rows dx: bias gradient of the linear that produced y (IDENT mode; nullable)
   int rows, C;
   int Z, H, W;          // UP / DOWN: HIGH-resolution token grid
   float scale;          // DropPath factor of the branch (1 in eval)
@@ -33,18 +34,19 @@ struct LnBwdArgs {
 template <bool kFp16, int kMode, int kC>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
   constexpr int NP = (kC / 4 + 31) / 32;           // float4 pieces per lane
-  __shared__ float s_dg[kC], s_db[kC];
-  for (int i = threadIdx.x; i < kC; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  __shared__ float s_dg[kC], s_db[kC], s_dy[kC];
+  for (int i = threadIdx.x; i < kC; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; s_dy[i] = 0.f; }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  float4 gam[NP], adg[NP], adb[NP];
+  float4 gam[NP], adg[NP], adb[NP], ady[NP];
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
     const int q = lane + 32 * i;
     gam[i] = q < kC / 4 ? *reinterpret_cast<const float4*>(a.gamma + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     adg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     adb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ady[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const int W2 = a.W / 2, H2 = (a.H + 1) / 2;
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.rows; row += warps_total) {
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
       if (q >= kC / 4) continue;
       const float d0 = rstd * (gv[i].x - m1 - yv[i].x * m2), d1 = rstd * (gv[i].y - m1 - yv[i].y * m2);
       const float d2 = rstd * (gv[i].z - m1 - yv[i].z * m2), d3 = rstd * (gv[i].w - m1 - yv[i].w * m2);
+      ady[i].x += d0; ady[i].y += d1; ady[i].z += d2; ady[i].w += d3;
       if constexpr (kMode == LNB_DOWN) {
         constexpr int QH = kC / 8;
         const int dh = q / QH, r = q % QH;
@@ -148,11 +151,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
     atomicAdd(&s_dg[q * 4 + 2], adg[i].z); atomicAdd(&s_dg[q * 4 + 3], adg[i].w);
     atomicAdd(&s_db[q * 4 + 0], adb[i].x); atomicAdd(&s_db[q * 4 + 1], adb[i].y);
     atomicAdd(&s_db[q * 4 + 2], adb[i].z); atomicAdd(&s_db[q * 4 + 3], adb[i].w);
+    if (a.dbias) {
+      atomicAdd(&s_dy[q * 4 + 0], ady[i].x); atomicAdd(&s_dy[q * 4 + 1], ady[i].y);
+      atomicAdd(&s_dy[q * 4 + 2], ady[i].z); atomicAdd(&s_dy[q * 4 + 3], ady[i].w);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kC; i += blockDim.x) {
     if (a.dgamma) atomicAdd(a.dgamma + i, a.palpha * s_dg[i]);
     if (a.dbeta) atomicAdd(a.dbeta + i, a.palpha * s_db[i]);
+    if (a.dbias) atomicAdd(a.dbias + i, a.palpha * s_dy[i]);
   }
 }
 
@@ -178,32 +186,57 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return fmaf(x, pdf, cdf);
 }
 
+// dh, pre: [M, N] 16-bit.  Thread = 8 consecutive columns of a row (fixed column group, rows strided), so that the
+// bias gradient of linear1, db[n] += alpha * sum_m dpre[m, n], falls out of the same pass (nullable).
 template <bool kFp16>
-__global__ void __launch_bounds__(256) gelu_bwd_kernel(uint16_t* __restrict__ dh, const uint16_t* __restrict__ pre, size_t n8) {
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t i0 = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < n8; i0 += 2 * stride) {
-    const size_t i1 = i0 + stride;
-    const bool two = i1 < n8;
-    uint4 d[2], p[2];
-    d[0] = ldg16(reinterpret_cast<const uint4*>(dh) + i0);      // coherent: dh is rewritten in place
-    p[0] = ldg_nc16(reinterpret_cast<const uint4*>(pre) + i0);
-    if (two) {
-      d[1] = ldg16(reinterpret_cast<const uint4*>(dh) + i1);
-      p[1] = ldg_nc16(reinterpret_cast<const uint4*>(pre) + i1);
-    }
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(uint16_t* __restrict__ dh, const uint16_t* __restrict__ pre, int M, int N,
+                                                       float* __restrict__ db, float alpha) {
+  extern __shared__ float s_acc[];               // [N]
+  if (db) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+  }
+  const int tpr = N / 8;                         // threads per row
+  const int rpi = blockDim.x / tpr;              // rows per iteration of this block
+  const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < rpi) {
+    const int step = gridDim.x * rpi;
+    for (int m = blockIdx.x * rpi + rl; m < M; m += 2 * step) {
+      uint4 d[2], p[2];
+      bool ok[2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !two) break;
-      uint32_t* dw = reinterpret_cast<uint32_t*>(&d[u]);
-      const uint32_t* pw = reinterpret_cast<const uint32_t*>(&p[u]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float x0 = unpack16_lo<kFp16>(pw[k]), x1 = unpack16_hi<kFp16>(pw[k]);
-        const float g0 = unpack16_lo<kFp16>(dw[k]), g1 = unpack16_hi<kFp16>(dw[k]);
-        dw[k] = pack16<kFp16>(g0 * gelu_grad(x0), g1 * gelu_grad(x1));
+      for (int u = 0; u < 2; ++u) {
+        const int mm = m + u * step;
+        ok[u] = mm < M;
+        if (ok[u]) {
+          d[u] = ldg16(dh + size_t(mm) * N + cg * 8);         // coherent: dh is rewritten in place
+          p[u] = ldg_nc16(pre + size_t(mm) * N + cg * 8);
+        }
       }
-      reinterpret_cast<uint4*>(dh)[u == 0 ? i0 : i1] = d[u];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!ok[u]) continue;
+        uint32_t* dw = reinterpret_cast<uint32_t*>(&d[u]);
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(&p[u]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float x0 = unpack16_lo<kFp16>(pw[k]), x1 = unpack16_hi<kFp16>(pw[k]);
+          const float g0 = unpack16_lo<kFp16>(dw[k]) * gelu_grad(x0), g1 = unpack16_hi<kFp16>(dw[k]) * gelu_grad(x1);
+          acc[2 * k] += g0; acc[2 * k + 1] += g1;
+          dw[k] = pack16<kFp16>(g0, g1);
+        }
+        stg16(dh + size_t(m + u * step) * N + cg * 8, d[u]);
+      }
     }
+    if (db) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&s_acc[cg * 8 + k], acc[k]);
+    }
+  }
+  if (db) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(db + i, alpha * s_acc[i]);
   }
 }
 

@@ -817,7 +817,7 @@ static int launch_ln_bwd(const LnBwdArgs& a, int mode, cudaStream_t s) {
 }
 
 extern "C" int pangu_layernorm_bwd(const float* y, const float* g, const float* gamma, void* dx16, float* dx32,
-                                   float* dgamma, float* dbeta, int rows, int C, int mode, int Z, int H, int W,
+                                   float* dgamma, float* dbeta, float* dbias, int rows, int C, int mode, int Z, int H, int W,
                                    float scale, float palpha, int fp16, void* stream) {
   PG_TRY(ensure_init());
   PG_REQUIRE(rows > 0 && y && g && gamma, "layernorm_bwd: null argument");
@@ -825,32 +825,37 @@ extern "C" int pangu_layernorm_bwd(const float* y, const float* g, const float* 
   if (mode == LNB_UP) PG_REQUIRE(rows == Z * H * W && W % 2 == 0, "layernorm_bwd(up): rows must be the high-res token count");
   if (mode == LNB_DOWN) PG_REQUIRE(rows == Z * ((H + 1) / 2) * (W / 2), "layernorm_bwd(down): rows must be the low-res token count");
   LnBwdArgs a;
-  a.y = y; a.g = g; a.gamma = gamma; a.dx16 = dx16; a.dx32 = dx32; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.y = y; a.g = g; a.gamma = gamma; a.dx16 = dx16; a.dx32 = dx32; a.dgamma = dgamma; a.dbeta = dbeta; a.dbias = dbias;
   a.rows = rows; a.C = C; a.Z = Z; a.H = H; a.W = W; a.scale = scale; a.palpha = palpha; a.eps = 1e-5f;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return fp16 ? launch_ln_bwd<true>(a, mode, s) : launch_ln_bwd<false>(a, mode, s);
 }
 
-extern "C" int pangu_gelu_bwd(void* dh16, const void* pre16, long long n, int fp16, void* stream) {
+extern "C" int pangu_gelu_bwd(void* dh16, const void* pre16, int M, int N, float* dbias, float alpha, int fp16, void* stream) {
   PG_TRY(ensure_init());
-  PG_REQUIRE(n > 0 && n % 8 == 0, "gelu_bwd: element count must be a positive multiple of 8");
+  PG_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && N <= 2048, "gelu_bwd: N must be a positive multiple of 8, at most 2048");
+  PG_REQUIRE((reinterpret_cast<uintptr_t>(dh16) & 15) == 0 && (reinterpret_cast<uintptr_t>(pre16) & 15) == 0, "gelu_bwd: misaligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t n8 = size_t(n) / 8;
-  const int grid = int((n8 + 255) / 256 < size_t(16 * g_num_sms) ? (n8 + 255) / 256 : size_t(16 * g_num_sms));
-  if (fp16) gelu_bwd_kernel<true><<<grid, 256, 0, s>>>(static_cast<uint16_t*>(dh16), static_cast<const uint16_t*>(pre16), n8);
-  else gelu_bwd_kernel<false><<<grid, 256, 0, s>>>(static_cast<uint16_t*>(dh16), static_cast<const uint16_t*>(pre16), n8);
+  const int tpr = N / 8;
+  const int rpi = 256 / tpr > 0 ? 256 / tpr : 1;
+  const int block = tpr * rpi;                  // 192 for N = 768 / 1536
+  int grid = (M + 2 * rpi - 1) / (2 * rpi);
+  if (grid > 16 * g_num_sms) grid = 16 * g_num_sms;
+  const size_t smem = dbias ? N * sizeof(float) : 0;
+  if (fp16) gelu_bwd_kernel<true><<<grid, block, smem, s>>>(static_cast<uint16_t*>(dh16), static_cast<const uint16_t*>(pre16), M, N, dbias, alpha);
+  else gelu_bwd_kernel<false><<<grid, block, smem, s>>>(static_cast<uint16_t*>(dh16), static_cast<const uint16_t*>(pre16), M, N, dbias, alpha);
   PG_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int pangu_window_attention_bwd(const void* qkv16, const void* datt16w, const float* earth_bias, void* dqkv16,
-                                          float* dbias, int Z, int H, int W, int C, int heads, int roll, float palpha,
-                                          int fp16, void* stream) {
+                                          float* dbias, float* dbqkv, int Z, int H, int W, int C, int heads, int roll,
+                                          float palpha, int fp16, void* stream) {
   PG_TRY(ensure_init());
   PG_TRY(check_grid(Z, H, W, C, heads));
   const Geo g = make_geo(Z, H, W);
   AttnBwdArgs a;
-  a.qkv = qkv16; a.datt = datt16w; a.bias = earth_bias; a.dqkv = dqkv16; a.dbias = dbias;
+  a.qkv = qkv16; a.datt = datt16w; a.bias = earth_bias; a.dqkv = dqkv16; a.dbias = dbias; a.dbqkv = dbqkv;
   a.C = C; a.heads = heads; a.types = g.types; a.nLon = g.nLon; a.nH = g.nH; a.roll = roll ? 1 : 0;
   a.plane_rows = sh_rows_padded(g.nLon * g.types * 144);
   a.q_scale = 0.17677669529663687f;

@@ -268,25 +268,27 @@ def colsum16(src16: Tensor, out: Tensor, fp16: bool, n_valid: Optional[int] = No
 
 def layernorm_bwd(y: Tensor, g: Tensor, gamma: Tensor, dgamma: Optional[Tensor], dbeta: Optional[Tensor], rows: int,
                   C: int, mode: int, fp16: bool, dx16: Optional[Tensor] = None, dx32: Optional[Tensor] = None,
-                  grid=(8, 1, 12), scale: float = 1.0, palpha: float = 1.0) -> None:
+                  grid=(8, 1, 12), scale: float = 1.0, palpha: float = 1.0, dbias: Optional[Tensor] = None) -> None:
+    """``dbias`` (mode 0): [C] += palpha * sum_rows dx -- the bias gradient of the linear that produced ``y``."""
     f = torch.float32
     Z, H, W = grid
     _call("pangu_layernorm_bwd", _p(y, f, "y"), _p(g, f, "g"), _p(gamma, f, "gamma"), _p(dx16, dtype16(fp16)), _p(dx32, f),
-          _p(dgamma, f), _p(dbeta, f), rows, C, int(mode), Z, H, W, float(scale), float(palpha), int(fp16), _stream())
+          _p(dgamma, f), _p(dbeta, f), _p(dbias, f), rows, C, int(mode), Z, H, W, float(scale), float(palpha), int(fp16), _stream())
 
 
-def gelu_bwd(dh16: Tensor, pre16: Tensor, fp16: bool) -> None:
-    """dh16 *= gelu'(pre16) in place."""
-    from ctypes import c_longlong
+def gelu_bwd(dh16: Tensor, pre16: Tensor, fp16: bool, dbias: Optional[Tensor] = None, alpha: float = 1.0) -> None:
+    """dh16 *= gelu'(pre16) in place ([M, N]); ``dbias`` [N] += alpha * column sums of the result."""
     h = dtype16(fp16)
-    _call("pangu_gelu_bwd", _p(dh16, h, "dh16"), _p(pre16, h, "pre16"), c_longlong(dh16.numel()), int(fp16), _stream())
+    M, N = dh16.shape
+    _call("pangu_gelu_bwd", _p(dh16, h, "dh16"), _p(pre16, h, "pre16"), M, N, _p(dbias, torch.float32), float(alpha), int(fp16),
+          _stream())
 
 
 def window_attention_bwd(qkv16, datt16w, earth_bias, dqkv16, dbias, Z, H, W, C, heads, roll: bool, fp16: bool,
-                         palpha: float = 1.0) -> None:
+                         palpha: float = 1.0, dbqkv: Optional[Tensor] = None) -> None:
     h, f = dtype16(fp16), torch.float32
     _call("pangu_window_attention_bwd", _p(qkv16, h, "qkv"), _p(datt16w, h, "datt"), _p(earth_bias, f, "earth_specific_bias"),
-          _p(dqkv16, h, "dqkv"), _p(dbias, f, "dbias"), Z, H, W, C, heads, int(bool(roll)), float(palpha), int(fp16), _stream())
+          _p(dqkv16, h, "dqkv"), _p(dbias, f, "dbias"), _p(dbqkv, f, "dbqkv"), Z, H, W, C, heads, int(bool(roll)), float(palpha), int(fp16), _stream())
 
 
 def recover_grad_gather(d_upper, d_surface, dy_upper, dy_surface, lat, lon, fp16: bool, scale: float = 1.0) -> None:

@@ -152,8 +152,11 @@ def test_layernorm_bwd_plain(fmt, C):
     dx16 = torch.empty(rows, C, dtype=torch.float16 if fp16 else torch.bfloat16, device=DEV)
     dg0, db0 = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
     dg, db = dg0.clone(), db0.clone()
-    ops.layernorm_bwd(y, go, gamma, dg, db, rows, C, 0, fp16, dx16=dx16, scale=scale)
+    dbias = torch.zeros(C, device=DEV)
+    ops.layernorm_bwd(y, go, gamma, dg, db, rows, C, 0, fp16, dx16=dx16, scale=scale, dbias=dbias, palpha=0.5)
+    dg, db = dg0 + 2 * (dg - dg0), db0 + 2 * (db - db0)           # undo palpha = 0.5
     assert rel_l2(dx16.float(), yd.grad) < OUT16_TOL[fmt]
+    assert rel_l2(2 * dbias, yd.grad.sum(0)) < 1e-3              # fused bias gradient of the producing linear
     assert rel_l2(dg - dg0, gd.grad) < 1e-4
     assert rel_l2(db - db0, bd.grad) < 1e-4
 
@@ -212,8 +215,17 @@ def test_gelu_bwd(fmt):
     dh = _r16(torch.randn(1000, 768, generator=g), fp16).to(DEV)
     pd = pre.double().requires_grad_(True)
     (F.gelu(pd) * dh.double()).sum().backward()
-    ops.gelu_bwd(dh, pre, fp16)
+    db = torch.zeros(768, device=DEV)
+    ops.gelu_bwd(dh, pre, fp16, dbias=db, alpha=2.0)
     assert rel_l2(dh.float(), pd.grad) < OUT16_TOL[fmt]
+    assert rel_l2(db, 2.0 * pd.grad.sum(0)) < 1e-3               # fused bias gradient (column sums)
+    # ragged row count, wide rows, no bias output
+    pre2 = _r16(torch.randn(333, 1536, generator=g), fp16).to(DEV)
+    dh2 = _r16(torch.randn(333, 1536, generator=g), fp16).to(DEV)
+    p2 = pre2.double().requires_grad_(True)
+    (F.gelu(p2) * dh2.double()).sum().backward()
+    ops.gelu_bwd(dh2, pre2, fp16)
+    assert rel_l2(dh2.float(), p2.grad) < OUT16_TOL[fmt]
 
 
 @pytest.mark.parametrize("fmt", FORMATS)
@@ -248,7 +260,8 @@ def test_window_attention_bwd(fmt, H, C, heads, roll):
     (o * datt.double()).sum().backward()
     dqkv = torch.full((Tp, 3 * C), float("nan"), dtype=h16, device=DEV)
     dbias = torch.zeros(types, heads, 144, 144, device=DEV)
-    ops.window_attention_bwd(qkv.to(DEV), datt.to(DEV), bias.to(DEV), dqkv, dbias, Z, H, W, C, heads, roll, fp16)
+    dbqkv = torch.zeros(3 * C, device=DEV)
+    ops.window_attention_bwd(qkv.to(DEV), datt.to(DEV), bias.to(DEV), dqkv, dbias, Z, H, W, C, heads, roll, fp16, dbqkv=dbqkv)
     torch.cuda.synchronize()
 
     def planes(t):     # [nLon, types, heads, 144, 32] -> [Tp, C]
@@ -260,6 +273,8 @@ def test_window_attention_bwd(fmt, H, C, heads, roll):
     assert rel_l2(out[:, C:2 * C], planes(k.grad)) < tol
     assert rel_l2(out[:, 2 * C:], planes(v.grad)) < tol
     assert rel_l2(dbias, bd.grad[0]) < tol
+    ref_cols = torch.cat([planes(q_raw.grad).sum(0), planes(k.grad).sum(0), planes(v.grad).sum(0)])
+    assert rel_l2(dbqkv, ref_cols) < tol                          # fused attention.linear1.bias gradient
 
 
 @pytest.mark.parametrize("fmt", FORMATS)
