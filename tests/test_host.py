@@ -176,3 +176,40 @@ def test_lora_merge_matches_restated_peft_semantics():
         bad = dict(peft)
         bad.pop(f"base_model.model.{mod}.lora_B.default.weight")
         merge_lora_state_dict(bad)
+
+
+def test_add_lora_wraps_67_linears_and_round_trips():
+    """finetune/lora_tune.py:124-139: adapters on every nn.Linear (67), base frozen, the two output convs trainable;
+    state_dict keys follow peft's child names; the peft-style checkpoint merges back to a strict 223-key state_dict
+    whose weights equal the effective weights the kernels read; adapter dropout > 0 is refused in training mode."""
+    import pangu_pytorch_b200 as pb
+    from pangu_pytorch_b200 import lora
+    m = pb.PanguModel(device="cpu")
+    plain_keys = list(m.state_dict().keys())
+    lora.add_lora(m, r=16, lora_alpha=16.0, lora_dropout=0.0)
+    wrapped = {n: mod for n, mod in m.named_modules() if isinstance(mod, lora.LoraLinear)}
+    assert len(wrapped) == 67
+    trainable = [n for n, p in m.named_parameters() if p.requires_grad]
+    assert len(trainable) == 2 * 67 + 4 and all(("lora_" in n) or n.startswith("_output_layer.") for n in trainable)
+    n0 = "layers.EarthSpecificLayer1.blocks.EarthSpecificBlock0.attention.linear1"
+    sd = m.state_dict()
+    assert {n0 + ".base_layer.weight", n0 + ".base_layer.bias", n0 + ".lora_A.default.weight",
+            n0 + ".lora_B.default.weight"} <= set(sd)
+    mod = wrapped[n0]
+    assert tuple(mod.A.shape) == (16, 384) and tuple(mod.B.shape) == (1152, 16)
+    assert torch.equal(mod.weight, mod.base_layer.weight)                      # B starts at zero (peft init)
+    mod.B.data.normal_(0, 0.05, generator=torch.Generator().manual_seed(1))
+    eff = mod.base_layer.weight + mod.scaling * (mod.B @ mod.A)
+    assert torch.allclose(mod.weight, eff, atol=1e-6) and not mod.weight.requires_grad
+    merged = lora.merge_lora_state_dict(lora.peft_state_dict(m))
+    assert sorted(merged) == sorted(plain_keys)
+    assert torch.allclose(merged[n0 + ".weight"], eff.detach(), atol=1e-6)
+    pb.PanguModel(device="cpu").load_state_dict(merged, strict=True)
+    # adapter dropout cannot be folded into the operand: refused while training, accepted in eval
+    m2 = torch.nn.Linear(8, 8)
+    w = lora.LoraLinear(m2, r=4, lora_alpha=4.0, lora_dropout=0.1)
+    w.train()
+    with pytest.raises(NotImplementedError):
+        _ = w.weight
+    w.eval()
+    assert w.weight.shape == (8, 8)
