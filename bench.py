@@ -61,6 +61,10 @@ def peaks():
 def cpu_sample_setup():
     import torch
     from oracle import pangu_oracle as O
+    try:                                  # the GPU arm may have pinned this process next to its GPU: the CPU leg gets every core
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except OSError:
+        pass
     torch.set_num_threads(os.cpu_count() or 1)
     p = O.reference_like_weights(seed=0)
     inputs = O.synthetic_inputs(seed=1, lat=LAT, lon=STRIP)
@@ -157,6 +161,18 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Pin this process to the CPU cores next to its GPU (NVML's ideal affinity) before any pinned host buffer is
+    allocated, so that the end-to-end copies of the 8 ranks do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return f"cpu affinity = NVML ideal set of GPU {index} ({len(os.sched_getaffinity(0))} cores)"
+    except Exception as e:          # not fatal: the copies just may be slower
+        return f"unbound ({type(e).__name__})"
+
+
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
@@ -171,6 +187,7 @@ def run_gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pb.set_operand_dtype(args.operands)
@@ -319,7 +336,7 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
                     "ms_per_step": round(e2e_ms_max / args.steps, 3),
-                    "how": "PanguModel.forward on pinned host inputs; H2D/D2H double-buffered on side streams"},
+                    "how": "PanguModel.forward on pinned host inputs; H2D/D2H double-buffered on side streams", "host": numa},
             "gpu_launches": launches,
             "roofline": roofline}
     if world == 1 and not args.no_cpu:
