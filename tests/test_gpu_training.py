@@ -151,3 +151,53 @@ def test_lora_training_gradients():
     n0 = "layers.EarthSpecificLayer1.blocks.EarthSpecificBlock2.attention.linear1"
     assert torch.allclose(merged[n0 + ".weight"].cpu(), eff[n0 + ".weight"].detach(), atol=1e-6)
     training.release_tape(model)
+
+
+def test_full_025_backward_directional_derivative():
+    """Size-independent check of the backward at the FULL 0.25 degree shapes (BASELINE.json configs[3]), where the
+    CPU oracle's autograd is out of reach: for random directions v in a few parameter tensors, the central
+    difference of the loss kernel's value, (L(theta + eps v) - L(theta - eps v)) / (2 eps), must match <grad, v>.
+    The loss is a mean over 1e8 grid points, so the forward's rounding noise averages out of the difference."""
+    import pangu_pytorch_b200 as pb
+    from pangu_pytorch_b200 import ops, training, engine
+    pb.set_operand_dtype("bf16")
+    pb.free_workspaces()
+    torch.manual_seed(0)
+    model = pb.PanguModel(device=DEV).to(DEV).train()
+    for blk in [m for m in model.modules() if hasattr(m, "drop_path")]:
+        blk.drop_path.drop_prob = 0.0
+    g = torch.Generator(device=DEV).manual_seed(1)
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    up, sf, maps, ch = rn(1, 5, 13, 721, 1440), rn(1, 4, 721, 1440), rn(1, 3, 724, 1440), rn(1, 1, 1, 13, 721, 1440)
+    tu, ts = rn(1, 5, 13, 721, 1440), rn(1, 4, 721, 1440)
+    stats = [torch.zeros(4, device=DEV), torch.ones(4, device=DEV), torch.zeros(13, 1, 1, 5, device=DEV),
+             torch.ones(13, 1, 1, 5, device=DEV)]
+    training.train_step(model, up, sf, stats, maps, ch, tu, ts)
+    params = dict(model.named_parameters())
+    assert all(torch.isfinite(p.grad).all() for p in params.values())
+
+    def loss_at():
+        with torch.no_grad():
+            ou, os_ = model(up, sf, stats, maps, ch)
+            l, _, _ = ops.l1_loss(ou, os_, tu, ts, stats[0], stats[1], stats[2].reshape(13, 5).contiguous(),
+                                  stats[3].reshape(13, 5).contiguous())
+        return float(l)
+
+    names = ["_output_layer.conv.bias", "layers.EarthSpecificLayer3.blocks.EarthSpecificBlock1.norm2.bias",
+             "layers.EarthSpecificLayer2.blocks.EarthSpecificBlock0.linear.linear2.bias",
+             "layers.EarthSpecificLayer0.blocks.EarthSpecificBlock1.attention.linear1.bias"]
+    for i, name in enumerate(names):
+        p = params[name]
+        v = torch.randn(p.shape, device=DEV, generator=g)
+        v /= v.norm()
+        analytic = float((p.grad * v).sum())
+        eps = 2e-2
+        with torch.no_grad():
+            p.add_(eps * v); lp = loss_at()
+            p.add_(-2 * eps * v); lm = loss_at()
+            p.add_(eps * v)
+        numeric = (lp - lm) / (2 * eps)
+        print(f"directional derivative {name}: analytic {analytic:.4e} numeric {numeric:.4e}")
+        assert abs(numeric - analytic) < 0.1 * abs(analytic) + 2e-5, (name, analytic, numeric)
+    training.release_tape(model)
+    pb.free_workspaces()
