@@ -121,6 +121,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   tc_fence_after();
   if (*tmem_slot != 0u) __trap();     // all 512 columns: the allocation can only start at TMEM address 0
   constexpr uint32_t tmem = 0u;       // compile-time constant keeps the MMA operands in uniform registers
+  pdl_trigger();
+  pdl_wait();                         // qkv of the preceding GEMM is read from here on
 
   // balanced contiguous range of (type, head, lon window) units for this CTA
   const long long total = (long long)a.types * a.heads * a.nLon;

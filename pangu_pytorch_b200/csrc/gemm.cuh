@@ -172,6 +172,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if constexpr (CL == 1) __syncthreads(); else cluster_sync_all();   // peer barriers initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();     // persistent grid, every CTA resident: the next kernel's CTAs may take over SMs as ours retire
+  pdl_wait();        // the prologue above overlapped the previous kernel's tail; its outputs are needed from here on
 
   if (warp == 0) {
     // ================================ TMA producer ================================
