@@ -187,7 +187,7 @@ def run_gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(local)
+    numa = bind_to_gpu_numa_node(local) if os.environ.get("PANGU_BENCH_BIND_NUMA") else "unbound (default; PANGU_BENCH_BIND_NUMA=1 binds to the GPU's NVML-ideal cores: measured no effect at 8 ranks)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pb.set_operand_dtype(args.operands)
