@@ -185,10 +185,12 @@ struct CfgLin16 : CfgBase {    // (bias) -> 16-bit row-major (pre-activation rec
 struct CfgAcc192 : CfgBase {   // fp32 out = residual + acc (dgrad accumulating into the gradient stream), row maps
   static constexpr int BN = 192, UN = 192, STAGES = 4;
   static constexpr bool RESID = true, OUT32 = true;
+  static constexpr int CLUSTER = PANGU_CLUSTER_M;
 };
 struct CfgOut16Map : CfgBase { // 16-bit out, destination row map (dgrad scattered into window order)
   static constexpr int BN = 192, UN = 192, STAGES = 4;
   static constexpr bool OUT16 = true;
+  static constexpr int CLUSTER = PANGU_CLUSTER_M;
 };
 
 struct GemmOperands {

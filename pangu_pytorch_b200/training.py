@@ -234,7 +234,8 @@ def _block_backward(blk, ws, roll, t: BlockTape, sc: Scratch, g32, G, fp16):
     pa = 1.0 / LOSS_SCALE[fp16]
     ops.set_tag("hi" if C == 192 else "lo")
     # ---------------- x = x + s2 * LN2(Mlp(x))            (models/layers.py:251)
-    ops.linear(t.hidden, mlp._w2.get(mlp.linear2.weight), mlp.linear2.bias, sc.y32, sc.tmp16, False, fp16)
+    # pre-LayerNorm values y2 = hidden W2^T + b2 (fp32 only: the plain-GEMM path of pangu_dgrad with the (out, in) weight)
+    ops.dgrad(t.hidden, mlp._w2.get(mlp.linear2.weight), 0, fp16, out32=sc.y32, bias=mlp.linear2.bias)
     ops.layernorm_bwd(sc.y32, g32, blk.norm2.weight, G(blk.norm2.weight), G(blk.norm2.bias), T, C, LNB_IDENT, fp16,
                       dx16=sc.dy16, scale=t.s2, palpha=pa, dbias=G(mlp.linear2.bias))      # + d linear2.bias
     _linear_bwd(sc.dy16, t.hidden, mlp.linear2, G, fp16, with_bias=False)
@@ -244,7 +245,7 @@ def _block_backward(blk, ws, roll, t: BlockTape, sc: Scratch, g32, G, fp16):
     _linear_bwd(sc.dh16, t.xmid16, mlp.linear1, G, fp16, with_bias=False)
     ops.dgrad(sc.dh16, _wt(mlp, "w1", mlp.linear1.weight, fp16), 0, fp16, out32=g32, resid32=g32)
     # ---------------- x = shortcut + s1 * LN1(window_reverse(attention(window_partition(x))))   (:185-250)
-    ops.linear(t.att, att._w2.get(att.linear2.weight), att.linear2.bias, sc.y32, sc.tmp16, False, fp16)
+    ops.dgrad(t.att, att._w2.get(att.linear2.weight), 0, fp16, out32=sc.y32, bias=att.linear2.bias)       # y1, fp32 only
     ops.layernorm_bwd(sc.y32, g32, blk.norm1.weight, G(blk.norm1.weight), G(blk.norm1.bias), T, C, LNB_IDENT, fp16,
                       dx16=sc.dy16, scale=t.s1, palpha=pa, dbias=G(att.linear2.bias))      # + d attention.linear2.bias
     _linear_bwd(sc.dy16, t.att, att.linear2, G, fp16, with_bias=False)
