@@ -201,3 +201,51 @@ def test_full_025_backward_directional_derivative():
         assert abs(numeric - analytic) < 0.1 * abs(analytic) + 2e-5, (name, analytic, numeric)
     training.release_tape(model)
     pb.free_workspaces()
+
+
+def test_full_025_gradients_against_reference_golden():
+    """All 223 gradients at the FULL 0.25 degree shapes against the UNMODIFIED reference's own autograd
+    (tests/golden/train_grads.npz, written by oracle/make_golden.py --what train: eval-mode DropPath, stress weights,
+    0.5 * weighted-MSE loss so that the seed is smooth in the outputs).  The seed is formed here from the GPU
+    forward's own outputs, so this is the whole chain -- forward on the tape, seed, backward -- against the reference."""
+    import pangu_pytorch_b200 as pb
+    from pangu_pytorch_b200 import training
+    from tests.util import golden
+    gold = golden("train_grads.npz")
+    pb.set_operand_dtype("bf16")
+    pb.free_workspaces()
+    p = O.stress_weights(seed=int(gold["weights_seed"]), bias_std=0.5)
+    model = pb.PanguModel(device=DEV)
+    model.load_state_dict(p, strict=True)
+    model = model.to(DEV).train()
+    for blk in [m for m in model.modules() if hasattr(m, "drop_path")]:
+        blk.drop_path.drop_prob = 0.0
+    up, sf, stats, maps, ch = O.synthetic_inputs(seed=int(gold["inputs_seed"]), nontrivial_stats=True)
+    g = torch.Generator().manual_seed(int(gold["targets_seed"]))
+    tu = torch.randn(1, 5, 13, 721, 1440, generator=g).to(DEV)
+    ts = torch.randn(1, 4, 721, 1440, generator=g).to(DEV)
+    out, out_s = model(up.to(DEV), sf.to(DEV), [s.to(DEV) for s in stats], maps.to(DEV), ch.to(DEV))
+    wu = torch.tensor(O.UPPER_WEIGHTS, device=DEV).view(1, 5, 1, 1, 1)
+    ws = torch.tensor(O.SURFACE_WEIGHTS, device=DEV).view(1, 4, 1, 1)
+    with torch.no_grad():
+        du, ds = out - tu, out_s - ts
+        loss = 0.5 * (du * du * wu).mean() + 0.125 * (ds * ds * ws).mean()
+        gu, gs = du * wu / du.numel(), 0.25 * ds * ws / ds.numel()
+    assert abs(float(loss) - float(gold["loss"])) < 2e-3 * float(gold["loss"])
+    torch.autograd.backward((out, out_s), (gu, gs))
+    torch.cuda.synchronize()
+    worst = []
+    for name, prm in model.named_parameters():
+        pos = torch.from_numpy(gold[f"grad.{name}.pos"])
+        ref = torch.from_numpy(gold[f"grad.{name}.val"]).double()
+        mine = prm.grad.reshape(-1)[pos.to(DEV)].double().cpu()
+        err = float((mine - ref).norm() / ref.norm().clamp_min(1e-30))
+        nrm = float(prm.grad.double().norm()) / float(gold[f"grad.{name}.l2"])
+        worst.append((err, name, nrm))
+    worst.sort(reverse=True)
+    print("[full-size grads vs reference] worst:", [(round(e, 4), n.split("EarthSpecific")[-1], round(r, 4)) for e, n, r in worst[:6]])
+    for err, name, nrm in worst:
+        tol = TOL_BIAS_TABLE["bf16"] if name.endswith("earth_specific_bias") else TOL_GRAD["bf16"]
+        assert err < tol and abs(nrm - 1.0) < tol, (name, err, nrm)
+    training.release_tape(model)
+    pb.free_workspaces()

@@ -137,3 +137,14 @@ def test_scores_against_live_reference():
     assert torch.allclose(O.weighted_acc_channels(a, b), score.weighted_acc_torch_channels(a, b), rtol=1e-5, atol=1e-7)
     a4, b4 = a.unsqueeze(0), b.unsqueeze(0)
     assert torch.allclose(O.weighted_rmse_channels(a4, b4), score.weighted_rmse_torch_channels(a4, b4), rtol=1e-5)
+
+
+@pytest.mark.reference
+def test_block_gradients_against_live_reference():
+    """Oracle autograd == reference autograd for one EarthSpecificBlock per resolution and roll state (asserted inside)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    try:
+        import make_golden
+    finally:
+        sys.path.pop(0)
+    make_golden.gen_block_grads()
