@@ -208,6 +208,31 @@ def gen_full(kind: str):
     np.savez_compressed(os.path.join(GOLD, f"{kind}_forward.npz"), **out)
 
 
+def gen_rollout(steps: int = 7):
+    """7 x 24 h autoregressive rollout of the UNMODIFIED reference at the full 0.25 degree shapes (BASELINE.json
+    configs[1]): x_{k+1} = normBackData(model(x_k)) with the output-order statistics; ~7 min."""
+    _, RM = import_reference()
+    p = O.reference_like_weights(seed=0)
+    upper, surface, stats, maps, const_h = O.synthetic_inputs(seed=1, nontrivial_stats=True)
+    torch.manual_seed(0)
+    model = RM.PanguModel(device="cpu")
+    model.load_state_dict(p, strict=True)
+    model.eval()
+    ostats = O.output_statistics(stats)
+    out = {"weights_seed": np.int64(0), "inputs_seed": np.int64(1), "steps": np.int64(steps)}
+    for k in range(steps):
+        t0 = time.time()
+        with torch.no_grad():
+            ou, os_ = model(upper, surface, stats, maps, const_h)
+        upper, surface = O.norm_back_data(ou, os_, ostats)
+        put(out, f"step{k + 1}.upper", summarize(upper, 300 + 2 * k))
+        put(out, f"step{k + 1}.surface", summarize(surface, 301 + 2 * k))
+        out[f"step{k + 1}.upper.var_l2"] = upper[0].double().flatten(1).norm(dim=1).numpy()
+        out[f"step{k + 1}.surface.var_l2"] = surface[0].double().flatten(1).norm(dim=1).numpy()
+        print(f"reference rollout step {k + 1}: {time.time() - t0:.1f}s")
+    np.savez_compressed(os.path.join(GOLD, "rollout7.npz"), **out)
+
+
 def mse_seed_loss(ou, os_, tu, ts):
     """Smooth stand-in for the training loss used ONLY to pin the backward at full resolution: the weighted L1 of
     models/pangu_sample.py:61-67 has a sign() seed that flips wherever two forwards differ by rounding, so gradient
@@ -290,5 +315,6 @@ if __name__ == "__main__":
     for w in args.what.split(","):
         t0 = time.time()
         {"maps": gen_maps, "keys": gen_keys, "blocks": gen_blocks, "full": lambda: gen_full("full"),
-         "stress": lambda: gen_full("stress"), "train": gen_train, "blockgrads": gen_block_grads}[w]()
+         "stress": lambda: gen_full("stress"), "train": gen_train, "blockgrads": gen_block_grads,
+         "rollout": gen_rollout}[w]()
         print(f"[{w}] done in {time.time() - t0:.1f}s")

@@ -137,3 +137,25 @@ def test_graphed_rollout_is_bit_identical_to_eager():
     graphed = rollout_graphed(*args, steps=3)
     for (eu, es), (gu, gs) in zip(eager, graphed):
         assert torch.equal(eu, gu) and torch.equal(es, gs)
+
+
+@pytest.mark.parametrize("fmt", ["bf16", "fp16"])
+def test_full_025_seven_day_rollout_against_reference_golden(fmt):
+    """BASELINE.json configs[1]: 7 x 24 h free-running rollout at the full 0.25 degree shapes, every step against the
+    UNMODIFIED reference's own rollout (tests/golden/rollout7.npz, oracle/make_golden.py --what rollout).  One step
+    attenuates an input error by ~0.5, so the free-running bound is 2x the single-step tolerance."""
+    from pangu_pytorch_b200.rollout import rollout
+    from tests.util import golden, sampled_rel_l2
+    gold = golden("rollout7.npz")
+    p = O.reference_like_weights(seed=int(gold["weights_seed"]))
+    m = _model(p, fmt)
+    up, sf, stats, maps, ch = O.synthetic_inputs(seed=int(gold["inputs_seed"]), nontrivial_stats=True)
+    d = lambda t: t.to(DEV)
+    outs = rollout(m, d(up), d(sf), [d(s) for s in stats], d(maps), d(ch), steps=int(gold["steps"]), keep_on_device=False)
+    for k, (gu, gs) in enumerate(outs):
+        eu = sampled_rel_l2(gu, gold, f"step{k + 1}.upper")
+        es = sampled_rel_l2(gs, gold, f"step{k + 1}.surface")
+        vu = (gu[0].double().flatten(1).norm(dim=1) / torch.from_numpy(gold[f"step{k + 1}.upper.var_l2"])).numpy()
+        print(f"rollout {fmt} day {k + 1}: sampled rel-L2 upper {eu:.3e} surface {es:.3e}; per-variable norm ratio {vu.min():.4f}..{vu.max():.4f}")
+        assert eu < 2 * TOL_MODEL[fmt] and es < 2 * TOL_MODEL[fmt]
+        assert abs(vu - 1).max() < 2 * TOL_MODEL[fmt]
