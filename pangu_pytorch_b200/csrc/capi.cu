@@ -305,7 +305,7 @@ static int launch_mlp_fused_t(const void* x16_in, const void* w1_16, const void*
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(MF_THREADS);
+  cfg.blockDim = dim3(T::THREADS);
   cfg.dynamicSmemBytes = T::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -517,7 +517,12 @@ extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, cons
   PG_TRY(check_grid(Z, H, W, C, 0));
   const int T = Z * H * W;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static const bool fused = getenv("PANGU_B200_MLP_FUSED") != nullptr;     // development A/B switch (off until it wins)
+  // One-kernel Mlp (hidden activation kept in TMEM, csrc/mlp_fused.cuh): wins at C = 192 (500 vs 577 us: double-buffered
+  // Y accumulator), loses at C = 384 (TMEM holds a single Y).  It is taken when the caller does not ask for the hidden
+  // activation (ws_hidden == NULL; the training tape does ask).  PANGU_B200_MLP_FUSED = 0: never, 1: whenever allowed.
+  static const int fused_mode = getenv("PANGU_B200_MLP_FUSED") ? atoi(getenv("PANGU_B200_MLP_FUSED")) : -1;
+  const bool fused = ws_hidden == nullptr && (fused_mode < 0 ? C == 192 : fused_mode != 0);
+  PG_REQUIRE(fused || ws_hidden != nullptr, "mlp_ln_residual: ws_hidden is required on the two-kernel path (C=%d)", C);
   if (fused) {
     // one kernel: the hidden activation stays in tensor memory (ws_hidden is not touched)
     MlpArgs a;

@@ -26,16 +26,17 @@
 
 namespace pg {
 
-constexpr int MF_THREADS = 448;
 
 template <int C>
 struct MlpTraits {
   static constexpr int KX = C / 64;                    // K slabs of X (GEMM1)
   static constexpr int NH = C / 192;                   // 192-column halves of Y (GEMM2 N per instruction)
   static constexpr int NCH = 4 * C / 64;               // hidden chunks of 64 units
-  static constexpr int COL_H = C;                      // Hacc buffers follow the Y accumulator in TMEM
-  static constexpr int NB = (C == 192) ? 4 : 2;        // Hacc buffers of 64 columns: GEMM1 runs NB-1 chunks ahead of GEMM2
-  static_assert(C + NB * 64 <= 512 && NCH % NB == 0, "TMEM budget / buffer rotation");
+  static constexpr int YB = (C == 192) ? 2 : 1;        // Y accumulators: two at C=192, so that the LayerNorm epilogue of a
+                                                       // tile runs under the GEMMs of the next one (C=384: TMEM holds one)
+  static constexpr int COL_H = YB * C;                 // Hacc buffers follow the Y accumulator(s) in TMEM
+  static constexpr int NB = 2;                         // Hacc buffers of 64 columns: GEMM1 runs NB-1 chunks ahead of GEMM2
+  static_assert(YB * C + NB * 64 <= 512 && NCH % NB == 0, "TMEM budget / buffer rotation");
   static constexpr int S1 = (C == 192) ? 8 : 6;        // ring 1: W1 units [64 hidden x 64 k]  = 8 KB
   static constexpr int S2 = (C == 192) ? 3 : 2;        // ring 2: W2 units [192 out x 64 k]   = 24 KB
   static constexpr int X_BYTES = KX * 16384;
@@ -45,10 +46,13 @@ struct MlpTraits {
   static constexpr int OFF_R1 = X_BYTES;
   static constexpr int OFF_R2 = OFF_R1 + S1 * R1_UNIT;
   static constexpr int OFF_SLAB = OFF_R2 + S2 * R2_UNIT;
-  static constexpr int OFF_PAR = OFF_SLAB + 4 * SLAB_BYTES;       // b1 [4C], b2 / gamma / beta [C] fp32
-  static constexpr int OFF_TAB = OFF_PAR + 7 * C * 4;             // 4 warps x 64 ints
-  static constexpr int OFF_BAR = OFF_TAB + 4 * 64 * 4;
-  static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + 2 * NB + 2;
+  static constexpr int LNW = 4;                                   // LayerNorm epilogue warps (a second warpgroup alternating tiles
+                                                                  // was measured slower: 543 vs 508 us at C=192)
+  static constexpr int THREADS = 32 * (2 + LNW + 8);              // TMA, MMA, LayerNorm warps, 8 GELU warps
+  static constexpr int OFF_PAR = OFF_SLAB + LNW * SLAB_BYTES;     // b1 [4C], b2 / gamma / beta [C] fp32
+  static constexpr int OFF_TAB = OFF_PAR + 7 * C * 4;             // LNW warps x 64 ints
+  static constexpr int OFF_BAR = OFF_TAB + LNW * 64 * 4;
+  static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + 2 * NB + 2 * YB;
   static constexpr int SMEM_BYTES = 1024 + OFF_BAR + ((NUM_BARS * 8 + 16 + 127) / 128) * 128;
   static_assert(C == 192 || C == 384, "Pangu widths");
   static_assert(OFF_R1 % 1024 == 0 && OFF_R2 % 1024 == 0 && OFF_SLAB % 512 == 0, "operand alignment");
@@ -91,14 +95,21 @@ __device__ __forceinline__ void tmem_st32_(uint32_t taddr, const uint32_t* r) {
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16_(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait_() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int C, bool kFp16>
-__global__ void __launch_bounds__(MF_THREADS, 1)
+__global__ void __launch_bounds__(MlpTraits<C>::THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const MlpArgs a) {
   using T = MlpTraits<C>;
-  constexpr int KX = T::KX, NH = T::NH, NCH = T::NCH, S1 = T::S1, S2 = T::S2, NB = T::NB;
+  constexpr int KX = T::KX, NH = T::NH, NCH = T::NCH, S1 = T::S1, S2 = T::S2, NB = T::NB, YB = T::YB;
   extern __shared__ uint8_t mf_raw[];
   uint8_t* smem = mf_raw + ((1024u - (smem_u32(mf_raw) & 1023u)) & 1023u);
   uint8_t* xs = smem;                          // X tile: KX slabs [128 rows][128 B], SWIZZLE_128B
@@ -116,10 +127,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* r2full = r1empty + S1;             // [S2]
   uint64_t* r2empty = r2full + S2;             // [S2]  count 2
   uint64_t* hfull = r2empty + S2;              // [NB]  Hacc ready (GEMM1 done)
-  uint64_t* hready = hfull + NB;               // [NB]  H (16-bit) written back by 128 GELU threads
-  uint64_t* yfull = hready + NB;               // [1]   Y complete
-  uint64_t* yempty = yfull + 1;                // [1]   Y drained by the 128 epilogue threads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yempty + 1);
+  uint64_t* hready = hfull + NB;               // [NB]  H (16-bit) written back by the 256 GELU threads
+  uint64_t* yfull = hready + NB;               // [YB]  Y complete
+  uint64_t* yempty = yfull + YB;               // [YB]  Y drained by the 128 epilogue threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yempty + YB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta_rank = int(cluster_ctarank());
@@ -133,15 +144,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int k = 0; k < KX; ++k) { mbar_init(&xfull[k], 1); mbar_init(&xempty[k], 1); }
     for (int s = 0; s < S1; ++s) { mbar_init(&r1full[s], 1); mbar_init(&r1empty[s], 2); }
     for (int s = 0; s < S2; ++s) { mbar_init(&r2full[s], 1); mbar_init(&r2empty[s], 2); }
-    for (int b = 0; b < NB; ++b) { mbar_init(&hfull[b], 1); mbar_init(&hready[b], 128); }
-    mbar_init(yfull, 1);
-    mbar_init(yempty, 128);
+    for (int b = 0; b < NB; ++b) { mbar_init(&hfull[b], 1); mbar_init(&hready[b], 256); }
+    for (int y = 0; y < YB; ++y) { mbar_init(&yfull[y], 1); mbar_init(&yempty[y], 128); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   // epilogue parameters (shared by all tiles)
-  for (int i = threadIdx.x; i < 4 * C; i += MF_THREADS) s_b1[i] = a.b1[i];
-  for (int i = threadIdx.x; i < C; i += MF_THREADS) { s_b2[i] = a.b2[i]; s_gamma[i] = a.gamma[i]; s_beta[i] = a.beta[i]; }
+  for (int i = threadIdx.x; i < 4 * C; i += T::THREADS) s_b1[i] = a.b1[i];
+  for (int i = threadIdx.x; i < C; i += T::THREADS) { s_b2[i] = a.b2[i]; s_gamma[i] = a.gamma[i]; s_beta[i] = a.beta[i]; }
   tc_fence_before();
   cluster_sync_all();          // peer barriers are initialised before any multicast / remote commit
   tc_fence_after();
@@ -224,7 +234,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     auto gemm2 = [&](int c_in_tile, int tile_use) {
       const int cgx = tile_use * NCH + c_in_tile, hb = cgx % NB;
       mbar_wait(&hready[hb], (cgx / NB) & 1);
-      if (c_in_tile == 0) mbar_wait(yempty, (tile_use & 1) ^ 1);      // the epilogue has read the previous tile's Y
+      const int yb = tile_use % YB;
+      if (c_in_tile == 0) mbar_wait(&yempty[yb], ((tile_use / YB) & 1) ^ 1);   // the epilogue has drained this Y buffer
       tc_fence_after();
       for (int h = 0; h < NH; ++h, ++p2) {
         const int s = p2 % S2;
@@ -234,10 +245,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)     // K = 64 hidden units: H advances 8 TMEM columns per K16
-            umma_f16_ts_(tmem + h * 192, tmem + T::COL_H + 64 * hb + 8 * kk, db + uint64_t(kk * 2), idesc2,
+            umma_f16_ts_(tmem + yb * C + h * 192, tmem + T::COL_H + 64 * hb + 8 * kk, db + uint64_t(kk * 2), idesc2,
                          (c_in_tile | kk) != 0 ? 1u : 0u);
           umma_commit_mcast(&r2empty[s], uint16_t(3));
-          if (c_in_tile == NCH - 1 && h == NH - 1) umma_commit(yfull);
+          if (c_in_tile == NCH - 1 && h == NH - 1) umma_commit(&yfull[yb]);
         }
         __syncwarp();
       }
@@ -249,7 +260,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       if (cgx >= NB - 1) gemm2((cgx - (NB - 1)) % NCH, (cgx - (NB - 1)) / NCH);
     }
     (void)tuse;
-  } else if (warp < 6) {
+  } else if (warp < 2 + T::LNW) {
     // ================================ LayerNorm + residual epilogue ================================
     // one warp per TMEM lane quadrant; thread = one token row (statistics are thread-local)
     const int quad = warp & 3;
@@ -258,10 +269,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     int* s_tok = reinterpret_cast<int*>(smem + T::OFF_TAB) + ew * 64;
     int* s_dst = s_tok + 32;
     const Geo geo = make_geo(a.Z, a.H, a.W);
-    int tuse = 0;
-    for (int unit = pair; unit < num_units; unit += num_pairs, ++tuse) {
+    // LayerNorm warpgroup w of LNW / 4 takes this CTA's tiles w, w + LNW / 4, ...
+    for (int tuse = ew >> 2; pair + tuse * num_pairs < num_units; tuse += T::LNW / 4) {
+      const int unit = pair + tuse * num_pairs;
       const int tile = 2 * unit + cta_rank;
-      const uint32_t tacc = tmem + (uint32_t(quad * 32) << 16);
+      const int yb = tuse % YB;
+      const uint32_t tacc = tmem + (uint32_t(quad * 32) << 16) + yb * C;
       __syncwarp();
       {
         const int g = tile * 128 + quad * 32 + lane;
@@ -283,7 +296,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       };
       uint4 resq[PPR];
       load_resid(0, resq);         // latency hidden behind the wait for the accumulator
-      mbar_wait(yfull, tuse & 1);
+      mbar_wait(&yfull[yb], (tuse / YB) & 1);
       tc_fence_after();
       // ---- LayerNorm statistics of (acc + b2) over the row: shifted sums, packed fp32x2 math
       float mean, rstd;
@@ -346,7 +359,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         if (c0 + 32 >= C) {          // accumulator fully read: hand the Y buffer back to the MMA warp
           tc_fence_before();
-          mbar_arrive(yempty);
+          mbar_arrive(&yempty[yb]);
         }
         __syncwarp();
         // phase B: slab -> global, coalesced (8 lanes per row), + residual; fp32 stream and 16-bit shadow
@@ -375,36 +388,38 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   } else {
     // ================================ GELU warps ================================
-    // warpgroup wgp handles the chunks with (global chunk index & 1) == wgp, i.e. Hacc buffer wgp
-    const int quad = warp & 3, wgp = (warp - 6) >> 2;
+    // Both warpgroups work on EVERY chunk, 32 of its 64 hidden columns each: the G1 -> GELU -> G2 dependency chain
+    // (two Hacc buffers) is what paces the kernel, so the GELU latency per chunk is halved rather than two chunks being
+    // processed side by side.  Warpgroup 1 writes its packed H over fp32 columns that warpgroup 0 still has to read,
+    // hence the named barrier between the loads and the stores.
+    const int quad = warp & 3, wgp = (warp - (2 + T::LNW)) >> 2;
     const uint32_t hbase = tmem + (uint32_t(quad * 32) << 16) + T::COL_H;
-    int cgx = wgp;   // global chunk index of this warpgroup's next chunk (NCH and NB are even: parity is preserved)
+    int cgx = 0;
     for (int unit = pair; unit < num_units; unit += num_pairs) {
-      for (int c = wgp; c < NCH; c += 2, cgx += 2) {
+      for (int c = 0; c < NCH; ++c, ++cgx) {
         const int hb = cgx % NB;
         const uint32_t haddr = hbase + 64 * hb;
         mbar_wait(&hfull[hb], (cgx / NB) & 1);
         tc_fence_after();
-        uint32_t r[2][32];
-        tmem_ld32(haddr, r[0]);
-        tmem_ld32(haddr + 32, r[1]);
+        uint32_t r[32];
+        tmem_ld32(haddr + 32 * wgp, r);
         tmem_ld_wait();
-        uint32_t pk[32];
-        const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 64);
+        tc_fence_before();
+        named_bar_sync(2, 256);        // every fp32 column of this chunk is in registers
+        tc_fence_after();
+        uint32_t pk[16];
+        const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 64 + 32 * wgp);
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bb = b4[hh * 8 + j4];
-            float v0 = __uint_as_float(r[hh][4 * j4]) + bb.x, v1 = __uint_as_float(r[hh][4 * j4 + 1]) + bb.y;
-            float v2 = __uint_as_float(r[hh][4 * j4 + 2]) + bb.z, v3 = __uint_as_float(r[hh][4 * j4 + 3]) + bb.w;
-            gelu_erf2(v0, v1);
-            gelu_erf2(v2, v3);
-            pk[hh * 16 + 2 * j4] = pack16<kFp16>(v0, v1);
-            pk[hh * 16 + 2 * j4 + 1] = pack16<kFp16>(v2, v3);
-          }
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bb = b4[j4];
+          float v0 = __uint_as_float(r[4 * j4]) + bb.x, v1 = __uint_as_float(r[4 * j4 + 1]) + bb.y;
+          float v2 = __uint_as_float(r[4 * j4 + 2]) + bb.z, v3 = __uint_as_float(r[4 * j4 + 3]) + bb.w;
+          gelu_erf2(v0, v1);
+          gelu_erf2(v2, v3);
+          pk[2 * j4] = pack16<kFp16>(v0, v1);
+          pk[2 * j4 + 1] = pack16<kFp16>(v2, v3);
         }
-        tmem_st32_(haddr, pk);       // H (64 x 16-bit = 32 columns) over the first half of its own accumulator
+        tmem_st16_(haddr + 16 * wgp, pk);    // H (64 x 16-bit = 32 columns) over the first half of its own accumulator
         tmem_st_wait_();
         tc_fence_before();
         mbar_arrive(&hready[hb]);

@@ -9,7 +9,7 @@ HBM layout of one resolution (``GridWorkspace``), T = Z*H*W real tokens, Tp = wi
                              pad rows are zeroed once here and never written again
     qkv      [3C/32, Tp', 32] 16-bit, one plane per (q|k|v, head), window order rows, q pre-scaled
     att      [Tp, C ] 16-bit heads merged; the block path uses the first T rows in NATURAL token order
-    hidden   [T , 4C] 16-bit GELU(linear1) activations
+    hidden   [T , 4C] 16-bit GELU(linear1) activations (C = 384 only: at C = 192 they stay in tensor memory)
 """
 from __future__ import annotations
 
@@ -64,7 +64,8 @@ class GridWorkspace:
         # head-major: [3*heads planes][Tp rounded up to 128][32] (csrc/attention_tc.cuh)
         self.qkv = torch.empty(3 * C // 32, (Tp + 127) // 128 * 128, 32, dtype=h, device=device)
         self.att = torch.empty(Tp, C, dtype=h, device=device)
-        self.hidden = torch.empty(T, 4 * C, dtype=h, device=device)
+        # Mlp hidden activations: not materialised at C = 192 (single-kernel Mlp); the training tape supplies its own
+        self.hidden = None if C == 192 else torch.empty(T, 4 * C, dtype=h, device=device)
 
 
 _WORKSPACES: Dict[tuple, GridWorkspace] = {}

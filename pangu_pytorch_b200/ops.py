@@ -80,7 +80,7 @@ def set_tag(tag: str) -> None:
     _TAG[0] = tag
 
 
-def _call(name, *args):
+def _call(name, *args, kernels=None):
     prof = _PROFILE[0]
     if prof is None:
         _lib.call(name, *args)
@@ -90,7 +90,7 @@ def _call(name, *args):
         _lib.call(name, *args)
         b.record()
         prof.records.append((name, _TAG[0], a, b))
-    _LAUNCHES[0] += _KERNELS_PER_CALL[name]
+    _LAUNCHES[0] += _KERNELS_PER_CALL[name] if kernels is None else kernels
 
 
 def check_device() -> None:
@@ -154,7 +154,7 @@ def mlp_ln_residual(x16_in, w1, b1, w2, b2, gamma, beta, ws_hidden, x32, x16_out
     h, f = dtype16(fp16), torch.float32
     _call("pangu_mlp_ln_residual", _p(x16_in, h), _p(w1, h), _p(b1, f), _p(w2, h), _p(b2, f), _p(gamma, f),
           _p(beta, f), _p(ws_hidden, h), _p(x32, f), _p(x16_out, h), Z, H, W, C, int(roll_out), float(res_scale),
-          int(fp16), _stream())
+          int(fp16), _stream(), kernels=1 if ws_hidden is None else 2)
 
 
 def downsample(x32_in, gamma, beta, w16, ws_a, x32_out, x16w_out, Z, H, W, C, fp16: bool) -> None:
