@@ -293,6 +293,18 @@ static int launch_mlp_fused_t(const void* x16_in, const void* w1_16, const void*
   PG_TRY(make_map(&mx, x16_in, a.T, C, C, 128));
   PG_TRY(make_map(&m1, w1_16, 4 * C, C, C, 32));          // W1 [4C, C]: a CTA fetches 32 of a chunk's 64 hidden rows
   PG_TRY(make_map(&m2, w2_16, C, 4 * C, 4 * C, 96));      // W2 [C, 4C]: a CTA fetches 96 of a half's 192 output rows
+  CUtensorMap mr = mx;
+  if (T::RES_TMA) {     // fp32 residual stream [T, C]: 32-column x 32-row SWIZZLE_128B tiles (loaded, updated in place, stored)
+    PG_REQUIRE((reinterpret_cast<uintptr_t>(a.x32) & 15) == 0, "mlp: residual stream not 16 B aligned");
+    cuuint64_t dims[2] = {cuuint64_t(C), cuuint64_t(a.T)};
+    cuuint64_t strides[1] = {cuuint64_t(C) * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.x32, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled(mlp residual) failed (%d)", int(r));
+  }
   auto kern = mlp_fused_kernel<C, kFp16>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -315,7 +327,7 @@ static int launch_mlp_fused_t(const void* x16_in, const void* w1_16, const void*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PG_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, m1, m2, a));
+  PG_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, m1, m2, mr, a));
   PG_CUDA(cudaGetLastError());
   return 0;
 }

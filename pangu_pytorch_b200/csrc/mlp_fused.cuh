@@ -36,13 +36,17 @@ struct MlpTraits {
                                                        // tile runs under the GEMMs of the next one (C=384: TMEM holds one)
   static constexpr int COL_H = YB * C;                 // Hacc buffers follow the Y accumulator(s) in TMEM
   static constexpr int NB = 2;                         // Hacc buffers of 64 columns: GEMM1 runs NB-1 chunks ahead of GEMM2
+                                                       // (four 32-column buffers were measured much slower, 823 vs 484 us:
+                                                       // twice the barrier round trips in the single MMA-issuing warp)
   static_assert(YB * C + NB * 64 <= 512 && NCH % NB == 0, "TMEM budget / buffer rotation");
-  static constexpr int S1 = (C == 192) ? 8 : 6;        // ring 1: W1 units [64 hidden x 64 k]  = 8 KB
+  static constexpr int S1 = (C == 192) ? 7 : 6;        // ring 1: W1 units [64 hidden x 64 k]  = 8 KB
   static constexpr int S2 = (C == 192) ? 3 : 2;        // ring 2: W2 units [192 out x 64 k]   = 24 KB
   static constexpr int X_BYTES = KX * 16384;
   static constexpr int R1_UNIT = 8192, R2_UNIT = 24576;
   static constexpr int STG_PITCH = 32 * 4 + 16;        // epilogue slab row pitch (bytes), conflict-free 16 B rows
-  static constexpr int SLAB_BYTES = 32 * STG_PITCH;    // 4608 per epilogue warp
+  static constexpr bool RES_TMA = (C == 192);          // residual stream moved by TMA through two swizzled [32 x 32] fp32
+                                                       // tiles per epilogue warp (C=384: no shared memory left for them)
+  static constexpr int SLAB_BYTES = RES_TMA ? 2 * 4096 : 32 * STG_PITCH;    // per epilogue warp
   static constexpr int OFF_R1 = X_BYTES;
   static constexpr int OFF_R2 = OFF_R1 + S1 * R1_UNIT;
   static constexpr int OFF_SLAB = OFF_R2 + S2 * R2_UNIT;
@@ -52,10 +56,10 @@ struct MlpTraits {
   static constexpr int OFF_PAR = OFF_SLAB + LNW * SLAB_BYTES;     // b1 [4C], b2 / gamma / beta [C] fp32
   static constexpr int OFF_TAB = OFF_PAR + 7 * C * 4;             // LNW warps x 64 ints
   static constexpr int OFF_BAR = OFF_TAB + LNW * 64 * 4;
-  static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + 2 * NB + 2 * YB;
+  static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + 2 * NB + 2 * YB + 2 * LNW;
   static constexpr int SMEM_BYTES = 1024 + OFF_BAR + ((NUM_BARS * 8 + 16 + 127) / 128) * 128;
   static_assert(C == 192 || C == 384, "Pangu widths");
-  static_assert(OFF_R1 % 1024 == 0 && OFF_R2 % 1024 == 0 && OFF_SLAB % 512 == 0, "operand alignment");
+  static_assert(OFF_R1 % 1024 == 0 && OFF_R2 % 1024 == 0 && OFF_SLAB % (RES_TMA ? 1024 : 512) == 0, "operand alignment");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
 
@@ -107,7 +111,7 @@ __device__ __forceinline__ void tmem_st_wait_() { asm volatile("tcgen05.wait::st
 template <int C, bool kFp16>
 __global__ void __launch_bounds__(MlpTraits<C>::THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                 const __grid_constant__ CUtensorMap tmW2, const MlpArgs a) {
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmRes, const MlpArgs a) {
   using T = MlpTraits<C>;
   constexpr int KX = T::KX, NH = T::NH, NCH = T::NCH, S1 = T::S1, S2 = T::S2, NB = T::NB, YB = T::YB;
   extern __shared__ uint8_t mf_raw[];
@@ -130,7 +134,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* hready = hfull + NB;               // [NB]  H (16-bit) written back by the 256 GELU threads
   uint64_t* yfull = hready + NB;               // [YB]  Y complete
   uint64_t* yempty = yfull + YB;               // [YB]  Y drained by the 128 epilogue threads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yempty + YB);
+  uint64_t* rfull = yempty + YB;               // [LNW][2] residual tile landed (RES_TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2 * T::LNW);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta_rank = int(cluster_ctarank());
@@ -141,11 +146,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
+    if constexpr (T::RES_TMA) tma_prefetch_desc(&tmRes);
     for (int k = 0; k < KX; ++k) { mbar_init(&xfull[k], 1); mbar_init(&xempty[k], 1); }
     for (int s = 0; s < S1; ++s) { mbar_init(&r1full[s], 1); mbar_init(&r1empty[s], 2); }
     for (int s = 0; s < S2; ++s) { mbar_init(&r2full[s], 1); mbar_init(&r2empty[s], 2); }
     for (int b = 0; b < NB; ++b) { mbar_init(&hfull[b], 1); mbar_init(&hready[b], 256); }
     for (int y = 0; y < YB; ++y) { mbar_init(&yfull[y], 1); mbar_init(&yempty[y], 128); }
+    for (int i = 0; i < 2 * T::LNW; ++i) mbar_init(&rfull[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -283,107 +290,217 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         s_dst[lane] = (tok >= 0 && a.roll_out >= 0) ? token_to_win_row(geo, tok, a.roll_out) : tok;
       }
       __syncwarp();
-      constexpr int PPR = 8;       // 16 B fp32 pieces per 32-column row chunk
-      auto load_resid = [&](int cc, uint4 (&dst)[PPR]) {
-#pragma unroll
-        for (int it = 0; it < PPR; ++it) {
-          const int id = it * 32 + lane;
-          const int rr = id / PPR, pc = id % PPR;
-          const int tok = s_tok[rr];
-          dst[it] = make_uint4(0u, 0u, 0u, 0u);
-          if (tok >= 0) dst[it] = ldg16(a.x32 + size_t(tok) * C + cc + pc * 4);
+      if constexpr (T::RES_TMA) {
+        // ---- residual stream by TMA: two [32 rows x 32 fp32 columns] SWIZZLE_128B tiles per warp; chunk c lives in
+        // slot c & 1; the LayerNorm result is added in place and the tile leaves with one bulk store.
+        constexpr int NCHK = C / 32;
+        uint8_t* slots = smem + T::OFF_SLAB + ew * T::SLAB_BYTES;
+        uint64_t* rf = rfull + 2 * ew;
+        const int row0 = tile * 128 + quad * 32;
+        auto fetch = [&](int c) {            // lane 0
+          mbar_arrive_expect_tx(&rf[c & 1], 4096);
+          tma_load_2d(&tmRes, &rf[c & 1], slots + (c & 1) * 4096, c * 32, row0);
+        };
+        if (lane == 0) {
+          bulk_wait_read<0>();               // the previous tile's stores have read both slots
+          fetch(0);
+          fetch(1);
         }
-      };
-      uint4 resq[PPR];
-      load_resid(0, resq);         // latency hidden behind the wait for the accumulator
-      mbar_wait(&yfull[yb], (tuse / YB) & 1);
-      tc_fence_after();
-      // ---- LayerNorm statistics of (acc + b2) over the row: shifted sums, packed fp32x2 math
-      float mean, rstd;
-      {
-        float shift = 0.f;
-        f32x2 s1 = pack2(0.f, 0.f), s2 = pack2(0.f, 0.f);
-#pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tacc + c0, r);
-          tmem_ld_wait();
-          if (c0 == 0) shift = __uint_as_float(r[0]) + s_b2[0];
-          const f32x2 nshift = pack2(-shift, -shift);
-          const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bb = b4[j4];
-            const f32x2 v01 = add2(add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y)), nshift);
-            const f32x2 v23 = add2(add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w)), nshift);
-            s1 = add2(s1, add2(v01, v23));
-            s2 = fma2(v01, v01, s2);
-            s2 = fma2(v23, v23, s2);
-          }
-        }
-        float s1a, s1b, s2a, s2b;
-        unpack2(s1, s1a, s1b);
-        unpack2(s2, s2a, s2b);
-        const float inv_n = 1.0f / float(C);
-        const float m = (s1a + s1b) * inv_n;
-        const float var = fmaxf((s2a + s2b) * inv_n - m * m, 0.f);
-        mean = shift + m;
-        rstd = rsqrtf(var + a.eps);
-      }
-      const f32x2 ln_a = pack2(rstd, rstd), ln_b = pack2(-mean * rstd, -mean * rstd);
-#pragma unroll 1
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        uint4 resn[PPR];
-        if (c0 + 32 < C) load_resid(c0 + 32, resn);
-        // phase A: TMEM -> registers -> (acc + b2 - mean) * rstd * gamma + beta -> slab (row per lane)
+        mbar_wait(&yfull[yb], (tuse / YB) & 1);
+        tc_fence_after();
+        float mean, rstd;
         {
+          float shift = 0.f;
+          f32x2 s1 = pack2(0.f, 0.f), s2 = pack2(0.f, 0.f);
+#pragma unroll 1
+          for (int c0 = 0; c0 < C; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c0, r);
+            tmem_ld_wait();
+            if (c0 == 0) shift = __uint_as_float(r[0]) + s_b2[0];
+            const f32x2 nshift = pack2(-shift, -shift);
+            const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4];
+              const f32x2 v01 = add2(add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y)), nshift);
+              const f32x2 v23 = add2(add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w)), nshift);
+              s1 = add2(s1, add2(v01, v23));
+              s2 = fma2(v01, v01, s2);
+              s2 = fma2(v23, v23, s2);
+            }
+          }
+          float s1a, s1b, s2a, s2b;
+          unpack2(s1, s1a, s1b);
+          unpack2(s2, s2a, s2b);
+          const float inv_n = 1.0f / float(C);
+          const float m = (s1a + s1b) * inv_n;
+          const float var = fmaxf((s2a + s2b) * inv_n - m * m, 0.f);
+          mean = shift + m;
+          rstd = rsqrtf(var + a.eps);
+        }
+        const f32x2 ln_a = pack2(rstd * a.res_scale, rstd * a.res_scale), ln_b = pack2(-mean * rstd * a.res_scale, -mean * rstd * a.res_scale);
+        const f32x2 rs2 = pack2(a.res_scale, a.res_scale);
+#pragma unroll 1
+        for (int c = 0; c < NCHK; ++c) {
+          const int c0 = c * 32;
+          uint8_t* tl = slots + (c & 1) * 4096;
           uint32_t r[32];
           tmem_ld32(tacc + c0, r);
+          mbar_wait(&rf[c & 1], (tuse * (NCHK / 2) + (c >> 1)) & 1);     // each slot is filled NCHK / 2 times per tile
           tmem_ld_wait();
           const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
           const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
           const float4* e4 = reinterpret_cast<const float4*>(s_beta + c0);
-          uint4* dstp = reinterpret_cast<uint4*>(slab + lane * T::STG_PITCH);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
+          for (int j4 = 0; j4 < 8; ++j4) {      // x + s * ((acc + b2 - mean) * rstd * gamma + beta), in place (row per lane)
+            uint4* cell = reinterpret_cast<uint4*>(tl + lane * 128 + ((j4 ^ (lane & 7)) << 4));
+            const uint4 q = *cell;
             const float4 bb = b4[j4], gg = g4[j4], ee = e4[j4];
             f32x2 v01 = add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y));
             f32x2 v23 = add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w));
-            v01 = fma2(fma2(v01, ln_a, ln_b), pack2(gg.x, gg.y), pack2(ee.x, ee.y));
-            v23 = fma2(fma2(v23, ln_a, ln_b), pack2(gg.z, gg.w), pack2(ee.z, ee.w));
+            v01 = fma2(fma2(v01, ln_a, ln_b), pack2(gg.x, gg.y), fma2(rs2, pack2(ee.x, ee.y), pack2(__uint_as_float(q.x), __uint_as_float(q.y))));
+            v23 = fma2(fma2(v23, ln_a, ln_b), pack2(gg.z, gg.w), fma2(rs2, pack2(ee.z, ee.w), pack2(__uint_as_float(q.z), __uint_as_float(q.w))));
             float v0, v1, v2, v3;
             unpack2(v01, v0, v1);
             unpack2(v23, v2, v3);
-            dstp[j4] = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+            *cell = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+          }
+          if (c == NCHK - 1) {         // accumulator fully read: hand the Y buffer back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&yempty[yb]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < a.T) {
+            tma_store_2d(&tmRes, tl, c0, row0);     // rows beyond T are clipped
+            bulk_commit();
+          }
+          // 16-bit shadow from the finished tile: 64 B rows, 4 lanes per row, optionally scattered to window order
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int id = it * 32 + lane;
+            const int rr = id >> 2, pc = id & 3;
+            const int dst = s_dst[rr];
+            if (dst < 0) continue;
+            const uint4 a0 = *reinterpret_cast<const uint4*>(tl + rr * 128 + (((2 * pc) ^ (rr & 7)) << 4));
+            const uint4 a1 = *reinterpret_cast<const uint4*>(tl + rr * 128 + (((2 * pc + 1) ^ (rr & 7)) << 4));
+            uint4 h;
+            h.x = pack16<kFp16>(__uint_as_float(a0.x), __uint_as_float(a0.y));
+            h.y = pack16<kFp16>(__uint_as_float(a0.z), __uint_as_float(a0.w));
+            h.z = pack16<kFp16>(__uint_as_float(a1.x), __uint_as_float(a1.y));
+            h.w = pack16<kFp16>(__uint_as_float(a1.z), __uint_as_float(a1.w));
+            stg16(reinterpret_cast<uint16_t*>(a.out16) + size_t(dst) * C + c0 + pc * 8, h);
+          }
+          __syncwarp();
+          if (lane == 0 && c + 2 < NCHK) {
+            bulk_wait_read<0>();           // the store above has read this slot
+            fetch(c + 2);
           }
         }
-        if (c0 + 32 >= C) {          // accumulator fully read: hand the Y buffer back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&yempty[yb]);
+      } else {
+        constexpr int PPR = 8;       // 16 B fp32 pieces per 32-column row chunk
+        auto load_resid = [&](int cc, uint4 (&dst)[PPR]) {
+  #pragma unroll
+          for (int it = 0; it < PPR; ++it) {
+            const int id = it * 32 + lane;
+            const int rr = id / PPR, pc = id % PPR;
+            const int tok = s_tok[rr];
+            dst[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (tok >= 0) dst[it] = ldg16(a.x32 + size_t(tok) * C + cc + pc * 4);
+          }
+        };
+        uint4 resq[PPR];
+        load_resid(0, resq);         // latency hidden behind the wait for the accumulator
+        mbar_wait(&yfull[yb], (tuse / YB) & 1);
+        tc_fence_after();
+        // ---- LayerNorm statistics of (acc + b2) over the row: shifted sums, packed fp32x2 math
+        float mean, rstd;
+        {
+          float shift = 0.f;
+          f32x2 s1 = pack2(0.f, 0.f), s2 = pack2(0.f, 0.f);
+  #pragma unroll 1
+          for (int c0 = 0; c0 < C; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c0, r);
+            tmem_ld_wait();
+            if (c0 == 0) shift = __uint_as_float(r[0]) + s_b2[0];
+            const f32x2 nshift = pack2(-shift, -shift);
+            const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
+  #pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4];
+              const f32x2 v01 = add2(add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y)), nshift);
+              const f32x2 v23 = add2(add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w)), nshift);
+              s1 = add2(s1, add2(v01, v23));
+              s2 = fma2(v01, v01, s2);
+              s2 = fma2(v23, v23, s2);
+            }
+          }
+          float s1a, s1b, s2a, s2b;
+          unpack2(s1, s1a, s1b);
+          unpack2(s2, s2a, s2b);
+          const float inv_n = 1.0f / float(C);
+          const float m = (s1a + s1b) * inv_n;
+          const float var = fmaxf((s2a + s2b) * inv_n - m * m, 0.f);
+          mean = shift + m;
+          rstd = rsqrtf(var + a.eps);
         }
-        __syncwarp();
-        // phase B: slab -> global, coalesced (8 lanes per row), + residual; fp32 stream and 16-bit shadow
-#pragma unroll
-        for (int it = 0; it < PPR; ++it) {
-          const int id = it * 32 + lane;
-          const int rr = id / PPR, pc = id % PPR;
-          const int tok = s_tok[rr];
-          if (tok < 0) continue;
-          const int col = c0 + pc * 4;
-          const uint4 v = *reinterpret_cast<const uint4*>(slab + rr * T::STG_PITCH + pc * 16);
-          const uint4 q = resq[it];
-          const float f0 = fmaf(a.res_scale, __uint_as_float(v.x), __uint_as_float(q.x));
-          const float f1 = fmaf(a.res_scale, __uint_as_float(v.y), __uint_as_float(q.y));
-          const float f2 = fmaf(a.res_scale, __uint_as_float(v.z), __uint_as_float(q.z));
-          const float f3 = fmaf(a.res_scale, __uint_as_float(v.w), __uint_as_float(q.w));
-          stg16(a.x32 + size_t(tok) * C + col,
-                make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)));
-          *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.out16) + size_t(s_dst[rr]) * C + col) =
-              make_uint2(pack16<kFp16>(f0, f1), pack16<kFp16>(f2, f3));
+        const f32x2 ln_a = pack2(rstd, rstd), ln_b = pack2(-mean * rstd, -mean * rstd);
+  #pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          uint4 resn[PPR];
+          if (c0 + 32 < C) load_resid(c0 + 32, resn);
+          // phase A: TMEM -> registers -> (acc + b2 - mean) * rstd * gamma + beta -> slab (row per lane)
+          {
+            uint32_t r[32];
+            tmem_ld32(tacc + c0, r);
+            tmem_ld_wait();
+            const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
+            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
+            const float4* e4 = reinterpret_cast<const float4*>(s_beta + c0);
+            uint4* dstp = reinterpret_cast<uint4*>(slab + lane * T::STG_PITCH);
+  #pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4], gg = g4[j4], ee = e4[j4];
+              f32x2 v01 = add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y));
+              f32x2 v23 = add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w));
+              v01 = fma2(fma2(v01, ln_a, ln_b), pack2(gg.x, gg.y), pack2(ee.x, ee.y));
+              v23 = fma2(fma2(v23, ln_a, ln_b), pack2(gg.z, gg.w), pack2(ee.z, ee.w));
+              float v0, v1, v2, v3;
+              unpack2(v01, v0, v1);
+              unpack2(v23, v2, v3);
+              dstp[j4] = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+            }
+          }
+          if (c0 + 32 >= C) {          // accumulator fully read: hand the Y buffer back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&yempty[yb]);
+          }
+          __syncwarp();
+          // phase B: slab -> global, coalesced (8 lanes per row), + residual; fp32 stream and 16-bit shadow
+  #pragma unroll
+          for (int it = 0; it < PPR; ++it) {
+            const int id = it * 32 + lane;
+            const int rr = id / PPR, pc = id % PPR;
+            const int tok = s_tok[rr];
+            if (tok < 0) continue;
+            const int col = c0 + pc * 4;
+            const uint4 v = *reinterpret_cast<const uint4*>(slab + rr * T::STG_PITCH + pc * 16);
+            const uint4 q = resq[it];
+            const float f0 = fmaf(a.res_scale, __uint_as_float(v.x), __uint_as_float(q.x));
+            const float f1 = fmaf(a.res_scale, __uint_as_float(v.y), __uint_as_float(q.y));
+            const float f2 = fmaf(a.res_scale, __uint_as_float(v.z), __uint_as_float(q.z));
+            const float f3 = fmaf(a.res_scale, __uint_as_float(v.w), __uint_as_float(q.w));
+            stg16(a.x32 + size_t(tok) * C + col,
+                  make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)));
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.out16) + size_t(s_dst[rr]) * C + col) =
+                make_uint2(pack16<kFp16>(f0, f1), pack16<kFp16>(f2, f3));
+          }
+          __syncwarp();
+  #pragma unroll
+          for (int it = 0; it < PPR; ++it) resq[it] = resn[it];
         }
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < PPR; ++it) resq[it] = resn[it];
       }
     }
   } else {
@@ -427,6 +544,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   }
 
+  if constexpr (T::RES_TMA) {
+    if (warp >= 2 && warp < 2 + T::LNW && lane == 0) bulk_wait_all();     // shared memory must outlive the bulk stores
+  }
   tc_fence_before();
   cluster_sync_all();          // no multicast / remote commit may target an exited CTA
   if (warp == 1) {
