@@ -544,6 +544,7 @@ extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, cons
     a.Z = Z; a.H = H; a.W = W;
     a.roll_out = roll_out < 0 ? -1 : (roll_out > 0 ? 1 : 0);
     a.res_scale = res_scale; a.eps = 1e-5f;
+    a.debug = getenv("PANGU_B200_GEMM_DEBUG") ? atoi(getenv("PANGU_B200_GEMM_DEBUG")) : 0;
     if (C == 192) return fp16 ? launch_mlp_fused_t<192, true>(x16_in, w1_16, w2_16, a, s) : launch_mlp_fused_t<192, false>(x16_in, w1_16, w2_16, a, s);
     return fp16 ? launch_mlp_fused_t<384, true>(x16_in, w1_16, w2_16, a, s) : launch_mlp_fused_t<384, false>(x16_in, w1_16, w2_16, a, s);
   }

@@ -76,6 +76,8 @@ struct MlpArgs {
   int roll_out;         // < 0: out16 in natural order, else window order of that roll state
   float res_scale;      // DropPath factor (1 in eval)
   float eps;
+  int debug;            // development ablations (timing only): bit2 LayerNorm epilogue reduced to its barrier handshakes,
+                        // bit3 GELU arithmetic skipped
 };
 
 // D[tmem] (+)= A[tmem, 16-bit packed] * B[smem]
@@ -290,6 +292,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         s_dst[lane] = (tok >= 0 && a.roll_out >= 0) ? token_to_win_row(geo, tok, a.roll_out) : tok;
       }
       __syncwarp();
+      if (a.debug & 4) {
+        mbar_wait(&yfull[yb], (tuse / YB) & 1);
+        tc_fence_after();
+        tc_fence_before();
+        mbar_arrive(&yempty[yb]);
+        continue;
+      }
       if constexpr (T::RES_TMA) {
         // ---- residual stream by TMA: two [32 rows x 32 fp32 columns] SWIZZLE_128B tiles per warp; chunk c lives in
         // slot c & 1; the LayerNorm result is added in place and the tile leaves with one bulk store.
@@ -531,8 +540,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const float4 bb = b4[j4];
           float v0 = __uint_as_float(r[4 * j4]) + bb.x, v1 = __uint_as_float(r[4 * j4 + 1]) + bb.y;
           float v2 = __uint_as_float(r[4 * j4 + 2]) + bb.z, v3 = __uint_as_float(r[4 * j4 + 3]) + bb.w;
-          gelu_erf2(v0, v1);
-          gelu_erf2(v2, v3);
+          if (!(a.debug & 8)) {
+            gelu_erf2(v0, v1);
+            gelu_erf2(v2, v3);
+          }
           pk[2 * j4] = pack16<kFp16>(v0, v1);
           pk[2 * j4 + 1] = pack16<kFp16>(v2, v3);
         }
