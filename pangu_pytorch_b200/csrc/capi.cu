@@ -533,7 +533,7 @@ extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, cons
   // Y accumulator), loses at C = 384 (TMEM holds a single Y).  It is taken when the caller does not ask for the hidden
   // activation (ws_hidden == NULL; the training tape does ask).  PANGU_B200_MLP_FUSED = 0: never, 1: whenever allowed.
   static const int fused_mode = getenv("PANGU_B200_MLP_FUSED") ? atoi(getenv("PANGU_B200_MLP_FUSED")) : -1;
-  const bool fused = ws_hidden == nullptr && (fused_mode < 0 ? C == 192 : fused_mode != 0);
+  const bool fused = ws_hidden == nullptr && C == 192 && fused_mode != 0;
   PG_REQUIRE(fused || ws_hidden != nullptr, "mlp_ln_residual: ws_hidden is required on the two-kernel path (C=%d)", C);
   if (fused) {
     // one kernel: the hidden activation stays in tensor memory (ws_hidden is not touched)
@@ -545,8 +545,7 @@ extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, cons
     a.roll_out = roll_out < 0 ? -1 : (roll_out > 0 ? 1 : 0);
     a.res_scale = res_scale; a.eps = 1e-5f;
     a.debug = getenv("PANGU_B200_GEMM_DEBUG") ? atoi(getenv("PANGU_B200_GEMM_DEBUG")) : 0;
-    if (C == 192) return fp16 ? launch_mlp_fused_t<192, true>(x16_in, w1_16, w2_16, a, s) : launch_mlp_fused_t<192, false>(x16_in, w1_16, w2_16, a, s);
-    return fp16 ? launch_mlp_fused_t<384, true>(x16_in, w1_16, w2_16, a, s) : launch_mlp_fused_t<384, false>(x16_in, w1_16, w2_16, a, s);
+    return fp16 ? launch_mlp_fused_t<192, true>(x16_in, w1_16, w2_16, a, s) : launch_mlp_fused_t<192, false>(x16_in, w1_16, w2_16, a, s);
   }
   {
     GemmOperands o{x16_in, uint64_t(C), nullptr, 0, C, 0, w1_16, uint64_t(C), T, 4 * C};

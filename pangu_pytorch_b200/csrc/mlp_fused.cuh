@@ -39,10 +39,11 @@ struct MlpTraits {
                                                        // (four 32-column buffers were measured much slower, 823 vs 484 us:
                                                        // twice the barrier round trips in the single MMA-issuing warp)
   static_assert(YB * C + NB * 64 <= 512 && NCH % NB == 0, "TMEM budget / buffer rotation");
-  static constexpr int S1 = (C == 192) ? 7 : 6;        // ring 1: W1 units [64 hidden x 64 k]  = 8 KB
+  static constexpr int S1 = 2;                         // ring 1: W1 CHUNK units [64 hidden x C k] = KX x 8 KB (one barrier
+                                                       // round trip per chunk in the MMA-issuing warp instead of KX)
   static constexpr int S2 = (C == 192) ? 3 : 2;        // ring 2: W2 units [192 out x 64 k]   = 24 KB
   static constexpr int X_BYTES = KX * 16384;
-  static constexpr int R1_UNIT = 8192, R2_UNIT = 24576;
+  static constexpr int R1_UNIT = KX * 8192, R2_UNIT = 24576;
   static constexpr int STG_PITCH = 32 * 4 + 16;        // epilogue slab row pitch (bytes), conflict-free 16 B rows
   static constexpr bool RES_TMA = (C == 192);          // residual stream moved by TMA through two swizzled [32 x 32] fp32
                                                        // tiles per epilogue warp (C=384: no shared memory left for them)
@@ -58,7 +59,7 @@ struct MlpTraits {
   static constexpr int OFF_BAR = OFF_TAB + LNW * 64 * 4;
   static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + 2 * NB + 2 * YB + 2 * LNW;
   static constexpr int SMEM_BYTES = 1024 + OFF_BAR + ((NUM_BARS * 8 + 16 + 127) / 128) * 128;
-  static_assert(C == 192 || C == 384, "Pangu widths");
+  static_assert(C == 192, "the single-kernel Mlp is built for C = 192 (at C = 384 neither TMEM nor shared memory has room)");
   static_assert(OFF_R1 % 1024 == 0 && OFF_R2 % 1024 == 0 && OFF_SLAB % (RES_TMA ? 1024 : 512) == 0, "operand alignment");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
@@ -173,15 +174,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (lane == 0) {
       int p1 = 0, p2 = 0;        // ring positions (running counters)
       int xuse = 0;              // tiles loaded so far (X barrier phases)
-      auto load_w1 = [&](int c) {          // chunk c (0..NCH-1): KX units
-        for (int k = 0; k < KX; ++k, ++p1) {
-          const int s = p1 % S1;
-          mbar_wait(&r1empty[s], ((p1 / S1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&r1full[s], T::R1_UNIT);
-          // this CTA fetches 32 of the 64 hidden rows and multicasts them to the pair
-          tma_load_2d_mcast(&tmW1, &r1full[s], r1 + s * T::R1_UNIT + cta_rank * 4096, k * 64, c * 64 + cta_rank * 32,
+      auto load_w1 = [&](int c) {          // chunk c (0..NCH-1): one unit of KX slabs [64 hidden x 64 k]
+        const int s = p1 % S1;
+        mbar_wait(&r1empty[s], ((p1 / S1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&r1full[s], T::R1_UNIT);
+        for (int k = 0; k < KX; ++k)       // this CTA fetches 32 of the 64 hidden rows of every slab and multicasts them to the pair
+          tma_load_2d_mcast(&tmW1, &r1full[s], r1 + s * T::R1_UNIT + k * 8192 + cta_rank * 4096, k * 64, c * 64 + cta_rank * 32,
                             uint16_t(3), kEvictLast);
-        }
+        ++p1;
       };
       auto load_w2 = [&](int c) {          // chunk c: NH units [192 out rows x 64 k]
         for (int h = 0; h < NH; ++h, ++p2) {
@@ -222,23 +222,30 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     int tuse = 0;              // tiles started (X / Y barrier phases)
     auto gemm1 = [&](int c_in_tile, int tile_use) {      // chunk -> Hacc[cgx & 1]; cgx = global index of that chunk
       const int cgx = tile_use * NCH + c_in_tile, hb = cgx % NB;
-      for (int k = 0; k < KX; ++k, ++p1) {
-        const int s = p1 % S1;
-        if (c_in_tile == 0) mbar_wait(&xfull[k], tile_use & 1);
-        mbar_wait(&r1full[s], (p1 / S1) & 1);
-        tc_fence_after();
-        const uint64_t da = make_sdesc_sw128(xs_u32 + k * 16384);
-        const uint64_t db = make_sdesc_sw128(r1_u32 + s * T::R1_UNIT);
-        if (elect_one()) {
+      const int s = p1 % S1;
+      if (c_in_tile == 0) {
+        for (int k = 0; k < KX; ++k) mbar_wait(&xfull[k], tile_use & 1);
+      }
+      mbar_wait(&r1full[s], (p1 / S1) & 1);
+      tc_fence_after();
+      const uint32_t xa = xs_u32, wb = r1_u32 + s * T::R1_UNIT;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < KX; ++k) {
+          const uint64_t da = make_sdesc_sw128(xa + k * 16384);
+          const uint64_t db = make_sdesc_sw128(wb + k * 8192);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_f16_ss(tmem + T::COL_H + 64 * hb, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc1, (k | kk) != 0 ? 1u : 0u);
-          umma_commit_mcast(&r1empty[s], uint16_t(3));
-          if (c_in_tile == NCH - 1) umma_commit(&xempty[k]);     // last reader of this X slab
-          if (k == KX - 1) umma_commit(&hfull[hb]);
         }
-        __syncwarp();
+        umma_commit_mcast(&r1empty[s], uint16_t(3));
+        if (c_in_tile == NCH - 1) {
+          for (int k = 0; k < KX; ++k) umma_commit(&xempty[k]);     // last reader of the X slabs
+        }
+        umma_commit(&hfull[hb]);
       }
+      __syncwarp();
+      ++p1;
     };
     auto gemm2 = [&](int c_in_tile, int tile_use) {
       const int cgx = tile_use * NCH + c_in_tile, hb = cgx % NB;
