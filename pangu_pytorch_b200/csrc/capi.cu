@@ -291,8 +291,8 @@ static int launch_mlp_fused_t(const void* x16_in, const void* w1_16, const void*
   using T = MlpTraits<C>;
   CUtensorMap mx, m1, m2;
   PG_TRY(make_map(&mx, x16_in, a.T, C, C, 128));
-  PG_TRY(make_map(&m1, w1_16, 4 * C, C, C, 32));          // W1 [4C, C]: a CTA fetches 32 of a chunk's 64 hidden rows
-  PG_TRY(make_map(&m2, w2_16, C, 4 * C, 4 * C, 96));      // W2 [C, 4C]: a CTA fetches 96 of a half's 192 output rows
+  PG_TRY(make_map(&m1, w1_16, 4 * C, C, C, T::MCAST ? 32 : 64));     // W1 [4C, C]: a chunk's 64 hidden rows (half of them with multicast)
+  PG_TRY(make_map(&m2, w2_16, C, 4 * C, 4 * C, T::MCAST ? 96 : 192));   // W2 [C, 4C]: 192 output rows (96 with multicast)
   CUtensorMap mr = mx;
   if (T::RES_TMA) {     // fp32 residual stream [T, C]: 32-column x 32-row SWIZZLE_128B tiles (loaded, updated in place, stored)
     PG_REQUIRE((reinterpret_cast<uintptr_t>(a.x32) & 15) == 0, "mlp: residual stream not 16 B aligned");

@@ -42,6 +42,11 @@ struct MlpTraits {
   static constexpr int S1 = 2;                         // ring 1: W1 CHUNK units [64 hidden x C k] = KX x 8 KB (one barrier
                                                        // round trip per chunk in the MMA-issuing warp instead of KX)
   static constexpr int S2 = (C == 192) ? 3 : 2;        // ring 2: W2 units [192 out x 64 k]   = 24 KB
+#ifndef PANGU_MLP_MCAST
+#define PANGU_MLP_MCAST 1
+#endif
+  static constexpr bool MCAST = PANGU_MLP_MCAST != 0;  // weight units shared by the CTA pair through TMA multicast (couples the two
+                                                       // CTAs' rings: every slot waits for both) or fetched by each CTA on its own
   static constexpr int X_BYTES = KX * 16384;
   static constexpr int R1_UNIT = KX * 8192, R2_UNIT = 24576;
   static constexpr int STG_PITCH = 32 * 4 + 16;        // epilogue slab row pitch (bytes), conflict-free 16 B rows
@@ -151,8 +156,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmW2);
     if constexpr (T::RES_TMA) tma_prefetch_desc(&tmRes);
     for (int k = 0; k < KX; ++k) { mbar_init(&xfull[k], 1); mbar_init(&xempty[k], 1); }
-    for (int s = 0; s < S1; ++s) { mbar_init(&r1full[s], 1); mbar_init(&r1empty[s], 2); }
-    for (int s = 0; s < S2; ++s) { mbar_init(&r2full[s], 1); mbar_init(&r2empty[s], 2); }
+    for (int s = 0; s < S1; ++s) { mbar_init(&r1full[s], 1); mbar_init(&r1empty[s], T::MCAST ? 2 : 1); }
+    for (int s = 0; s < S2; ++s) { mbar_init(&r2full[s], 1); mbar_init(&r2empty[s], T::MCAST ? 2 : 1); }
     for (int b = 0; b < NB; ++b) { mbar_init(&hfull[b], 1); mbar_init(&hready[b], 256); }
     for (int y = 0; y < YB; ++y) { mbar_init(&yfull[y], 1); mbar_init(&yempty[y], 128); }
     for (int i = 0; i < 2 * T::LNW; ++i) mbar_init(&rfull[i], 1);
@@ -178,9 +183,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int s = p1 % S1;
         mbar_wait(&r1empty[s], ((p1 / S1) & 1) ^ 1);
         mbar_arrive_expect_tx(&r1full[s], T::R1_UNIT);
-        for (int k = 0; k < KX; ++k)       // this CTA fetches 32 of the 64 hidden rows of every slab and multicasts them to the pair
-          tma_load_2d_mcast(&tmW1, &r1full[s], r1 + s * T::R1_UNIT + k * 8192 + cta_rank * 4096, k * 64, c * 64 + cta_rank * 32,
-                            uint16_t(3), kEvictLast);
+        for (int k = 0; k < KX; ++k) {
+          if constexpr (T::MCAST)          // this CTA fetches 32 of the 64 hidden rows of every slab and multicasts them to the pair
+            tma_load_2d_mcast(&tmW1, &r1full[s], r1 + s * T::R1_UNIT + k * 8192 + cta_rank * 4096, k * 64, c * 64 + cta_rank * 32,
+                              uint16_t(3), kEvictLast);
+          else
+            tma_load_2d_hint(&tmW1, &r1full[s], r1 + s * T::R1_UNIT + k * 8192, k * 64, c * 64, kEvictLast);
+        }
         ++p1;
       };
       auto load_w2 = [&](int c) {          // chunk c: NH units [192 out rows x 64 k]
@@ -188,8 +197,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int s = p2 % S2;
           mbar_wait(&r2empty[s], ((p2 / S2) & 1) ^ 1);
           mbar_arrive_expect_tx(&r2full[s], T::R2_UNIT);
-          tma_load_2d_mcast(&tmW2, &r2full[s], r2 + s * T::R2_UNIT + cta_rank * 12288, c * 64, h * 192 + cta_rank * 96,
-                            uint16_t(3), kEvictLast);
+          if constexpr (T::MCAST)
+            tma_load_2d_mcast(&tmW2, &r2full[s], r2 + s * T::R2_UNIT + cta_rank * 12288, c * 64, h * 192 + cta_rank * 96,
+                              uint16_t(3), kEvictLast);
+          else
+            tma_load_2d_hint(&tmW2, &r2full[s], r2 + s * T::R2_UNIT, c * 64, h * 192, kEvictLast);
         }
       };
       auto load_x = [&](int tile, int use) {   // use-th X tile of this CTA; slabs free up as the previous tile's last GEMM1 retires
@@ -238,7 +250,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int kk = 0; kk < 4; ++kk)
             umma_f16_ss(tmem + T::COL_H + 64 * hb, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc1, (k | kk) != 0 ? 1u : 0u);
         }
-        umma_commit_mcast(&r1empty[s], uint16_t(3));
+        if constexpr (T::MCAST) umma_commit_mcast(&r1empty[s], uint16_t(3)); else umma_commit(&r1empty[s]);
         if (c_in_tile == NCH - 1) {
           for (int k = 0; k < KX; ++k) umma_commit(&xempty[k]);     // last reader of the X slabs
         }
@@ -263,7 +275,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int kk = 0; kk < 4; ++kk)     // K = 64 hidden units: H advances 8 TMEM columns per K16
             umma_f16_ts_(tmem + yb * C + h * 192, tmem + T::COL_H + 64 * hb + 8 * kk, db + uint64_t(kk * 2), idesc2,
                          (c_in_tile | kk) != 0 ? 1u : 0u);
-          umma_commit_mcast(&r2empty[s], uint16_t(3));
+          if constexpr (T::MCAST) umma_commit_mcast(&r2empty[s], uint16_t(3)); else umma_commit(&r2empty[s]);
           if (c_in_tile == NCH - 1 && h == NH - 1) umma_commit(&yfull[yb]);
         }
         __syncwarp();
@@ -534,6 +546,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t haddr = hbase + 64 * hb;
         mbar_wait(&hfull[hb], (cgx / NB) & 1);
         tc_fence_after();
+        if (a.debug & 16) {            // development ablation: barrier hand-offs only, no TMEM traffic
+          tc_fence_before();
+          mbar_arrive(&hready[hb]);
+          continue;
+        }
         uint32_t r[32];
         tmem_ld32(haddr + 32 * wgp, r);
         tmem_ld_wait();
