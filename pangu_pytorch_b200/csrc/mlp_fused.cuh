@@ -41,7 +41,8 @@ struct MlpTraits {
   static_assert(YB * C + NB * 64 <= 512 && NCH % NB == 0, "TMEM budget / buffer rotation");
   static constexpr int S1 = 2;                         // ring 1: W1 CHUNK units [64 hidden x C k] = KX x 8 KB (one barrier
                                                        // round trip per chunk in the MMA-issuing warp instead of KX)
-  static constexpr int S2 = (C == 192) ? 3 : 2;        // ring 2: W2 units [192 out x 64 k]   = 24 KB
+  static constexpr int S2 = 2;                         // ring 2: W2 units [192 out x 64 k]   = 24 KB
+  static constexpr int NHS = 2;                        // H operand buffers in shared memory [128 x 64] 16-bit = 16 KB, one per GELU warpgroup
 #ifndef PANGU_MLP_MCAST
 #define PANGU_MLP_MCAST 1
 #endif
@@ -55,14 +56,15 @@ struct MlpTraits {
   static constexpr int SLAB_BYTES = RES_TMA ? 2 * 4096 : 32 * STG_PITCH;    // per epilogue warp
   static constexpr int OFF_R1 = X_BYTES;
   static constexpr int OFF_R2 = OFF_R1 + S1 * R1_UNIT;
-  static constexpr int OFF_SLAB = OFF_R2 + S2 * R2_UNIT;
+  static constexpr int OFF_H = OFF_R2 + S2 * R2_UNIT;
+  static constexpr int OFF_SLAB = OFF_H + NHS * 16384;
   static constexpr int LNW = 4;                                   // LayerNorm epilogue warps (a second warpgroup alternating tiles
                                                                   // was measured slower: 543 vs 508 us at C=192)
-  static constexpr int THREADS = 32 * (2 + LNW + 8);              // TMA, MMA, LayerNorm warps, 8 GELU warps
+  static constexpr int THREADS = 32 * (3 + LNW + 8);              // TMA, GEMM1 issuer, GEMM2 issuer, LayerNorm warps, 8 GELU warps
   static constexpr int OFF_PAR = OFF_SLAB + LNW * SLAB_BYTES;     // b1 [4C], b2 / gamma / beta [C] fp32
   static constexpr int OFF_TAB = OFF_PAR + 7 * C * 4;             // LNW warps x 64 ints
   static constexpr int OFF_BAR = OFF_TAB + LNW * 64 * 4;
-  static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + 2 * NB + 2 * YB + 2 * LNW;
+  static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + 2 * NB + 2 * NHS + 2 * YB + 2 * LNW;
   static constexpr int SMEM_BYTES = 1024 + OFF_BAR + ((NUM_BARS * 8 + 16 + 127) / 128) * 128;
   static_assert(C == 192, "the single-kernel Mlp is built for C = 192 (at C = 384 neither TMEM nor shared memory has room)");
   static_assert(OFF_R1 % 1024 == 0 && OFF_R2 % 1024 == 0 && OFF_SLAB % (RES_TMA ? 1024 : 512) == 0, "operand alignment");
@@ -127,6 +129,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* xs = smem;                          // X tile: KX slabs [128 rows][128 B], SWIZZLE_128B
   uint8_t* r1 = smem + T::OFF_R1;              // W1 units
   uint8_t* r2 = smem + T::OFF_R2;              // W2 units
+  uint8_t* hs = smem + T::OFF_H;               // H operand buffers
   float* s_b1 = reinterpret_cast<float*>(smem + T::OFF_PAR);
   float* s_b2 = s_b1 + 4 * C;
   float* s_gamma = s_b2 + C;
@@ -139,8 +142,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* r2full = r1empty + S1;             // [S2]
   uint64_t* r2empty = r2full + S2;             // [S2]  count 2
   uint64_t* hfull = r2empty + S2;              // [NB]  Hacc ready (GEMM1 done)
-  uint64_t* hready = hfull + NB;               // [NB]  H (16-bit) written back by the 256 GELU threads
-  uint64_t* yfull = hready + NB;               // [YB]  Y complete
+  uint64_t* hempty = hfull + NB;               // [NB]  Hacc loaded into registers by the 128 GELU threads of its warpgroup
+  uint64_t* sfull = hempty + NB;               // [NHS] H (16-bit, K-major SWIZZLE_128B) written to shared memory by 128 threads
+  uint64_t* sempty = sfull + T::NHS;           // [NHS] GEMM2 has read the H buffer
+  uint64_t* yfull = sempty + T::NHS;           // [YB]  Y complete
   uint64_t* yempty = yfull + YB;               // [YB]  Y drained by the 128 epilogue threads
   uint64_t* rfull = yempty + YB;               // [LNW][2] residual tile landed (RES_TMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2 * T::LNW);
@@ -158,7 +163,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int k = 0; k < KX; ++k) { mbar_init(&xfull[k], 1); mbar_init(&xempty[k], 1); }
     for (int s = 0; s < S1; ++s) { mbar_init(&r1full[s], 1); mbar_init(&r1empty[s], T::MCAST ? 2 : 1); }
     for (int s = 0; s < S2; ++s) { mbar_init(&r2full[s], 1); mbar_init(&r2empty[s], T::MCAST ? 2 : 1); }
-    for (int b = 0; b < NB; ++b) { mbar_init(&hfull[b], 1); mbar_init(&hready[b], 256); }
+    for (int b = 0; b < NB; ++b) { mbar_init(&hfull[b], 1); mbar_init(&hempty[b], 128); }
+    for (int b = 0; b < T::NHS; ++b) { mbar_init(&sfull[b], 128); mbar_init(&sempty[b], 1); }
     for (int y = 0; y < YB; ++y) { mbar_init(&yfull[y], 1); mbar_init(&yempty[y], 128); }
     for (int i = 0; i < 2 * T::LNW; ++i) mbar_init(&rfull[i], 1);
     fence_barrier_init();
@@ -224,9 +230,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       (void)xuse;
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    // whole warp converged, warp-uniform operands; one elected lane issues
+  } else if (warp == 1 || warp == 2) {
+    // ================================ MMA issuers ================================
+    // Warp 1 issues every GEMM1, warp 2 every GEMM2 (whole warp converged, warp-uniform operands, one elected lane
+    // issues), so neither sits in the other's mbarrier round trips.  The hand-overs between the two GEMMs all go
+    // through mbarriers: Hacc back to GEMM1 as soon as the GELU warps hold it in registers (hempty), H to GEMM2 through
+    // a shared-memory operand buffer (sfull / sempty).
     constexpr uint32_t idesc1 = make_idesc_f16(128, 64, kFp16);
     constexpr uint32_t idesc2 = make_idesc_f16(128, 192, kFp16);
     const uint32_t xs_u32 = smem_u32(xs), r1_u32 = smem_u32(r1), r2_u32 = smem_u32(r2);
@@ -235,6 +244,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     auto gemm1 = [&](int c_in_tile, int tile_use) {      // chunk -> Hacc[cgx & 1]; cgx = global index of that chunk
       const int cgx = tile_use * NCH + c_in_tile, hb = cgx % NB;
       const int s = p1 % S1;
+      mbar_wait(&hempty[hb], ((cgx / NB) & 1) ^ 1);       // the GELU warps hold the buffer's previous contents in registers
+      tc_fence_after();
       if (c_in_tile == 0) {
         for (int k = 0; k < KX; ++k) mbar_wait(&xfull[k], tile_use & 1);
       }
@@ -259,12 +270,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       __syncwarp();
       ++p1;
     };
+    const uint32_t hs_u32 = smem_u32(hs);
     auto gemm2 = [&](int c_in_tile, int tile_use) {
-      const int cgx = tile_use * NCH + c_in_tile, hb = cgx % NB;
-      mbar_wait(&hready[hb], (cgx / NB) & 1);
+      const int cgx = tile_use * NCH + c_in_tile, sb = cgx % T::NHS;
+      mbar_wait(&sfull[sb], (cgx / T::NHS) & 1);         // GELU(H) of this chunk is in shared memory
       const int yb = tile_use % YB;
       if (c_in_tile == 0) mbar_wait(&yempty[yb], ((tile_use / YB) & 1) ^ 1);   // the epilogue has drained this Y buffer
       tc_fence_after();
+      const uint64_t da = make_sdesc_sw128(hs_u32 + sb * 16384);
       for (int h = 0; h < NH; ++h, ++p2) {
         const int s = p2 % S2;
         mbar_wait(&r2full[s], (p2 / S2) & 1);
@@ -272,10 +285,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint64_t db = make_sdesc_sw128(r2_u32 + s * T::R2_UNIT);
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)     // K = 64 hidden units: H advances 8 TMEM columns per K16
-            umma_f16_ts_(tmem + yb * C + h * 192, tmem + T::COL_H + 64 * hb + 8 * kk, db + uint64_t(kk * 2), idesc2,
-                         (c_in_tile | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk)     // K = 64 hidden units
+            umma_f16_ss(tmem + yb * C + h * 192, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc2, (c_in_tile | kk) != 0 ? 1u : 0u);
           if constexpr (T::MCAST) umma_commit_mcast(&r2empty[s], uint16_t(3)); else umma_commit(&r2empty[s]);
+          if (h == NH - 1) umma_commit(&sempty[sb]);
           if (c_in_tile == NCH - 1 && h == NH - 1) umma_commit(&yfull[yb]);
         }
         __syncwarp();
@@ -283,16 +296,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     };
     const int my_tiles = (num_units - pair + num_pairs - 1) / num_pairs;
     const int total = my_tiles * NCH;
-    for (int cgx = 0; cgx < total + NB - 1; ++cgx) {
-      if (cgx < total) gemm1(cgx % NCH, cgx / NCH);
-      if (cgx >= NB - 1) gemm2((cgx - (NB - 1)) % NCH, (cgx - (NB - 1)) / NCH);
+    if (warp == 1) {
+      for (int cgx = 0; cgx < total; ++cgx) gemm1(cgx % NCH, cgx / NCH);
+    } else {
+      for (int cgx = 0; cgx < total; ++cgx) gemm2(cgx % NCH, cgx / NCH);
     }
     (void)tuse;
-  } else if (warp < 2 + T::LNW) {
+  } else if (warp < 3 + T::LNW) {
     // ================================ LayerNorm + residual epilogue ================================
     // one warp per TMEM lane quadrant; thread = one token row (statistics are thread-local)
     const int quad = warp & 3;
-    const int ew = warp - 2;
+    const int ew = warp - 3;
     uint8_t* slab = smem + T::OFF_SLAB + ew * T::SLAB_BYTES;
     int* s_tok = reinterpret_cast<int*>(smem + T::OFF_TAB) + ew * 64;
     int* s_dst = s_tok + 32;
@@ -533,54 +547,53 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   } else {
     // ================================ GELU warps ================================
-    // Both warpgroups work on EVERY chunk, 32 of its 64 hidden columns each: the G1 -> GELU -> G2 dependency chain
-    // (two Hacc buffers) is what paces the kernel, so the GELU latency per chunk is halved rather than two chunks being
-    // processed side by side.  Warpgroup 1 writes its packed H over fp32 columns that warpgroup 0 still has to read,
-    // hence the named barrier between the loads and the stores.
-    const int quad = warp & 3, wgp = (warp - (2 + T::LNW)) >> 2;
-    const uint32_t hbase = tmem + (uint32_t(quad * 32) << 16) + T::COL_H;
-    int cgx = 0;
+    // Warpgroup w owns the chunks with (global chunk index & 1) == w, Hacc buffer w and H buffer w.  It pulls the fp32
+    // accumulator into registers and hands the TMEM buffer straight back (GEMM1 of chunk c + 2 may start), applies
+    // bias + GELU and writes the 16-bit H tile to shared memory as the K-major SWIZZLE_128B A operand of GEMM2.
+    const int quad = warp & 3, wgp = (warp - (3 + T::LNW)) >> 2;
+    const uint32_t haddr = tmem + (uint32_t(quad * 32) << 16) + T::COL_H + 64 * wgp;
+    const int row = quad * 32 + lane;
+    uint8_t* hrow = hs + wgp * 16384 + row * 128;
+    int n = 0;           // chunks this warpgroup has processed
     for (int unit = pair; unit < num_units; unit += num_pairs) {
-      for (int c = 0; c < NCH; ++c, ++cgx) {
-        const int hb = cgx % NB;
-        const uint32_t haddr = hbase + 64 * hb;
-        mbar_wait(&hfull[hb], (cgx / NB) & 1);
+      for (int c = wgp; c < NCH; c += 2, ++n) {
+        mbar_wait(&hfull[wgp], n & 1);
         tc_fence_after();
-        if (a.debug & 16) {            // development ablation: barrier hand-offs only, no TMEM traffic
-          tc_fence_before();
-          mbar_arrive(&hready[hb]);
-          continue;
-        }
-        uint32_t r[32];
-        tmem_ld32(haddr + 32 * wgp, r);
+        uint32_t r[2][32];
+        tmem_ld32(haddr, r[0]);
+        tmem_ld32(haddr + 32, r[1]);
         tmem_ld_wait();
         tc_fence_before();
-        named_bar_sync(2, 256);        // every fp32 column of this chunk is in registers
-        tc_fence_after();
-        uint32_t pk[16];
-        const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 64 + 32 * wgp);
+        mbar_arrive(&hempty[wgp]);
+        uint32_t pk[32];
+        const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 64);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bb = b4[j4];
-          float v0 = __uint_as_float(r[4 * j4]) + bb.x, v1 = __uint_as_float(r[4 * j4 + 1]) + bb.y;
-          float v2 = __uint_as_float(r[4 * j4 + 2]) + bb.z, v3 = __uint_as_float(r[4 * j4 + 3]) + bb.w;
-          if (!(a.debug & 8)) {
-            gelu_erf2(v0, v1);
-            gelu_erf2(v2, v3);
+        for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = b4[hh * 8 + j4];
+            float v0 = __uint_as_float(r[hh][4 * j4]) + bb.x, v1 = __uint_as_float(r[hh][4 * j4 + 1]) + bb.y;
+            float v2 = __uint_as_float(r[hh][4 * j4 + 2]) + bb.z, v3 = __uint_as_float(r[hh][4 * j4 + 3]) + bb.w;
+            if (!(a.debug & 8)) {
+              gelu_erf2(v0, v1);
+              gelu_erf2(v2, v3);
+            }
+            pk[hh * 16 + 2 * j4] = pack16<kFp16>(v0, v1);
+            pk[hh * 16 + 2 * j4 + 1] = pack16<kFp16>(v2, v3);
           }
-          pk[2 * j4] = pack16<kFp16>(v0, v1);
-          pk[2 * j4 + 1] = pack16<kFp16>(v2, v3);
         }
-        tmem_st16_(haddr + 16 * wgp, pk);    // H (64 x 16-bit = 32 columns) over the first half of its own accumulator
-        tmem_st_wait_();
-        tc_fence_before();
-        mbar_arrive(&hready[hb]);
+        mbar_wait(&sempty[wgp], (n & 1) ^ 1);        // GEMM2 of this warpgroup's previous chunk has read the buffer
+#pragma unroll
+        for (int q = 0; q < 8; ++q)                  // 8 x 16 B = this row's 64 hidden units, XOR-swizzled 16 B chunks
+          *reinterpret_cast<uint4*>(hrow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        fence_proxy_async_smem();
+        mbar_arrive(&sfull[wgp]);
       }
     }
   }
 
   if constexpr (T::RES_TMA) {
-    if (warp >= 2 && warp < 2 + T::LNW && lane == 0) bulk_wait_all();     // shared memory must outlive the bulk stores
+    if (warp >= 3 && warp < 3 + T::LNW && lane == 0) bulk_wait_all();     // shared memory must outlive the bulk stores
   }
   tc_fence_before();
   cluster_sync_all();          // no multicast / remote commit may target an exited CTA
