@@ -1,10 +1,14 @@
 """pangu_pytorch_b200 -- B200-native (sm_100a) implementation of the Pangu-Weather
-forward hot path behind the module API of zhaoshan2/pangu-pytorch.
+forward / backward hot path behind the module API of zhaoshan2/pangu-pytorch.
 
     from pangu_pytorch_b200 import PanguModel
     model = PanguModel(device="cuda").to("cuda").eval()
     model.load_state_dict(torch.load("pangu_weather_24_torch.pth")["model"])
     out_upper, out_surface = model(upper, surface, statistics, maps, const_h)
+
+Training (``model.train()``; the backward is hand-written kernels, see ``training``), data-parallel gradient
+mean (``dist``), LoRA (``lora``), autoregressive rollout and CUDA-graph replay (``rollout``), ensemble sharding
+(``ensemble``) and on-device evaluation scores (``ops.scores``) live in the sub-modules of the same names.
 
 ``install_reference_aliases()`` registers ``models.layers`` / ``models.pangu_model`` in
 ``sys.modules`` so that whole-module pickles written by the reference
