@@ -234,3 +234,36 @@ def test_full_025_forward_against_reference_golden(fmt, kind):
     print(f"0.25deg forward {fmt} {kind}: sampled rel-L2 upper {eu:.3e} surface {es:.3e}; norm ratios {vu} {vs}")
     assert eu < TOL_MODEL[fmt] and es < TOL_MODEL[fmt]
     assert np.all(np.abs(vu - 1) < TOL_MODEL[fmt]) and np.all(np.abs(vs - 1) < TOL_MODEL[fmt])
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+@pytest.mark.parametrize("roll_out", [-1, 0, 1])
+def test_mlp_single_kernel_matches_two_kernel_path(fmt, roll_out):
+    """pangu_mlp_ln_residual at C=192: the single-kernel path (no hidden-activation workspace; GELU output kept on the
+    SM) against the two-GEMM path (hidden activation through HBM) on the same operands -- same fp32 accumulation, same
+    16-bit rounding of the hidden activation, so only the summation order inside GEMM2 differs."""
+    from pangu_pytorch_b200 import engine, ops
+    fp16 = _fmt(fmt)
+    Z, H, W, C = 8, 181, 24, 192
+    ws = engine.workspace(DEV, Z, H, W, C)
+    g = torch.Generator().manual_seed(21 + roll_out)
+    h16 = ops.dtype16(fp16)
+    x16 = _round16(torch.randn(ws.T, C, generator=g), fp16).to(DEV)
+    x32 = torch.randn(ws.T, C, generator=g).to(DEV)
+    w1 = _round16(torch.randn(4 * C, C, generator=g) * 0.08, fp16).to(DEV)
+    w2 = _round16(torch.randn(C, 4 * C, generator=g) * 0.05, fp16).to(DEV)
+    b1, b2 = torch.randn(4 * C, generator=g).to(DEV) * 0.1, torch.randn(C, generator=g).to(DEV) * 0.1
+    gam, bet = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV), torch.randn(C, generator=g).to(DEV) * 0.1
+    outs = []
+    for hidden in (torch.empty(ws.T, 4 * C, dtype=h16, device=DEV), None):
+        xs = x32.clone()
+        rows = ws.Tp if roll_out >= 0 else ws.T
+        o16 = torch.zeros(rows, C, dtype=h16, device=DEV)
+        ops.mlp_ln_residual(x16, w1, b1, w2, b2, gam, bet, hidden, xs, o16, Z, H, W, C, roll_out, 0.9, fp16)
+        outs.append((xs, o16))
+    torch.cuda.synchronize()
+    (xa, oa), (xb, ob) = outs
+    assert torch.isfinite(xb).all()
+    assert rel_l2(xb, xa) < 2e-5
+    assert rel_l2(ob.float(), oa.float()) < (1e-3 if fp16 else 6e-3)
+    assert torch.equal(ob == 0, oa == 0)                     # same rows written (window scatter / pad rows untouched)
