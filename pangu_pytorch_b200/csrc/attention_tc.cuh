@@ -16,8 +16,8 @@
 // Per window:
 //
 //   S[128x144] = Q[0:128] K^T          tcgen05.mma, A/B from smem (K-major), fp32 accum in TMEM
-//   pass 1:  y = S*log2e + bias'       written back over S (TMEM), row maximum m
-//   pass 2:  P = exp2(y - m)           packed 16-bit, written over the first 72 columns of y
+//   y = S*log2e + bias'                72 keys per thread (two threads per query row), held in REGISTERS
+//   P = exp2(y - m)                    packed 16-bit, written over the first 72 columns of S (one TMEM store pass)
 //   O[128x32]  = P V                   tcgen05.mma, A = P from TMEM, B = V from smem (MN-major)
 //   rows 128..143 (144 = 128 + 16 does not fit an MMA M) are done by mma.sync "tail" warps that
 //   read the same smem tiles (the SWIZZLE_64B pattern equals the ldmatrix-friendly XOR swizzle).
@@ -25,12 +25,15 @@
 // qkv is stored head-major by the QKV GEMM ([3*heads planes][Tp_pad rows][32]), so every Q/K/V tile is
 // one contiguous 9 KB burst in HBM.
 // TMEM (512 columns = the whole SM, so the allocation starts at address 0):
-//   [0,144) bias' | [144,288) S0/P0 | [288,432) S1/P1 | [432,464) O0 | [464,496) O1.
+//   [0,144) bias' | [144,288) S0/P0 | [288,432) S1/P1 | [432,464) O0 | [464,496) O1 | [496,500) row sums l (buffer, half).
 // S of window g+2 is queued right behind PV of window g (the tensor pipe executes in issue order, so PV
 // has read P before the next S overwrites it).  The MMA warp runs converged with warp-uniform operands
 // (only the tcgen05 instructions are elected) and polls "next S" / "next PV" without blocking on either.
 // Warps (512 threads): 0 TMA producer, 1 MMA issuer, 2-7 tail warps (ring stage s belongs to warp 2 + s%6),
-// 8-15 softmax: two warpgroups alternate windows; thread = one full query row (TMEM lane).
+// 8-15 softmax: all eight on every window; thread = (query row = TMEM lane, half of the 144 keys), warps w and w+4 pair up.
+// Round 1 kept one full row per thread and wrote y back to TMEM between the max and the exp pass: 27 dependent TMEM round
+// trips per window (ncu: tensor pipe 12 %, long-scoreboard stalls on the TMEM waits).  With 72 keys per thread the row fits
+// the 128-register budget of a 512-thread CTA and the window needs 3 TMEM load waits and one store wait.
 #pragma once
 #include "attention.cuh"
 
@@ -43,8 +46,9 @@ constexpr int ATC_TAIL_WARPS = 6;                                // warps 2..7: 
 constexpr int ATC_STAGE_BYTES = ATT_BUF_BYTES;                   // 27648: Q, K, V tiles (or 3 bias boxes) of 9216 B
 constexpr int ATC_TB_PITCH = 148;                                // floats per row of the tail bias tile in smem
 constexpr int ATC_TB_BYTES = 16 * ATC_TB_PITCH * 4;              // rows 128..143
-constexpr int ATC_SMEM_BYTES = 1024 + ATC_STAGES * ATC_STAGE_BYTES + ATC_TB_BYTES + 512;
-constexpr uint32_t ATC_COL_BIAS = 0, ATC_COL_S = 144, ATC_COL_O = 432;
+constexpr int ATC_XM_BYTES = 2 * 128 * 2 * 2;                    // row-maximum mailbox: [S buffer][row][key half] bf16
+constexpr int ATC_SMEM_BYTES = ATC_STAGES * ATC_STAGE_BYTES + ATC_TB_BYTES + ATC_XM_BYTES + 256;   // base is 1024 B aligned (checked)
+constexpr uint32_t ATC_COL_BIAS = 0, ATC_COL_S = 144, ATC_COL_O = 432, ATC_COL_L = 496;
 static_assert(ATC_SMEM_BYTES <= 232448, "attention shared memory budget");
 static_assert(3 * ATC_STAGE_BYTES == ATT_TOK * ATT_TOK * 4, "a bias tile is exactly three ring slots");
 
@@ -83,24 +87,65 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// pointer forms: r must index registers after full unrolling (constant offsets into a local array)
+__device__ __forceinline__ void tmem_st32p(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st4p(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8p(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&r)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <bool kFp16>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmBias,
                            const AttnArgs a) {
-  extern __shared__ uint8_t atc_raw[];
-  uint8_t* smem = atc_raw + ((1024u - (smem_u32(atc_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t atc_raw[];
+  if ((smem_u32(atc_raw) & 1023u) != 0u) __trap();   // the swizzled tiles need 1024 B alignment and there is no slack to fix it up
+  uint8_t* smem = atc_raw;
   uint8_t* ring = smem;
   float* s_tbias = reinterpret_cast<float*>(smem + ATC_STAGES * ATC_STAGE_BYTES);     // [16][ATC_TB_PITCH]
-  uint8_t* misc = smem + ATC_STAGES * ATC_STAGE_BYTES + ATC_TB_BYTES;
+  uint16_t* s_xm = reinterpret_cast<uint16_t*>(smem + ATC_STAGES * ATC_STAGE_BYTES + ATC_TB_BYTES);   // [2][128][2]
+  uint8_t* misc = smem + ATC_STAGES * ATC_STAGE_BYTES + ATC_TB_BYTES + ATC_XM_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);      // [ATC_STAGES]  TMA bytes landed
   uint64_t* empty_bar = full_bar + ATC_STAGES;                 // [ATC_STAGES]  count 2 (window: PV commit + tail warp;
                                                                //                        bias: softmax group + tail group)
   uint64_t* sfull_bar = empty_bar + ATC_STAGES;                // [2]  S ready in TMEM
-  uint64_t* pfull_bar = sfull_bar + 2;                         // [2]  P written (128 threads of the owning warpgroup)
+  uint64_t* pfull_bar = sfull_bar + 2;                         // [2]  P written (the 256 softmax threads)
   uint64_t* ofull_bar = pfull_bar + 2;                         // [2]  O ready
-  uint64_t* oempty_bar = ofull_bar + 2;                        // [2]  O read out (128 threads of the owning warpgroup)
+  uint64_t* oempty_bar = ofull_bar + 2;                        // [2]  O read out (the 256 softmax threads)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -110,8 +155,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
     tma_prefetch_desc(&tmBias);
     for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&sfull_bar[b], 1); mbar_init(&pfull_bar[b], 128);
-      mbar_init(&ofull_bar[b], 1); mbar_init(&oempty_bar[b], 128);
+      mbar_init(&sfull_bar[b], 1); mbar_init(&pfull_bar[b], 256);
+      mbar_init(&ofull_bar[b], 1); mbar_init(&oempty_bar[b], 256);
     }
     fence_barrier_init();
   }
@@ -130,11 +175,11 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   const int u_end = int(total * (blockIdx.x + 1) / gridDim.x);
   const int nunits = u_end - u_begin;
   const int lw_first = u_begin % a.nLon;
+#ifdef PANGU_ATTN_TRACE     // development builds only: per-role clock64 timeline of CTA 5 ([role 8][window 64][event 4])
   const bool tracing = a.trace != nullptr && blockIdx.x == 5;
-#ifdef ATC_DEBUG_PRINT
-  auto TR = [&](int role, int g, int ev) { if (blockIdx.x == 5 && g < 4) printf("TR role %d g %d ev %d thr %d\n", role, g, ev, (int)threadIdx.x); };
+  auto TR = [&](int role, int g, int ev, bool who) { if (tracing && who && g < 64) a.trace[(role * 64 + g) * 4 + ev] = clock64(); };
 #else
-  auto TR = [&](int role, int g, int ev) { if (tracing && g < 64) a.trace[(role * 64 + g) * 4 + ev] = clock64(); };
+  auto TR = [](int, int, int, bool) {};
 #endif
   constexpr float kLog2e = 1.4426950408889634f;
 
@@ -159,7 +204,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         for (int i = 0; i < nwin; ++i, ++q) {
           const int st = q % ATC_STAGES;
           mbar_wait(&empty_bar[st], ((q / ATC_STAGES) & 1) ^ 1);
-          TR(0, u - u_begin + i, 0);
+          TR(0, u - u_begin + i, 0, true);
           uint8_t* dst = ring + st * ATC_STAGE_BYTES;
           const int row0 = ((lw + i) * a.types + t) * ATT_TOK;
           mbar_arrive_expect_tx(&full_bar[st], ATC_STAGE_BYTES);
@@ -200,7 +245,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
       } else if (cs.g < nunits && cs.g < cp.g + 2) {  // buffer cs.g & 1 is free: PV of window cs.g - 2 has been issued
         const int st = cs.q % ATC_STAGES, b = cs.g & 1;
         if (__any_sync(0xffffffffu, mbar_test_wait(&full_bar[st], (cs.q / ATC_STAGES) & 1))) {
-          TR(1, cs.g, 0);
+          TR(1, cs.g, 0, lane == 0);
           tc_fence_after();
           const uint32_t sq = ring_u32 + st * ATC_STAGE_BYTES;
           const uint64_t dq = make_sdesc_sw64(sq), dk = make_sdesc_sw64(sq + ATT_TILE_BYTES);
@@ -219,7 +264,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         const int st = cp.q % ATC_STAGES, b = cp.g & 1;
         if (__any_sync(0xffffffffu, mbar_test_wait(&pfull_bar[b], (cp.g >> 1) & 1))) {
           mbar_wait(&oempty_bar[b], ((cp.g >> 1) & 1) ^ 1);   // already true: the owner reads O(g-2) before it writes P(g)
-          TR(1, cp.g, 2);
+          TR(1, cp.g, 2, lane == 0);
           tc_fence_after();
           const uint64_t dv = make_sdesc_sw64(ring_u32 + st * ATC_STAGE_BYTES + 2 * ATT_TILE_BYTES);
           if (elect_one()) {
@@ -230,7 +275,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             umma_commit(&empty_bar[st]);
           }
           __syncwarp();
-          TR(1, cp.g, 3);
+          TR(1, cp.g, 3, lane == 0);
           advance(cp, false);
           progress = true;
         }
@@ -302,7 +347,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           if (st % ATC_TAIL_WARPS != warp - 2) continue;
           mbar_wait(&full_bar[st], (q / ATC_STAGES) & 1);
           uint8_t* tile = ring + st * ATC_STAGE_BYTES;
-          if (lane == 0) TR(2, g, 0);
+          TR(2, g, 0, lane == 0);
           const uint32_t sq = smem_u32(tile), sk = sq + ATT_TILE_BYTES, sv = sk + ATT_TILE_BYTES;
           uint32_t qa[2][4];
           {
@@ -380,25 +425,29 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             }
           }
           __syncwarp();
-          if (lane == 0) { TR(2, g, 1); mbar_arrive(&empty_bar[st]); }
+          TR(2, g, 1, lane == 0);
+          if (lane == 0) mbar_arrive(&empty_bar[st]);
         }
       } else {
-        // ============================== softmax + O epilogue (2 warpgroups) ==============================
-        // Warpgroup wg owns the windows with g % 2 == wg and the S/P/O buffers b = wg; a thread owns one
-        // full query row (TMEM lane).
-        const int quad = warp & 3, wg = (warp - 8) >> 2;
+        // ============================== softmax + O epilogue (8 warps on every window) ==============================
+        // Warps w and w + 4 share TMEM lane quadrant `quad`; a thread owns one query row (TMEM lane) and one HALF of
+        // its 144 keys: the 72 scores are loaded once and stay in registers from the bias add to the packed P store
+        // (no TMEM write-back of y).  The two halves of a row meet twice: the row maximum goes through a 16-bit
+        // mailbox in shared memory (any common stabiliser >= max - small is exact for softmax; bf16 rounding keeps
+        // p <= 2^(|m| 2^-8)), the row sum through two spare TMEM columns read back with the output accumulator.
+        const int quad = warp & 3, half = (warp - 8) >> 2;
         const int r = quad * 32 + lane;
         const uint32_t lane_addr = tmem + (uint32_t(quad * 32) << 16);
-        const uint32_t bias_addr = lane_addr + ATC_COL_BIAS;
-        const uint32_t s_addr = lane_addr + ATC_COL_S + 144 * wg;
+        const uint32_t bias_addr = lane_addr + ATC_COL_BIAS + 72 * half;
+        const int pair_bar = 3 + quad;           // named barrier of the two warps that share this lane quadrant
 
-        // ---- segment start: bias tile -> TMEM (this warpgroup moves boxes wg, wg+2, ... of its rows)
-        if (threadIdx.x == 256) TR(6, seg, 0);
-        named_bar_sync(1, 256);                  // both warpgroups have finished pass 1 of the previous segment
+        // ---- segment start: bias tile -> TMEM (each half moves boxes half, half+2, ... of its rows)
+        TR(6, seg, 0, threadIdx.x == 256);
+        named_bar_sync(1, 256);                  // every softmax thread has finished the bias reads of the previous segment
 #pragma unroll
         for (int j = 0; j < 3; ++j) mbar_wait(&full_bar[(qb + j) % ATC_STAGES], ((qb + j) / ATC_STAGES) & 1);
 #pragma unroll 1
-        for (int p = wg; p < 9; p += 2) {
+        for (int p = half; p < 9; p += 2) {
           const uint8_t* box = box_ptr(p);
           uint32_t v[16];
 #pragma unroll
@@ -408,32 +457,32 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             v[4 * c + 0] = __float_as_uint((f.x + m) * kLog2e); v[4 * c + 1] = __float_as_uint((f.y + m) * kLog2e);
             v[4 * c + 2] = __float_as_uint((f.z + m) * kLog2e); v[4 * c + 3] = __float_as_uint((f.w + m) * kLog2e);
           }
-          tmem_st16(bias_addr + 16 * p, v);
+          tmem_st16(lane_addr + ATC_COL_BIAS + 16 * p, v);
         }
         tmem_st_wait();
         tc_fence_before();
-        named_bar_sync(1, 256);                  // the other warpgroup's boxes of every bias row are in TMEM too
+        named_bar_sync(1, 256);                  // the other half's boxes of every bias row are in TMEM too
         tc_fence_after();
         if (threadIdx.x >= 256 && threadIdx.x < 259) mbar_arrive(&empty_bar[(qb + threadIdx.x - 256) % ATC_STAGES]);
-        if (threadIdx.x == 256) TR(6, seg, 1);
+        TR(6, seg, 1, threadIdx.x == 256);
 
         const int my_base = row_base(r);
-        float l_prev = 1.f;
-        auto epilogue = [&](int j, float l) {      // j: window index inside the segment
-          const int g = gbase + j;
-          mbar_wait(&ofull_bar[wg], (g >> 1) & 1);
+        auto epilogue = [&](int j) {               // j: window index inside the segment; this thread stores 16 of the 32 channels
+          const int g = gbase + j, b = g & 1;
+          mbar_wait(&ofull_bar[b], (g >> 1) & 1);
           tc_fence_after();
-          uint32_t o[32];
-          tmem_ld32(lane_addr + ATC_COL_O + 32 * wg, o);
+          uint32_t o[16], ls[2];
+          tmem_ld16(lane_addr + ATC_COL_O + 32 * b + 16 * half, o);
+          tmem_ld2(lane_addr + ATC_COL_L + 2 * b, ls);
           tmem_ld_wait();
           tc_fence_before();
-          mbar_arrive(&oempty_bar[wg]);
+          mbar_arrive(&oempty_bar[b]);
           const int orow = out_row(my_base, r, lw0 + j);
           if (orow < 0) return;                   // zero pad row of the window: its output is cropped away
-          const float inv = 1.0f / l;
-          uint8_t* dst = reinterpret_cast<uint8_t*>(a.out) + size_t(orow) * (size_t(a.C) * 2) + head * 64;
+          const float inv = 1.0f / (__uint_as_float(ls[0]) + __uint_as_float(ls[1]));
+          uint8_t* dst = reinterpret_cast<uint8_t*>(a.out) + size_t(orow) * (size_t(a.C) * 2) + head * 64 + 32 * half;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 2; ++q) {
             uint4 v;
             v.x = pack16<kFp16>(__uint_as_float(o[8 * q + 0]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
             v.y = pack16<kFp16>(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
@@ -442,85 +491,85 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             stg16(dst + 16 * q, v);
           }
         };
-        int last = -1;
-        for (int i = (wg - gbase % 2 + 2) % 2; i < nwin; i += 2) {
-          const int g = gbase + i;
-          if (r == 0) TR(3, g, 0);
-          // ---- output of this warpgroup's previous window: its PV is queued right ahead of this window's S
-          if (last >= 0) epilogue(last, l_prev);
-          if (r == 0) TR(3, g, 3);
-          mbar_wait(&sfull_bar[wg], (g >> 1) & 1);
-          if (r == 0) TR(3, g, 1);
+        const f32x2 l2e2 = pack2(kLog2e, kLog2e);
+#pragma unroll 1
+        for (int i = 0; i < nwin; ++i) {
+          const int g = gbase + i, b = g & 1;
+          const uint32_t s_addr = lane_addr + ATC_COL_S + 144 * b + 72 * half;
+          TR(3, g, 0, r == 0 && half == 0);
+          mbar_wait(&sfull_bar[b], (g >> 1) & 1);
+          TR(3, g, 1, r == 0 && half == 0);
           tc_fence_after();
-          // ---- pass 1: y = S*log2e + bias' (written back over S) and its row maximum.  TMEM loads are
-          //      software pipelined: piece p+1 is in flight while piece p is processed.
+          // ---- y = S*log2e + bias' for this thread's 72 keys, kept in registers; bias' streams through two 16-column
+          //      buffers (3 TMEM waits per window instead of 27 dependent round trips)
+          uint32_t y[72], bb[2][16];
+          tmem_ld32p(s_addr, y);
+          tmem_ld32p(s_addr + 32, y + 32);
+          tmem_ld8p(s_addr + 64, y + 64);
+          tmem_ld16(bias_addr, bb[0]);
+          tmem_ld16(bias_addr + 16, bb[1]);
+          tmem_ld_wait();
           float pm = -INFINITY;
-          {
-            const f32x2 l2e2 = pack2(kLog2e, kLog2e);
-            uint32_t sa[2][16], ba[2][16];
-            tmem_ld16(s_addr, sa[0]);
-            tmem_ld16(bias_addr, ba[0]);
-            tmem_ld_wait();
+          auto addbias = [&](int c0, const uint32_t* bsrc, int n) {
 #pragma unroll
-            for (int part = 0; part < 9; ++part) {
-              const int cur = part & 1;
-              if (part + 1 < 9) {
-                tmem_ld16(s_addr + 16 * (part + 1), sa[cur ^ 1]);
-                tmem_ld16(bias_addr + 16 * (part + 1), ba[cur ^ 1]);
-              }
-              uint32_t y[16];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float a0, a1;
-                unpack2(fma2(pack2(__uint_as_float(sa[cur][2 * e]), __uint_as_float(sa[cur][2 * e + 1])), l2e2,
-                             pack2(__uint_as_float(ba[cur][2 * e]), __uint_as_float(ba[cur][2 * e + 1]))), a0, a1);
-                pm = max3(pm, a0, a1);
-                y[2 * e] = __float_as_uint(a0); y[2 * e + 1] = __float_as_uint(a1);
-              }
-              tmem_ld_wait();        // piece p+1 is in registers
-              tmem_st16(s_addr + 16 * part, y);
+            for (int e = 0; e < 8; ++e) {
+              if (2 * e >= n) break;
+              float a0, a1;
+              unpack2(fma2(pack2(__uint_as_float(y[c0 + 2 * e]), __uint_as_float(y[c0 + 2 * e + 1])), l2e2,
+                           pack2(__uint_as_float(bsrc[2 * e]), __uint_as_float(bsrc[2 * e + 1]))), a0, a1);
+              pm = max3(pm, a0, a1);
+              y[c0 + 2 * e] = __float_as_uint(a0); y[c0 + 2 * e + 1] = __float_as_uint(a1);
             }
+          };
+          addbias(0, bb[0], 16);
+          tmem_ld16(bias_addr + 32, bb[0]);
+          addbias(16, bb[1], 16);
+          tmem_ld16(bias_addr + 48, bb[1]);
+          tmem_ld_wait();
+          addbias(32, bb[0], 16);
+          tmem_ld8p(bias_addr + 64, bb[0]);
+          addbias(48, bb[1], 16);
+          tmem_ld_wait();
+          addbias(64, bb[0], 8);
+          TR(3, g, 2, r == 0 && half == 0);
+          // ---- row maximum: meet the other half of the row
+          {
+            const uint16_t m16 = __bfloat16_as_ushort(__float2bfloat16_rn(pm));
+            s_xm[(b * 128 + r) * 2 + half] = m16;
+            named_bar_sync(pair_bar, 64);
+            const uint32_t both = *reinterpret_cast<const uint32_t*>(&s_xm[(b * 128 + r) * 2]);
+            pm = fmaxf(__uint_as_float(both << 16), __uint_as_float(both & 0xFFFF0000u));
           }
-          if (r == 0) TR(3, g, 2);
-          // ---- pass 2: P = exp2(y - max), packed 16-bit, written over the first 72 columns of y
+          // ---- P = exp2(y - m), packed 16-bit, into columns [36*half, +36) of this window's S buffer.  The partner
+          //      loaded its scores (which these columns may overlap) before it arrived at the pair barrier above.
           const f32x2 negm2 = pack2(-pm, -pm);
           f32x2 lsum = pack2(0.f, 0.f);
-          tmem_st_wait();            // this thread's y stores have landed
-          {
-            uint32_t sa[2][16];
-            tmem_ld16(s_addr, sa[0]);
-            tmem_ld_wait();
+          uint32_t pk[36];
 #pragma unroll
-            for (int part = 0; part < 9; ++part) {
-              const int cur = part & 1;
-              uint32_t pk[8];
-              if (part + 1 < 9) tmem_ld16(s_addr + 16 * (part + 1), sa[cur ^ 1]);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float a0, a1;
-                unpack2(add2(pack2(__uint_as_float(sa[cur][2 * e]), __uint_as_float(sa[cur][2 * e + 1])), negm2), a0, a1);
-                const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
-                lsum = add2(lsum, pack2(p0, p1));
-                pk[e] = pack16<kFp16>(p0, p1);
-              }
-              tmem_ld_wait();   // piece p+1 has landed: y columns [16(p+1), +16) are in registers before ...
-              // ... P columns [8p, +8) overwrite y columns that this thread has already consumed (8p+8 <= 16(p+1))
-              tmem_st8(s_addr + 8 * part, pk);
-            }
+          for (int e = 0; e < 36; ++e) {
+            float a0, a1;
+            unpack2(add2(pack2(__uint_as_float(y[2 * e]), __uint_as_float(y[2 * e + 1])), negm2), a0, a1);
+            const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+            lsum = add2(lsum, pack2(p0, p1));
+            pk[e] = pack16<kFp16>(p0, p1);
           }
+          const uint32_t p_addr = lane_addr + ATC_COL_S + 144 * b + 36 * half;
+          tmem_st32p(p_addr, pk);
+          tmem_st4p(p_addr + 32, pk + 32);
           {
             float a0, a1;
             unpack2(lsum, a0, a1);
-            l_prev = a0 + a1;
+            tmem_st1(lane_addr + ATC_COL_L + 2 * b + half, __float_as_uint(a0 + a1));
           }
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&pfull_bar[wg]);
-          if (r == 0) TR(4, g, 0);
-          last = i;
+          mbar_arrive(&pfull_bar[b]);
+          TR(4, g, 0, r == 0 && half == 0);
+          // ---- output of the previous window: its PV was queued one window ago
+          if (i > 0) epilogue(i - 1);
         }
-        if (last >= 0) epilogue(last, l_prev);
-        if (threadIdx.x == 256) TR(6, seg, 2);
+        epilogue(nwin - 1);
+        TR(6, seg, 2, threadIdx.x == 256);
       }
       gbase += nwin;
       u += nwin;

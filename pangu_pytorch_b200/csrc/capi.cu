@@ -338,7 +338,9 @@ static EpiArgs epi_defaults() {
   e.Z = 8; e.H = 1; e.W = 12;
   e.res_scale = 1.f; e.q_scale = 1.f; e.eps = 1e-5f;
   e.rowmap = RM_IDENT; e.dstmap = DM_IDENT;
+#ifdef PANGU_DEV_SWITCHES     // development builds only (-DPANGU_DEV_SWITCHES): timing ablations, results invalid
   if (const char* d = getenv("PANGU_B200_GEMM_DEBUG")) e.debug = atoi(d);
+#endif
   return e;
 }
 
@@ -443,7 +445,9 @@ extern "C" int pangu_window_attention(const void* qkv16, const float* earth_bias
   a.lon_per_cta = g.nLon;
   a.debug = 0;
   a.trace = nullptr;
+#ifdef PANGU_ATTN_TRACE       // development builds only (-DPANGU_ATTN_TRACE): device pointer of a clock64 timeline buffer
   if (const char* e = getenv("PANGU_B200_ATTN_TRACE")) a.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+#endif
   const int Tp = g.nLon * g.types * 144;
   a.plane_rows = sh_rows_padded(Tp);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -544,7 +548,10 @@ extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, cons
     a.Z = Z; a.H = H; a.W = W;
     a.roll_out = roll_out < 0 ? -1 : (roll_out > 0 ? 1 : 0);
     a.res_scale = res_scale; a.eps = 1e-5f;
-    a.debug = getenv("PANGU_B200_GEMM_DEBUG") ? atoi(getenv("PANGU_B200_GEMM_DEBUG")) : 0;
+    a.debug = 0;
+#ifdef PANGU_DEV_SWITCHES
+    if (const char* d = getenv("PANGU_B200_GEMM_DEBUG")) a.debug = atoi(d);
+#endif
     return fp16 ? launch_mlp_fused_t<192, true>(x16_in, w1_16, w2_16, a, s) : launch_mlp_fused_t<192, false>(x16_in, w1_16, w2_16, a, s);
   }
   {
