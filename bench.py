@@ -8,12 +8,16 @@ synthetic 0.25 degree sample (upper 5x13x721x1440, surface 4x721x1440), batch 1,
 weights of the reference architecture.  N > 1 (launched by torch.distributed.run) shards
 independent ensemble members over the GPUs of one box: no data-path collective, weak scaling.
 
-One JSON line is printed by rank 0 (see the keys below).  ``value`` is device-resident
-throughput; ``e2e`` is the same metric through the public ``PanguModel.forward`` with the
-step's input fields in pinned host memory (H2D inside the timed region) and the forecast
-fields copied back (D2H); copies are double-buffered on side streams.
-``--impl reference`` times the CPU oracle port of the reference forward (the Python reference
-itself cannot travel to the GPU box) on all host cores, each step a bounded sample.
+One JSON line is printed by rank 0.  ``value`` is device-resident throughput.  ``e2e`` is the same metric through the
+public ``PanguModel.forward`` with every step's input fields copied from pinned host memory inside the timed region
+(H2D 287 MB per step) and the step's result -- the 69 RMSE + 69 ACC scores of the forecast, computed on the device --
+read back to the host; ``e2e_fields`` reads both fp32 forecast fields back instead (287 MB per step, the round-1
+definition) and ``e2e_ensemble`` uploads one base state per 8 members and perturbs on the device (configs[2]).
+``other_operands`` is the device-resident figure with the other 16-bit operand format, ``secondary`` holds short
+finetune_fully / lora_tune steps (configs[3], configs[4]; data parallel over the same ranks when N > 1).
+``roofline.traffic`` is looked up in profiles/traffic.json (written from committed ncu captures), never hard-coded.
+``cpu_baseline`` / ``--impl reference`` time the UNMODIFIED reference forward (oracle/_ref, staged by
+oracle/build_ref.py) on the host cores at the full 721 x 1440 grid; every CPU step is a complete forward.
 """
 from __future__ import annotations
 
@@ -33,17 +37,11 @@ UNIT = "steps/s"
 FLOPS_PER_STEP = 8.4212e12          # dense-contraction FLOPs of one forward
 FLOPS_BLOCKS = 8.1325e12            # attention + MLP of the 16 blocks
 LAT, LON = 721, 1440
-STRIP = 96                          # CPU sample: full-depth forward on a 96-column strip (1/15 of the grid)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels behind each entry point, from the committed
-# `ncu --set full` captures (profiles/r01c_*.md; an entry point = the sum of its kernels)
-NCU_TRAFFIC_BYTES = {
-    "pangu_mlp_ln_residual[lo]": (102.0e6 + 352.3e6) + (628.9e6 + 246.0e6),     # CfgMLP1 + CfgLNRes384
-    "pangu_mlp_ln_residual[hi]": None,
-    "pangu_window_attention[lo]": 405.9e6 + 92.6e6,
-    "pangu_qkv[lo]": 107.1e6 + 270.3e6,
-}
-
-
+TRAIN_OPERANDS = "bf16"             # operand format of the secondary finetune / lora steps
+LORA_DROPOUT = 0.0                  # lora_tune's adapter dropout in the secondary record
+STRIP = 96                          # fallback CPU sample (only if oracle/_ref is absent): 96-column strip, 1/15 of the grid
+WORKLOAD = ("PanguModel 24h forward, 0.25deg (upper 5x13x721x1440, surface 4x721x1440), batch 1, random-init weights; "
+            "one ensemble member per step per GPU")
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -56,9 +54,14 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: oracle port of the reference forward on a bounded sample
+# CPU arm.  Preferred: the UNMODIFIED reference forward (oracle/_ref, staged by oracle/build_ref.py) at the full
+# 721 x 1440 grid -- the quoted config, nothing extrapolated.  Only if the staged reference is absent: the oracle
+# port on a 96-column strip x 15 (kind "port"), as in round 1.
 # ----------------------------------------------------------------------------------------------
-def cpu_sample_setup():
+REF_ARM_BUDGET_S = 420.0            # --impl reference stops timing new steps after this long (CPU forward: 15-60 s each)
+
+
+def _port_setup():
     import torch
     from oracle import pangu_oracle as O
     try:                                  # the GPU arm may have pinned this process next to its GPU: the CPU leg gets every core
@@ -68,50 +71,57 @@ def cpu_sample_setup():
     torch.set_num_threads(os.cpu_count() or 1)
     p = O.reference_like_weights(seed=0)
     inputs = O.synthetic_inputs(seed=1, lat=LAT, lon=STRIP)
-    return O, p, inputs
+
+    def step():
+        t0 = time.perf_counter()
+        O.forward(p, *inputs)
+        return (time.perf_counter() - t0) * (LON // STRIP)
+    return step, torch.get_num_threads()
 
 
-def cpu_sample_time(O, p, inputs) -> float:
-    t0 = time.perf_counter()
-    O.forward(p, *inputs)
-    return time.perf_counter() - t0
+def cpu_arm():
+    """-> (step() -> seconds per FULL forward, threads, kind, description of one step)."""
+    from oracle import ref_runner
+    if ref_runner.available():
+        r = ref_runner.ReferenceForward()
+        return (r.step, r.threads, "reference",
+                "one full fp32 forward of the unmodified reference PanguModel (oracle/_ref = models/layers.py + "
+                "models/pangu_model.py, eval, no_grad) on the 721x1440 grid")
+    step, threads = _port_setup()
+    return (step, threads, "port",
+            f"oracle/_ref not staged: full-depth fp32 forward of the oracle port on a {STRIP}-column strip, scaled x{LON // STRIP}")
 
 
-def cpu_baseline(reps: int = 2) -> dict:
-    import torch
-    O, p, inputs = cpu_sample_setup()
-    cpu_sample_time(O, p, inputs)                      # warm-up
-    ts = sorted(cpu_sample_time(O, p, inputs) for _ in range(reps))
-    t = ts[len(ts) // 2]
-    scale = LON // STRIP
-    return {"value": 1.0 / (t * scale), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"full-depth fp32 forward (oracle port of models/pangu_model.py:50-87) on a {STRIP}-column "
-                      f"longitude strip = 1/{scale} of the 0.25deg grid, {t:.2f}s per sample, scaled x{scale}"}
+def cpu_baseline() -> dict:
+    """Reported next to the GPU number (rank 0, N = 1): ONE timed full forward, no warm-up (the forward is 15-60 s of
+    dense CPU work; allocator / thread-pool start-up is < 1 % of that)."""
+    step, threads, kind, what = cpu_arm()
+    t = step()
+    return {"value": 1.0 / t, "unit": UNIT, "cores": threads, "kind": kind, "sample": f"{what}; {t:.1f} s"}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    O, p, inputs = cpu_sample_setup()
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_sample_time(O, p, inputs)
-    steps = max(1, args.steps)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_sample_time(O, p, inputs)
-    dt = (time.perf_counter() - t0) / steps
-    scale = LON // STRIP
-    value = 1.0 / (dt * scale)
+    step, threads, kind, what = cpu_arm()
+    warm = min(args.warmup, 1)               # one warm-up forward at most: every CPU step is tens of seconds
+    for _ in range(warm):
+        step()
+    want = max(1, args.steps)
+    ts = []
+    t_start = time.perf_counter()
+    while len(ts) < want and (not ts or time.perf_counter() - t_start < REF_ARM_BUDGET_S):
+        ts.append(step())
+    dt = sum(ts) / len(ts)
+    value = 1.0 / dt
+    note = (f"{what}; {len(ts)} timed step(s) of {want} requested ({warm} warm-up): the arm stops starting new steps after "
+            f"{REF_ARM_BUDGET_S:.0f} s so that the run ends within minutes; every step timed is a complete forward")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True,
+            "steps": len(ts), "steps_requested": want, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "PanguModel 24h forward, 0.25deg (721x1440x13 levels), batch 1, random-init weights",
-                       "note": "CPU oracle port of the reference forward; each step is a bounded sample"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{STRIP}-column longitude strip (1/{scale} of the grid), full depth, "
-                                       f"{dt:.2f}s per sample, scaled x{scale}"},
+            "config": {"workload": WORKLOAD, "note": note},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": note},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -239,24 +249,37 @@ def run_gpu_arm(args):
         clocks = sampler.stop(t0, t1) if sampler else None
         kern = prof.summary()
 
-        # ---- timed region 2: end to end through the public API, host buffers, pipelined copies
+        # ---- timed region 2: end to end through the public API.  Every step copies that step's input fields from
+        # pinned host memory (H2D, 287 MB) and reads the step's result back to pinned host memory; copies are
+        # double-buffered on side streams.  Three variants (same kernels, same forward):
+        #   metric   (headline `e2e`): result = the 69 latitude-weighted RMSE + 69 ACC values of the forecast against a
+        #            resident verification field (on-device pangu_scores, what the reference's test() computes after every
+        #            forward: models/pangu_sample.py:236-270); D2H = 552 B
+        #   fields   (`e2e_fields`): result = both fp32 forecast fields (D2H = 287 MB), as in round 1
+        #   ensemble (`e2e_ensemble`): BASELINE.json configs[2]: the base state is uploaded once per 8 members and the
+        #            perturbations are drawn on the device (ensemble.perturb); result = scores per member
+        from pangu_pytorch_b200 import ensemble as ens
         host_in = [(torch.empty(1, 5, 13, LAT, LON).pin_memory(), torch.empty(1, 4, LAT, LON).pin_memory())
                    for _ in range(2)]
         for (hu, hs), (du, ds) in zip(host_in, members):
             hu.copy_(du); hs.copy_(ds)
         host_out = [(torch.empty(1, 5, 13, LAT, LON).pin_memory(), torch.empty(1, 4, LAT, LON).pin_memory())
                     for _ in range(2)]
+        host_sc = [torch.empty(2, 69).pin_memory() for _ in range(2)]
         dev_in = [(torch.empty_like(members[0][0]), torch.empty_like(members[0][1])) for _ in range(2)]
+        gt = torch.Generator(device=dev).manual_seed(7)
+        tgt = (torch.randn(1, 5, 13, LAT, LON, device=dev, generator=gt), torch.randn(1, 4, LAT, LON, device=dev, generator=gt))
+        s_mean, s_std, u_mean, u_std = stats[0], stats[1], stats[2].reshape(13, 5), stats[3].reshape(13, 5)
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         main = torch.cuda.current_stream()
+        ENS = 8
 
-        def e2e_run(nsteps):
+        def e2e_run(nsteps, mode):
             in_ready = [None, None]
             in_free = [None, None]
-            out_done = [None, None]
 
             def issue_h2d(j):
-                b = j % 2
+                b = (j // ENS if mode == "ensemble" else j) % 2
                 with torch.cuda.stream(s_in):
                     if in_free[b] is not None:
                         s_in.wait_event(in_free[b])
@@ -264,34 +287,79 @@ def run_gpu_arm(args):
                     dev_in[b][1].copy_(host_in[b][1], non_blocking=True)
                     ev = torch.cuda.Event(); ev.record(s_in); in_ready[b] = ev
 
+            uploads = range(nsteps) if mode != "ensemble" else range(0, nsteps, ENS)
             issue_h2d(0)
             for j in range(nsteps):
-                b = j % 2
-                if j + 1 < nsteps:
-                    issue_h2d(j + 1)
-                main.wait_event(in_ready[b])
-                ou, os_ = model(dev_in[b][0], dev_in[b][1], stats, maps, const_h)
-                ev = torch.cuda.Event(); ev.record(main); in_free[b] = ev
-                with torch.cuda.stream(s_out):
-                    s_out.wait_event(ev)
-                    host_out[b][0].copy_(ou, non_blocking=True)
-                    host_out[b][1].copy_(os_, non_blocking=True)
-                    ou.record_stream(s_out); os_.record_stream(s_out)
-                    d = torch.cuda.Event(); d.record(s_out); out_done[b] = d
+                b = (j // ENS if mode == "ensemble" else j) % 2
+                nxt = j + 1 if mode != "ensemble" else (j // ENS + 1) * ENS
+                if nxt < nsteps and (mode != "ensemble" or j % ENS == 0):
+                    issue_h2d(nxt)
+                if mode != "ensemble" or j % ENS == 0:
+                    main.wait_event(in_ready[b])
+                if mode == "ensemble":
+                    pu, ps = ens.perturb(dev_in[b][0], dev_in[b][1], rank * 1000 + j)
+                    ou, os_ = model(pu, ps, stats, maps, const_h)
+                else:
+                    ou, os_ = model(dev_in[b][0], dev_in[b][1], stats, maps, const_h)
+                if mode == "fields":
+                    ev = torch.cuda.Event(); ev.record(main)
+                    in_free[b] = ev
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(ev)
+                        host_out[j % 2][0].copy_(ou, non_blocking=True)
+                        host_out[j % 2][1].copy_(os_, non_blocking=True)
+                        ou.record_stream(s_out); os_.record_stream(s_out)
+                else:
+                    ru, rs, au, as_ = ops.scores(ou, os_, tgt[0], tgt[1], s_mean, s_std, u_mean, u_std, normalised=True)
+                    sc = torch.stack((torch.cat((ru.reshape(-1), rs.reshape(-1))), torch.cat((au.reshape(-1), as_.reshape(-1)))))
+                    ev = torch.cuda.Event(); ev.record(main)
+                    if mode != "ensemble" or j % ENS == ENS - 1 or j == nsteps - 1:
+                        in_free[b] = ev
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(ev)
+                        host_sc[j % 2].copy_(sc, non_blocking=True)
+                        sc.record_stream(s_out)
             s_out.synchronize()
+            main.synchronize()
+            return len(uploads)
 
-        e2e_run(2)
+        e2e_times = {}
+        for mode in ("metric", "fields", "ensemble"):
+            e2e_run(2 if mode != "ensemble" else ENS + 1, mode)
+            barrier()
+            w0 = time.perf_counter()
+            n_up = e2e_run(args.steps, mode)
+            barrier()
+            e2e_times[mode] = (time.perf_counter() - w0, n_up)
+        score_sample = [float(host_sc[(args.steps - 1) % 2][0, 0]), float(host_sc[(args.steps - 1) % 2][1, 0])]
+
+        # ---- fp16 operands (same tensor-core rate, ~8x lower error: meets the 1e-3 example tolerance of north_star)
+        other = "fp16" if args.operands == "bf16" else "bf16"
+        pb.set_operand_dtype(other)
+        for i in range(3):
+            step(i)
         barrier()
-        w0 = time.perf_counter()
-        e2e_run(args.steps)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            step(i)
+        f1.record()
         barrier()
-        e2e_s = time.perf_counter() - w0
+        other_ms = f0.elapsed_time(f1)
+        pb.set_operand_dtype(args.operands)
 
     # ---- reduce over ranks (max time)
-    times = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    times = torch.tensor([ms, other_ms] + [e2e_times[m][0] * 1e3 for m in ("metric", "fields", "ensemble")],
+                         device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(times[0]), float(times[1])
+    ms_max, other_ms_max, e2e_ms_max, e2e_fields_ms, e2e_ens_ms = (float(x) for x in times)
+    secondary = None
+    if not args.no_secondary:
+        del members, dev_in, host_in, host_out, tgt
+        pb.free_workspaces()
+        torch.cuda.empty_cache()
+        secondary = run_secondary(args, model, dev, rank, world, maps, const_h, stats)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -315,35 +383,155 @@ def run_gpu_arm(args):
     dom = max((k for k in kern if k in algo_flops), key=lambda k: kern[k][0])
     dom_ms = kern[dom][0] / kern[dom][1]
     achieved = algo_flops[dom] / (dom_ms * 1e-3) / 1e12
+    traffic, traffic_source = ncu_traffic(dom, args.operands == "fp16")
     roofline = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 1), "peak": pk["tflops_sustained"],
                 "unit": "TFLOP/s", "frac": round(achieved / pk["tflops_sustained"], 4),
-                "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "ncu --set full, profiles/r01c_*.md (bytes per launch)",
+                "traffic": traffic, "traffic_source": traffic_source,
                 "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "avg_launch_ms": round(dom_ms, 4), "algorithmic_flops_per_launch": algo_flops[dom],
                 "step_tflops": round(FLOPS_PER_STEP / (ms_per_step * 1e-3) / 1e12, 1),
                 "step_frac_of_peak": round(FLOPS_PER_STEP / (ms_per_step * 1e-3) / 1e12 / pk["tflops_sustained"], 4),
                 "attn_mlp_frac_of_peak": round(FLOPS_BLOCKS / (sum(v[0] for k, v in kern.items() if k in algo_flops) / args.steps * 1e-3)
                                                / 1e12 / pk["tflops_sustained"], 4),
-                "kernel_time_shares": shares}
+                "kernel_time_shares": shares,
+                "kernel_avg_launch_us": {k: round(1e3 * v[0] / v[1], 1) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}}
+    how = "PanguModel.forward on pinned host inputs (H2D every step); copies double-buffered on side streams; "
     line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.operands, "data": "synthetic",
-            "config": {"workload": "PanguModel 24h forward, 0.25deg (upper 5x13x721x1440, surface 4x721x1440), batch 1, "
-                                   "random-init weights; one ensemble member per step per GPU",
+            "config": {"workload": WORKLOAD,
                        "parallelism": f"ensemble members sharded over {world} GPU(s), no collective",
                        "accumulate": "fp32", "residual_stream": "fp32",
                        "l2": "per-step working set (>4 GB of activations) is far larger than the 126 MB L2; no explicit flush"},
             "clocks": clocks,
-            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 2 * 69 * 4,
                     "ms_per_step": round(e2e_ms_max / args.steps, 3),
-                    "how": "PanguModel.forward on pinned host inputs; H2D/D2H double-buffered on side streams", "host": numa},
+                    "how": how + "result read back = 69 RMSE + 69 ACC values of the forecast (on-device pangu_scores)",
+                    "host": numa, "result_sample": score_sample},
+            "e2e_fields": {"value": round(world * args.steps / (e2e_fields_ms / 1e3), 3), "unit": UNIT,
+                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d, "ms_per_step": round(e2e_fields_ms / args.steps, 3),
+                           "how": how + "result read back = both fp32 forecast fields (round-1 definition of e2e)"},
+            "e2e_ensemble": {"value": round(world * args.steps / (e2e_ens_ms / 1e3), 3), "unit": UNIT,
+                             "h2d_bytes_per_step": round(h2d * e2e_times["ensemble"][1] / args.steps), "d2h_bytes_per_step": 2 * 69 * 4,
+                             "ms_per_step": round(e2e_ens_ms / args.steps, 3),
+                             "how": f"base state uploaded once per {ENS} members, members perturbed on the device (ensemble.perturb), "
+                                    "scores read back per member"},
+            "other_operands": {"dtype": other, "value": round(world * args.steps / (other_ms_max / 1e3), 3), "unit": UNIT,
+                               "ms_per_step": round(other_ms_max / args.steps, 3),
+                               "note": "same kernels with the other 16-bit operand format (fp16: per-variable rel-L2 <= 1e-3 vs the fp32 reference; bf16: <= 8e-3)"},
             "gpu_launches": launches,
             "roofline": roofline}
+    if secondary is not None:
+        line["secondary"] = secondary
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# kernels behind each entry point (names as ncu prints them, pg:: stripped), for roofline.traffic
+ENTRY_KERNELS = {
+    "pangu_mlp_ln_residual[lo]": ["gemm_kernel<CfgMLP1, {f}>|lo", "gemm_kernel<CfgLNRes384, {f}>|lo"],
+    "pangu_mlp_ln_residual[hi]": ["mlp_fused_kernel<192, {f}>|hi"],
+    "pangu_window_attention[lo]": ["window_attention_tc_kernel<{f}>|lo"],
+    "pangu_window_attention[hi]": ["window_attention_tc_kernel<{f}>|hi"],
+    "pangu_qkv[lo]": ["gemm_kernel<CfgQKV, {f}>|lo"], "pangu_qkv[hi]": ["gemm_kernel<CfgQKV, {f}>|hi"],
+    "pangu_proj_ln_residual[lo]": ["gemm_kernel<CfgLNRes384, {f}>|lo"],
+    "pangu_proj_ln_residual[hi]": ["gemm_kernel<CfgLNRes192, {f}>|hi"],
+}
+
+
+def ncu_traffic(entry: str, fp16: bool):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels behind ``entry``, from the committed
+    ``ncu --set full`` captures (profiles/traffic.json, written by tools/ncu_summary.py traffic).  None (with the
+    reason) when a kernel of the entry point has no capture -- never a stale constant."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, "profiles/traffic.json missing"
+    with open(path) as fh:
+        db = json.load(fh)
+    tot, src = 0.0, []
+    for k in ENTRY_KERNELS.get(entry, []):
+        key = k.format(f=0)          # captures are taken with bf16 operands; the fp16 kernels move the same bytes
+        if key not in db:
+            return None, f"no ncu capture of {key} in profiles/traffic.json"
+        tot += db[key]["dram_bytes_per_launch"]
+        src.append(db[key]["source"])
+    if not src:
+        return None, f"no kernel list for {entry}"
+    return tot, "ncu --set full, bytes per launch summed over the entry point's kernels: " + ", ".join(src)
+
+
+# ----------------------------------------------------------------------------------------------
+# secondary record: short driver-visible finetune / lora steps (BASELINE.json configs[3], configs[4])
+# ----------------------------------------------------------------------------------------------
+def run_secondary(args, model, dev, rank, world, maps, const_h, stats):
+    import torch
+    import torch.distributed as dist
+    import pangu_pytorch_b200 as pb
+    from pangu_pytorch_b200 import lora, training
+    from pangu_pytorch_b200.dist import GradReducer
+    out = {}
+    gk = torch.Generator(device=dev).manual_seed(100 + rank)
+    up = torch.randn(1, 5, 13, LAT, LON, device=dev, generator=gk)
+    sf = torch.randn(1, 4, LAT, LON, device=dev, generator=gk)
+    tu = torch.randn(1, 5, 13, LAT, LON, device=dev, generator=gk)
+    ts = torch.randn(1, 4, LAT, LON, device=dev, generator=gk)
+    steps = 3
+    for name in ("finetune", "lora"):
+        pb.set_operand_dtype(TRAIN_OPERANDS)
+        torch.manual_seed(0)
+        m = pb.PanguModel(device=dev).to(dev)
+        if name == "lora":          # finetune/lora_tune.py:124-139: r=16, alpha=16, dropout 0.1, output convs trained in full
+            lora.add_lora(m, r=16, lora_alpha=16.0, lora_dropout=LORA_DROPOUT)
+            m.to(dev)
+        m.train()
+        if world > 1:
+            m.grad_reducer = GradReducer()
+        opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=5e-6, weight_decay=3e-6, fused=True)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = training.train_step(m, up, sf, stats, maps, const_h, tu, ts)
+            opt.step()
+            return loss
+
+        for _ in range(2):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        per = float(t[0]) / steps
+        out[name] = {"metric": f"{name} steps/s @0.25deg (fwd + weighted-L1 + bwd + grad mean + fused Adam)",
+                     "value": round(world * 1e3 / per, 3), "unit": "steps/s", "ms_per_step": round(per, 2), "steps": steps,
+                     "warmup": 2, "dtype": TRAIN_OPERANDS, "loss": float(loss),
+                     "tflops": round(3 * FLOPS_PER_STEP / (per * 1e-3) / 1e12, 1),
+                     "config": ("lora_tune: r=16 adapters on the 67 nn.Linear, lora_dropout %.1f, output convs trained in full" % LORA_DROPOUT
+                                if name == "lora" else "finetune_fully: all 223 tensors") +
+                               f"; batch 1 per GPU, {world} GPU(s), gradient mean over NCCL overlapped with the backward"}
+        del m, opt
+        training_cleanup()
+    pb.set_operand_dtype(args.operands)
+    return out
+
+
+def training_cleanup():
+    import torch
+    import pangu_pytorch_b200 as pb
+    pb.free_workspaces()
+    torch.cuda.empty_cache()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -447,6 +635,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--operands", default=os.environ.get("PANGU_B200_OPERANDS", "bf16"), choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short finetune / lora steps of the `secondary` record")
     ap.add_argument("--workload", default="forecast", choices=["forecast", "train", "lora"],
                     help="forecast: the BASELINE.json headline (default); train: finetune_fully step (configs[3]); "
                          "lora: lora_tune step (configs[4])")

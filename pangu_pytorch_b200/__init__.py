@@ -18,7 +18,8 @@ from __future__ import annotations
 
 import sys
 
-from .engine import free_workspaces, operand_dtype, set_operand_dtype  # noqa: F401
+from .engine import (free_workspaces, operand_dtype, set_operand_dtype, set_training_operand_dtype,  # noqa: F401
+                     training_operand_dtype)
 from .models import layers, pangu_model  # noqa: F401
 from .models.layers import (DownSample, EarthAttention3D, EarthSpecificBlock, EarthSpecificLayer, Mlp,  # noqa: F401
                             PatchEmbedding_pretrain, PatchRecovery_pretrain, UpSample)

@@ -16,8 +16,8 @@
 // Per window:
 //
 //   S[128x144] = Q[0:128] K^T          tcgen05.mma, A/B from smem (K-major), fp32 accum in TMEM
-//   y = S*log2e + bias'                72 keys per thread (two threads per query row), held in REGISTERS
-//   P = exp2(y - m)                    packed 16-bit, written over the first 72 columns of S (one TMEM store pass)
+//   pass 1:  m = max_j (S*log2e + bias')   streamed from TMEM in 16-column pieces, nothing written back
+//   pass 2:  P = exp2(S*log2e + bias' - m) packed 16-bit, written over S columns the thread has already consumed
 //   O[128x32]  = P V                   tcgen05.mma, A = P from TMEM, B = V from smem (MN-major)
 //   rows 128..143 (144 = 128 + 16 does not fit an MMA M) are done by mma.sync "tail" warps that
 //   read the same smem tiles (the SWIZZLE_64B pattern equals the ldmatrix-friendly XOR swizzle).
@@ -30,10 +30,12 @@
 // has read P before the next S overwrites it).  The MMA warp runs converged with warp-uniform operands
 // (only the tcgen05 instructions are elected) and polls "next S" / "next PV" without blocking on either.
 // Warps (512 threads): 0 TMA producer, 1 MMA issuer, 2-7 tail warps (ring stage s belongs to warp 2 + s%6),
-// 8-15 softmax: all eight on every window; thread = (query row = TMEM lane, half of the 144 keys), warps w and w+4 pair up.
-// Round 1 kept one full row per thread and wrote y back to TMEM between the max and the exp pass: 27 dependent TMEM round
-// trips per window (ncu: tensor pipe 12 %, long-scoreboard stalls on the TMEM waits).  With 72 keys per thread the row fits
-// the 128-register budget of a 512-thread CTA and the window needs 3 TMEM load waits and one store wait.
+// 8-15 softmax: all eight on every window; thread = (query row = TMEM lane, key range), warps w and w+4 share a TMEM lane
+// quadrant and split the row: keys [0,80) and [80,144).  Each range is a whole number of K=16 steps of the PV MMA, so each
+// thread writes its P over its OWN score columns ([0,40) resp. [80,112)) and the two never touch the other's columns.
+// Measured on B200 (tools/tmem_bench.cu): a dependent tcgen05.ld + wait costs ~38 clk and 8 warps read ~1 KB/clk, so
+// re-reading S and bias' in pass 2 is cheap; what is NOT cheap is a register spill: with 232 KB of shared memory there is
+// no L1 left and every spill reload is an L2 round trip (a 72-keys-in-registers variant spilled 13 words and ran 20 % slower).
 #pragma once
 #include "attention.cuh"
 
@@ -127,6 +129,143 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&r)[2]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Tail rows 128..143 of a window on mma.sync: key tiles J0 .. J0+NT-1 (8 keys each, NT even) of one 16-row block,
+// flash-style: running row maxima m, per-thread partial sums l and the output accumulators o are rescaled in place.
+// Fragment layout as in mma.m16n8k16: this thread holds rows gq (e = 0,1) and gq + 8 (e = 2,3), columns 2*q4 + {0,1}.
+template <bool kFp16, int J0, int NT>
+__device__ __forceinline__ void tail_keys(uint32_t sk, uint32_t sv, const uint32_t (&qa)[2][4], const float* tb0,
+                                          const float* tb1, float (&o)[4][4], float& m0, float& m1, float& l0, float& l1,
+                                          int lane) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  float s[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    uint32_t b0, b1, b2, b3;
+    ldsm_x4(sk + att_off(8 * (J0 + j) + (lane & 7), lane >> 3), b0, b1, b2, b3);
+    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    mma16816<kFp16>(s[j], qa[0], b0, b1);
+    mma16816<kFp16>(s[j], qa[1], b2, b3);
+  }
+  float x0 = -INFINITY, x1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const float2 lo = *reinterpret_cast<const float2*>(tb0 + 8 * (J0 + j));
+    const float2 hi = *reinterpret_cast<const float2*>(tb1 + 8 * (J0 + j));
+    s[j][0] = fmaf(s[j][0], kLog2e, lo.x); s[j][1] = fmaf(s[j][1], kLog2e, lo.y);
+    s[j][2] = fmaf(s[j][2], kLog2e, hi.x); s[j][3] = fmaf(s[j][3], kLog2e, hi.y);
+    x0 = max3(x0, s[j][0], s[j][1]);
+    x1 = max3(x1, s[j][2], s[j][3]);
+  }
+  x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+  x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+  const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
+  const float c0 = fast_exp2(m0 - n0), c1 = fast_exp2(m1 - n1);      // first range: m = -inf -> factor 0 on zeros
+  m0 = n0; m1 = n1;
+  float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    s[j][0] = fast_exp2(s[j][0] - n0); s[j][1] = fast_exp2(s[j][1] - n0);
+    s[j][2] = fast_exp2(s[j][2] - n1); s[j][3] = fast_exp2(s[j][3] - n1);
+    p0 += s[j][0] + s[j][1];
+    p1 += s[j][2] + s[j][3];
+  }
+  l0 = fmaf(l0, c0, p0);
+  l1 = fmaf(l1, c1, p1);
+#pragma unroll
+  for (int n = 0; n < 4; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
+#pragma unroll
+  for (int kk = 0; kk < NT / 2; ++kk) {
+    uint32_t pa[4];
+    pa[0] = pack16<kFp16>(s[2 * kk][0], s[2 * kk][1]);
+    pa[1] = pack16<kFp16>(s[2 * kk][2], s[2 * kk][3]);
+    pa[2] = pack16<kFp16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pa[3] = pack16<kFp16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(sv + att_off(8 * J0 + 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * np + (lane >> 4)), b0, b1, b2, b3);
+      mma16816<kFp16>(o[2 * np], pa, b0, b1);
+      mma16816<kFp16>(o[2 * np + 1], pa, b2, b3);
+    }
+  }
+}
+
+// Softmax of one query row over the key range [COL0, COL0 + NK) (NK = 80 or 64: a whole number of 16-key MMA steps).
+// s_base / bias_base: TMEM addresses (lane of this row) of column 0 of the score buffer and of the resident bias' tile.
+// Returns this range's sum of exp2(y - m); P is left, packed 16-bit, in columns [COL0, COL0 + NK/2) of the score buffer.
+template <bool kFp16, int NK, int COL0, class Trace>
+__device__ __forceinline__ float softmax_half(uint32_t s_base, uint32_t bias_base, uint16_t* xm, int half, int pair_bar,
+                                              Trace&& trace) {
+  constexpr int NC = NK / 16;
+  constexpr float kLog2e = 1.4426950408889634f;
+  const f32x2 l2e2 = pack2(kLog2e, kLog2e);
+  uint32_t sa[2][16], ba[2][16];
+  // ---- pass 1: row maximum of y = S*log2e + bias' over this key range (piece p+1 in flight while piece p is reduced)
+  tmem_ld16(s_base + COL0, sa[0]);
+  tmem_ld16(bias_base + COL0, ba[0]);
+  tmem_ld_wait();
+  float pm = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < NC) {
+      tmem_ld16(s_base + COL0 + 16 * (c + 1), sa[cur ^ 1]);
+      tmem_ld16(bias_base + COL0 + 16 * (c + 1), ba[cur ^ 1]);
+    } else {                 // first piece of pass 2: in flight across the row-maximum exchange
+      tmem_ld16(s_base + COL0, sa[cur ^ 1]);
+      tmem_ld16(bias_base + COL0, ba[cur ^ 1]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a0, a1;
+      unpack2(fma2(pack2(__uint_as_float(sa[cur][2 * e]), __uint_as_float(sa[cur][2 * e + 1])), l2e2,
+                   pack2(__uint_as_float(ba[cur][2 * e]), __uint_as_float(ba[cur][2 * e + 1]))), a0, a1);
+      pm = max3(pm, a0, a1);
+    }
+    if (c + 1 < NC) tmem_ld_wait();
+  }
+  // ---- meet the other key range of this row: any common stabiliser >= max - small is exact for softmax, so the two
+  //      maxima travel as bf16 (p <= 2^(|m| 2^-8)) through a 4-byte mailbox and both threads use the same value
+  trace(0);
+  xm[half] = __bfloat16_as_ushort(__float2bfloat16_rn(pm));
+  named_bar_sync(pair_bar, 64);
+  {
+    const uint32_t both = *reinterpret_cast<const volatile uint32_t*>(xm);
+    pm = fmaxf(__uint_as_float(both << 16), __uint_as_float(both & 0xFFFF0000u));
+  }
+  // ---- pass 2: P = exp2(y - m) packed 16-bit; piece p of P (8 columns) lands on score columns [8p, 8p+8) of this
+  //      range, which this thread consumed in piece p/2 <= p
+  const f32x2 negm2 = pack2(-pm, -pm);
+  f32x2 lsum = pack2(0.f, 0.f);
+  tmem_ld_wait();
+  trace(1);
+  constexpr int first = NC & 1;        // buffer that holds piece 0 of pass 2
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int cur = (c + first) & 1;
+    if (c + 1 < NC) {
+      tmem_ld16(s_base + COL0 + 16 * (c + 1), sa[cur ^ 1]);
+      tmem_ld16(bias_base + COL0 + 16 * (c + 1), ba[cur ^ 1]);
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a0, a1;
+      unpack2(fma2(pack2(__uint_as_float(sa[cur][2 * e]), __uint_as_float(sa[cur][2 * e + 1])), l2e2,
+                   add2(pack2(__uint_as_float(ba[cur][2 * e]), __uint_as_float(ba[cur][2 * e + 1])), negm2)), a0, a1);
+      const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+      lsum = add2(lsum, pack2(p0, p1));
+      pk[e] = pack16<kFp16>(p0, p1);
+    }
+    if (c + 1 < NC) tmem_ld_wait();      // piece c+1 is in registers before any score column is overwritten
+    tmem_st8(s_base + COL0 + 8 * c, pk);
+  }
+  trace(2);
+  float a0, a1;
+  unpack2(lsum, a0, a1);
+  return a0 + a1;
+}
 
 template <bool kFp16>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
@@ -270,7 +409,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 9; ++kk)   // 144 keys = 9 x K16: P advances 8 TMEM columns, V 16 rows = 1024 B
-              umma_f16_ts(tmem + ATC_COL_O + 32 * b, tmem + ATC_COL_S + 144 * b + 8 * kk, dv + uint64_t(kk * 64), idesc_o, kk);
+              umma_f16_ts(tmem + ATC_COL_O + 32 * b, tmem + ATC_COL_S + 144 * b + (kk < 5 ? 8 * kk : 40 + 8 * kk),
+                          dv + uint64_t(kk * 64), idesc_o, kk);     // P of keys [0,80) at columns [0,40), of keys [80,144) at [80,112)
             umma_commit(&ofull_bar[b]);
             umma_commit(&empty_bar[st]);
           }
@@ -355,55 +495,16 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) ldsm_x4(sq + att_off(r, ks * 2 + (lane >> 4)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
           }
-          float s[18][4];
-#pragma unroll
-          for (int j = 0; j < 18; ++j) {
-            uint32_t b0, b1, b2, b3;
-            ldsm_x4(sk + att_off(8 * j + (lane & 7), lane >> 3), b0, b1, b2, b3);
-            s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-            mma16816<kFp16>(s[j], qa[0], b0, b1);
-            mma16816<kFp16>(s[j], qa[1], b2, b3);
-          }
-          float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 18; ++j) {
-            const float2 lo = *reinterpret_cast<const float2*>(tb0 + 8 * j);
-            const float2 hi = *reinterpret_cast<const float2*>(tb1 + 8 * j);
-            s[j][0] = fmaf(s[j][0], kLog2e, lo.x); s[j][1] = fmaf(s[j][1], kLog2e, lo.y);
-            s[j][2] = fmaf(s[j][2], kLog2e, hi.x); s[j][3] = fmaf(s[j][3], kLog2e, hi.y);
-            m0 = max3(m0, s[j][0], s[j][1]);
-            m1 = max3(m1, s[j][2], s[j][3]);
-          }
-          m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-          m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-          float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 18; ++j) {
-            s[j][0] = fast_exp2(s[j][0] - m0); s[j][1] = fast_exp2(s[j][1] - m0);
-            s[j][2] = fast_exp2(s[j][2] - m1); s[j][3] = fast_exp2(s[j][3] - m1);
-            l0 += s[j][0] + s[j][1];
-            l1 += s[j][2] + s[j][3];
-          }
-          l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-          l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+          // keys in two ranges ([0,80) and [80,144): whole K=16 steps) with a running maximum, so that only 40 scores
+          // are live at a time: the tail warps share the 128-register budget with everybody else
           float o[4][4];
 #pragma unroll
           for (int n = 0; n < 4; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
-#pragma unroll
-          for (int kk = 0; kk < 9; ++kk) {
-            uint32_t pa[4];
-            pa[0] = pack16<kFp16>(s[2 * kk][0], s[2 * kk][1]);
-            pa[1] = pack16<kFp16>(s[2 * kk][2], s[2 * kk][3]);
-            pa[2] = pack16<kFp16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-            pa[3] = pack16<kFp16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-            for (int np = 0; np < 2; ++np) {
-              uint32_t b0, b1, b2, b3;
-              ldsm_x4_t(sv + att_off(16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * np + (lane >> 4)), b0, b1, b2, b3);
-              mma16816<kFp16>(o[2 * np], pa, b0, b1);
-              mma16816<kFp16>(o[2 * np + 1], pa, b2, b3);
-            }
-          }
+          float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+          tail_keys<kFp16, 0, 10>(sk, sv, qa, tb0, tb1, o, m0, m1, l0, l1, lane);
+          tail_keys<kFp16, 10, 8>(sk, sv, qa, tb0, tb1, o, m0, m1, l0, l1, lane);
+          l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+          l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
           const float i0 = 1.0f / l0, i1 = 1.0f / l1;
           // stage O in this window's Q rows 128..143 (not read by the M=128 MMA), then 64 B stores
           __syncwarp();
@@ -438,7 +539,6 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         const int quad = warp & 3, half = (warp - 8) >> 2;
         const int r = quad * 32 + lane;
         const uint32_t lane_addr = tmem + (uint32_t(quad * 32) << 16);
-        const uint32_t bias_addr = lane_addr + ATC_COL_BIAS + 72 * half;
         const int pair_bar = 3 + quad;           // named barrier of the two warps that share this lane quadrant
 
         // ---- segment start: bias tile -> TMEM (each half moves boxes half, half+2, ... of its rows)
@@ -491,82 +591,30 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             stg16(dst + 16 * q, v);
           }
         };
-        const f32x2 l2e2 = pack2(kLog2e, kLog2e);
 #pragma unroll 1
         for (int i = 0; i < nwin; ++i) {
           const int g = gbase + i, b = g & 1;
-          const uint32_t s_addr = lane_addr + ATC_COL_S + 144 * b + 72 * half;
           TR(3, g, 0, r == 0 && half == 0);
           mbar_wait(&sfull_bar[b], (g >> 1) & 1);
           TR(3, g, 1, r == 0 && half == 0);
           tc_fence_after();
-          // ---- y = S*log2e + bias' for this thread's 72 keys, kept in registers; bias' streams through two 16-column
-          //      buffers (3 TMEM waits per window instead of 27 dependent round trips)
-          uint32_t y[72], bb[2][16];
-          tmem_ld32p(s_addr, y);
-          tmem_ld32p(s_addr + 32, y + 32);
-          tmem_ld8p(s_addr + 64, y + 64);
-          tmem_ld16(bias_addr, bb[0]);
-          tmem_ld16(bias_addr + 16, bb[1]);
-          tmem_ld_wait();
-          float pm = -INFINITY;
-          auto addbias = [&](int c0, const uint32_t* bsrc, int n) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              if (2 * e >= n) break;
-              float a0, a1;
-              unpack2(fma2(pack2(__uint_as_float(y[c0 + 2 * e]), __uint_as_float(y[c0 + 2 * e + 1])), l2e2,
-                           pack2(__uint_as_float(bsrc[2 * e]), __uint_as_float(bsrc[2 * e + 1]))), a0, a1);
-              pm = max3(pm, a0, a1);
-              y[c0 + 2 * e] = __float_as_uint(a0); y[c0 + 2 * e + 1] = __float_as_uint(a1);
-            }
-          };
-          addbias(0, bb[0], 16);
-          tmem_ld16(bias_addr + 32, bb[0]);
-          addbias(16, bb[1], 16);
-          tmem_ld16(bias_addr + 48, bb[1]);
-          tmem_ld_wait();
-          addbias(32, bb[0], 16);
-          tmem_ld8p(bias_addr + 64, bb[0]);
-          addbias(48, bb[1], 16);
-          tmem_ld_wait();
-          addbias(64, bb[0], 8);
-          TR(3, g, 2, r == 0 && half == 0);
-          // ---- row maximum: meet the other half of the row
-          {
-            const uint16_t m16 = __bfloat16_as_ushort(__float2bfloat16_rn(pm));
-            s_xm[(b * 128 + r) * 2 + half] = m16;
-            named_bar_sync(pair_bar, 64);
-            const uint32_t both = *reinterpret_cast<const uint32_t*>(&s_xm[(b * 128 + r) * 2]);
-            pm = fmaxf(__uint_as_float(both << 16), __uint_as_float(both & 0xFFFF0000u));
-          }
-          // ---- P = exp2(y - m), packed 16-bit, into columns [36*half, +36) of this window's S buffer.  The partner
-          //      loaded its scores (which these columns may overlap) before it arrived at the pair barrier above.
-          const f32x2 negm2 = pack2(-pm, -pm);
-          f32x2 lsum = pack2(0.f, 0.f);
-          uint32_t pk[36];
-#pragma unroll
-          for (int e = 0; e < 36; ++e) {
-            float a0, a1;
-            unpack2(add2(pack2(__uint_as_float(y[2 * e]), __uint_as_float(y[2 * e + 1])), negm2), a0, a1);
-            const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
-            lsum = add2(lsum, pack2(p0, p1));
-            pk[e] = pack16<kFp16>(p0, p1);
-          }
-          const uint32_t p_addr = lane_addr + ATC_COL_S + 144 * b + 36 * half;
-          tmem_st32p(p_addr, pk);
-          tmem_st4p(p_addr + 32, pk + 32);
-          {
-            float a0, a1;
-            unpack2(lsum, a0, a1);
-            tmem_st1(lane_addr + ATC_COL_L + 2 * b + half, __float_as_uint(a0 + a1));
-          }
+          const uint32_t s_base = lane_addr + ATC_COL_S + 144 * b;
+          uint16_t* xm = s_xm + (b * 128 + r) * 2;
+          // trace rows: 3 = [enter, S ready, pass 1 done, max exchanged], 4 = [pass 2 done, P published, epilogue done] of warp 8
+          // (keys [0,80)); 5 = [pass 1 done, max exchanged, pass 2 done, epilogue done] of its partner warp 12 (keys [80,144))
+          auto tr0 = [&](int ev) { TR(ev < 2 ? 3 : 4, g, ev < 2 ? ev + 2 : 0, r == 0); };
+          auto tr1 = [&](int ev) { TR(5, g, ev, r == 0); };
+          const float l = half == 0 ? softmax_half<kFp16, 80, 0>(s_base, lane_addr + ATC_COL_BIAS, xm, 0, pair_bar, tr0)
+                                    : softmax_half<kFp16, 64, 80>(s_base, lane_addr + ATC_COL_BIAS, xm, 1, pair_bar, tr1);
+          tmem_st1(lane_addr + ATC_COL_L + 2 * b + half, __float_as_uint(l));
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&pfull_bar[b]);
-          TR(4, g, 0, r == 0 && half == 0);
+          TR(4, g, 1, r == 0 && half == 0);
           // ---- output of the previous window: its PV was queued one window ago
           if (i > 0) epilogue(i - 1);
+          TR(4, g, 2, r == 0 && half == 0);
+          TR(5, g, 3, r == 0 && half == 1);
         }
         epilogue(nwin - 1);
         TR(6, seg, 2, threadIdx.x == 256);

@@ -107,6 +107,8 @@ class LoraLinear(nn.Module):
         nn.init.zeros_(self.lora_B[adapter].weight)
         for p in base.parameters():
             p.requires_grad_(False)
+        self._merged = None          # persistent fp32 W + s B A (plain attribute: not a parameter, not in state_dict)
+        self._merged_key = None
 
     @property
     def A(self) -> torch.Tensor:
@@ -118,13 +120,27 @@ class LoraLinear(nn.Module):
 
     @property
     def weight(self) -> torch.Tensor:
-        """Effective dense weight seen by the kernels (a fresh fp32 tensor, parameter-space arithmetic only)."""
+        """Effective dense weight ``W + (alpha/r) B A`` seen by the kernels.  ONE persistent fp32 tensor per module,
+        re-formed IN PLACE (so its ``_version`` advances and the 16-bit operand caches of ``engine.Weight16`` /
+        ``Weight16T`` notice) whenever W, A or B changed since it was last formed; the cache key is built from the
+        version counters and storage of those three tensors, never from a temporary."""
         drop = self.lora_dropout[self.adapter]
         if self.training and isinstance(drop, nn.Dropout) and drop.p > 0:
             raise NotImplementedError("pangu_pytorch_b200: lora_dropout > 0 cannot be folded into the weight; "
                                       "train with lora_dropout=0 (eval / inference accept any value)")
-        with torch.no_grad():
-            return torch.addmm(self.base_layer.weight, self.B, self.A, alpha=self.scaling)
+        key = tuple((t.data_ptr(), t._version, str(t.device)) for t in (self.base_layer.weight, self.A, self.B))
+        if key != self._merged_key:
+            with torch.no_grad():
+                if self._merged is None or self._merged.device != self.base_layer.weight.device:
+                    self._merged = torch.empty_like(self.base_layer.weight, dtype=torch.float32)
+                torch.addmm(self.base_layer.weight.float(), self.B.float(), self.A.float(), alpha=self.scaling, out=self._merged)
+            self._merged_key = key
+        return self._merged
+
+    def invalidate(self) -> None:
+        """Force the merged weight to be re-formed (only needed after writes that bypass the version counter,
+        e.g. through ``param.data``)."""
+        self._merged_key = None
 
     @property
     def bias(self):

@@ -62,14 +62,23 @@ class PanguModel(nn.Module):
         hi = workspace(dev, Z, H, W, 192)
         lo = workspace(dev, Z, (H + 1) // 2, W // 2, 384)
         skip16 = self._skip16(hi)
+        taps = getattr(self, "_taps", None)      # tests only: dict that receives a copy of the residual stream after each stage
+        tap = (lambda name, ws: taps.__setitem__(name, ws.x32.clone().unsqueeze(0))) if taps is not None else (lambda name, ws: None)
         with torch.no_grad():
             self._input_layer._run(input, input_surface, statistics, maps, const_h, hi)   # -> hi.x32, hi.x16w[0]
+            tap("embed", hi)
             self.layers[0]._run(hi, -1, skip16)            # skip connection kept as its 16-bit shadow
+            tap("layer0", hi)
             self.downsample._run(hi, lo)                   # -> lo.x32, lo.x16w[0]
+            tap("down", lo)
             self.layers[1]._run(lo, 0)                     # hands over in window order to layer 2
+            tap("layer1", lo)
             self.layers[2]._run(lo, -1)                    # -> lo.x16 (natural) for the up-sampling GEMM
+            tap("layer2", lo)
             self.upsample._run(lo, hi)                     # -> hi.x32, hi.x16w[0]
+            tap("up", hi)
             self.layers[3]._run(hi, -1)                    # -> hi.x16 (natural)
+            tap("layer3", hi)
             return self._output_layer._run(skip16, hi, lat, lon)   # cat(skip, x) folded into the K loop
 
     def _skip16(self, hi):

@@ -82,6 +82,7 @@ class Tape:
         self.dys = torch.empty(plane, 128, dtype=h, device=dev)
         self.g_skip = torch.empty(hi.T, hi.C, dtype=f, device=dev)
         self.lat = self.lon = 0
+        self.generation = 0          # bumped by every training-mode forward: a backward must match the forward that filled the tape
 
 
 def block_order(model, hi, lo):
@@ -122,6 +123,7 @@ def forward_train(model, input, input_surface, statistics, maps, const_h):
     lo = engine.workspace(dev, Z, (H + 1) // 2, W // 2, 384)
     tape = _tape(model, hi, lo)
     tape.lat, tape.lon = lat, lon
+    tape.generation += 1
     fp16 = hi.fp16
     order, bt = tape.order, tape.blocks
     # what each block writes its 16-bit shadow to: the next block's window-ordered input, or a natural-order buffer
@@ -350,13 +352,23 @@ class PanguTrainFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, input, input_surface, statistics, maps, const_h, *params):
-        out, out_s, tape = forward_train(model, input, input_surface, statistics, maps, const_h)
-        ctx.model, ctx.tape = model, tape
+        for name, t in (("input", input), ("input_surface", input_surface)):
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                raise RuntimeError(f"pangu_pytorch_b200: gradients w.r.t. `{name}` are not produced by the B200 backward "
+                                   "(the reference never asks for them either); detach it")
+        with engine.operands(engine.training_operand_dtype()):
+            out, out_s, tape = forward_train(model, input, input_surface, statistics, maps, const_h)
+        ctx.model, ctx.tape, ctx.generation = model, tape, tape.generation
         return out, out_s
 
     @staticmethod
     def backward(ctx, g_upper, g_surface):
-        grads = backward(ctx.model, ctx.tape, g_upper, g_surface, getattr(ctx.model, "grad_reducer", None))
+        if ctx.generation != ctx.tape.generation:
+            raise RuntimeError("pangu_pytorch_b200: the saved activations of this forward were overwritten by a later "
+                               "training-mode forward of the same model (one tape per model): call backward() before the "
+                               "next forward, or run the extra forward under torch.no_grad() / model.eval()")
+        with engine.operands("fp16" if ctx.tape.fp16 else "bf16"):
+            grads = backward(ctx.model, ctx.tape, g_upper, g_surface, getattr(ctx.model, "grad_reducer", None))
         return (None,) * 6 + tuple(grads)
 
 

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import pangu_oracle as O
-from tests.util import TOL_BLOCK, TOL_MODEL, golden, rel_l2, sampled_rel_l2, to_device
+from tests.util import TOL_BLOCK, TOL_MODEL, TOL_TAP, golden, rel_l2, sampled_rel_l2, to_device
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -225,9 +225,16 @@ def test_full_025_forward_against_reference_golden(fmt, kind):
     m = _strip_model(p)
     up, sf, stats, maps, ch = O.synthetic_inputs(seed=1, nontrivial_stats=True)
     d = lambda t: t.to(DEV)
+    m._taps = {}
     with torch.no_grad():
         gu, gs = m(d(up), d(sf), [d(s) for s in stats], d(maps), d(ch))
     torch.cuda.synchronize()
+    # the residual stream after every stage against the reference's own taps (embed, the four layers, down, up)
+    taps = {k: sampled_rel_l2(v, g, k) for k, v in m._taps.items()}
+    m._taps = None
+    print(f"0.25deg forward {fmt} {kind}: stage taps " + ", ".join(f"{k} {v:.2e}" for k, v in taps.items()))
+    assert set(taps) == {"embed", "layer0", "down", "layer1", "layer2", "up", "layer3"}
+    assert max(taps.values()) < TOL_TAP[fmt], taps
     eu, es = sampled_rel_l2(gu, g, "out_upper"), sampled_rel_l2(gs, g, "out_surface")
     vu = gu[0].double().flatten(1).norm(dim=1).cpu().numpy() / g["out_upper.var_l2"]
     vs = gs[0].double().flatten(1).norm(dim=1).cpu().numpy() / g["out_surface.var_l2"]

@@ -22,12 +22,16 @@ from tests.util import rel_l2
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TOL_GRAD = {"bf16": 5e-2, "fp16": 1e-2}
+# earth_specific_bias tables (91 % of the parameters): dS = P o (dP - rowsum(P o dP)) cancels a large common-mode part, so
+# the rounding of q / k / v / dO is amplified.  fp16 operands -- the DEFAULT of the training path -- are within 4e-2
+# (measured <= 1.6e-2); the optional bf16 training format is 7-15 % off and only bounded here, see DESIGN.md 9.
 TOL_BIAS_TABLE = {"bf16": 2.5e-1, "fp16": 4e-2}
 
 
 def _setup(fmt, seed=3):
     import pangu_pytorch_b200 as pb
     pb.set_operand_dtype(fmt)
+    pb.set_training_operand_dtype(fmt)          # the training path has its own default (fp16); pin it to the format under test
     pb.free_workspaces()
     p = O.stress_weights(seed=seed, bias_std=0.5)
     model = pb.PanguModel(device=DEV)
@@ -161,6 +165,7 @@ def test_full_025_backward_directional_derivative():
     import pangu_pytorch_b200 as pb
     from pangu_pytorch_b200 import ops, training, engine
     pb.set_operand_dtype("bf16")
+    pb.set_training_operand_dtype("bf16")
     pb.free_workspaces()
     torch.manual_seed(0)
     model = pb.PanguModel(device=DEV).to(DEV).train()
@@ -203,8 +208,9 @@ def test_full_025_backward_directional_derivative():
     pb.free_workspaces()
 
 
-def test_full_025_gradients_against_reference_golden():
-    """All 223 gradients at the FULL 0.25 degree shapes against the UNMODIFIED reference's own autograd
+@pytest.mark.parametrize("fmt", ["fp16", "bf16"])
+def test_full_025_gradients_against_reference_golden(fmt):
+    """(fp16 = the default operand format of the training path, engine.training_operand_dtype.)  All 223 gradients at the FULL 0.25 degree shapes against the UNMODIFIED reference's own autograd
     (tests/golden/train_grads.npz, written by oracle/make_golden.py --what train: eval-mode DropPath, stress weights,
     0.5 * weighted-MSE loss so that the seed is smooth in the outputs).  The seed is formed here from the GPU
     forward's own outputs, so this is the whole chain -- forward on the tape, seed, backward -- against the reference."""
@@ -212,7 +218,8 @@ def test_full_025_gradients_against_reference_golden():
     from pangu_pytorch_b200 import training
     from tests.util import golden
     gold = golden("train_grads.npz")
-    pb.set_operand_dtype("bf16")
+    pb.set_operand_dtype(fmt)
+    pb.set_training_operand_dtype(fmt)
     pb.free_workspaces()
     p = O.stress_weights(seed=int(gold["weights_seed"]), bias_std=0.5)
     model = pb.PanguModel(device=DEV)
@@ -245,7 +252,7 @@ def test_full_025_gradients_against_reference_golden():
     worst.sort(reverse=True)
     print("[full-size grads vs reference] worst:", [(round(e, 4), n.split("EarthSpecific")[-1], round(r, 4)) for e, n, r in worst[:6]])
     for err, name, nrm in worst:
-        tol = TOL_BIAS_TABLE["bf16"] if name.endswith("earth_specific_bias") else TOL_GRAD["bf16"]
+        tol = TOL_BIAS_TABLE[fmt] if name.endswith("earth_specific_bias") else TOL_GRAD[fmt]
         assert err < tol and abs(nrm - 1.0) < tol, (name, err, nrm)
     training.release_tape(model)
     pb.free_workspaces()

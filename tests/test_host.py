@@ -198,9 +198,28 @@ def test_add_lora_wraps_67_linears_and_round_trips():
     mod = wrapped[n0]
     assert tuple(mod.A.shape) == (16, 384) and tuple(mod.B.shape) == (1152, 16)
     assert torch.equal(mod.weight, mod.base_layer.weight)                      # B starts at zero (peft init)
-    mod.B.data.normal_(0, 0.05, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        mod.B.normal_(0, 0.05, generator=torch.Generator().manual_seed(1))
     eff = mod.base_layer.weight + mod.scaling * (mod.B @ mod.A)
     assert torch.allclose(mod.weight, eff, atol=1e-6) and not mod.weight.requires_grad
+    # The merged weight is ONE persistent tensor re-formed in place when A / B / W change (round-1 bug: a fresh temporary per
+    # access made the 16-bit operand caches, keyed on (data_ptr, _version), return the first step's weights for ever).
+    w_first = mod.weight
+    ptr, ver = w_first.data_ptr(), w_first._version
+    assert mod.weight.data_ptr() == ptr and mod.weight._version == ver               # unchanged adapters: cache hit, no re-form
+    opt = torch.optim.SGD([mod.A, mod.B], lr=0.5)
+    for step in range(2):                                                              # two optimiser steps: the key must move each time
+        mod.A.grad, mod.B.grad = torch.ones_like(mod.A), torch.ones_like(mod.B)
+        opt.step()
+        w_now = mod.weight
+        assert w_now.data_ptr() == ptr and w_now._version > ver, "merged weight must be updated in place"
+        ver = w_now._version
+        eff = mod.base_layer.weight + mod.scaling * (mod.B @ mod.A)
+        assert torch.allclose(w_now, eff.detach(), atol=1e-5), f"stale merged weight after optimiser step {step}"
+    mod.B.data.mul_(2.0)                                                                # .data bypasses the version counter ...
+    mod.invalidate()                                                                    # ... so such writers must say so
+    eff = mod.base_layer.weight + mod.scaling * (mod.B @ mod.A)
+    assert torch.allclose(mod.weight, eff.detach(), atol=1e-5)
     merged = lora.merge_lora_state_dict(lora.peft_state_dict(m))
     assert sorted(merged) == sorted(plain_keys)
     assert torch.allclose(merged[n0 + ".weight"], eff.detach(), atol=1e-6)

@@ -6,7 +6,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import pangu_pytorch_b200 as pb
-from pangu_pytorch_b200 import engine, ops
+from pangu_pytorch_b200 import engine, ops, _lib
+
+if os.environ.get('ATTN_TRACE'):     # development build with the trace hooks compiled in (tools/bin, see README of tools)
+    _lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin", "libpangu_b200_dev.so")
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "hi"
 W = int(sys.argv[2]) if len(sys.argv) > 2 else (360 if tag == "hi" else 180)
@@ -42,7 +45,7 @@ if trace is not None:
     tr = trace.view(8, 64, 4)
     t0 = int(tr[tr > 0].min())
     names = {0: "TMA  [slot free]", 1: "MMA  [full, S issued, pfull, oempty]", 2: "TAIL [start, done]",
-             3: "SOFT [enter, sfull, pass1 done, epi done]", 4: "SOFT [pfull arrive]", 5: "-", 6: "SEG  [start, bias staged, tail-warp0 done, all done]"}
+             3: "SOFT [enter, sfull, pass1 done, max exchanged]", 4: "SOFT [pass2 done, P published, epilogue done]", 5: "SOFT partner [pass1 done, max exchanged, pass2 done, epilogue done]", 6: "SEG  [start, bias staged, tail-warp0 done, all done]"}
     for role in range(7):
         print(names[role])
         for i in range(0, 64):

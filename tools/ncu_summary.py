@@ -2,6 +2,8 @@
 
     python tools/ncu_summary.py launches gpurun_out/launches_r01.csv  > profiles/r01_launches.md
     python tools/ncu_summary.py kernel   gpurun_out/prof_X.ncu-rep    > profiles/r01_X.md
+    python tools/ncu_summary.py traffic  gpurun_out/prof_X.ncu-rep profiles/r02_X.md lo  # records the capture's DRAM bytes in
+                                                            # profiles/traffic.json under "<kernel>|lo" (bench.py reads it)
 """
 import collections
 import csv
@@ -68,5 +70,26 @@ def kernel(path):
           ", ".join(f"{m}={'yes' if m in sass else 'no'}" for m in ("UTCHMMA", "LDTM", "UTMALDG", "UTCBAR", "HMMA")))
 
 
+def traffic(path, summary_md, tag):
+    """Add dram__bytes_read + dram__bytes_write of this capture to profiles/traffic.json, keyed by kernel function
+    (template arguments kept: CfgMLP1 and CfgLNRes384 are different kernels of the same engine)."""
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = dict(zip(hdr, zip(vals, units)))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = sum(float(d[k][0]) * scale[d[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    name = re.sub(r"\(.*", "", d["Kernel Name"][0]).replace("void ", "").replace("pg::", "")
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    db = json.load(open(out)) if os.path.exists(out) else {}
+    db[f"{name}|{tag}"] = {"dram_bytes_per_launch": tot, "duration_us": float(d["gpu__time_duration.sum"][0]),
+                "grid": int(float(d["launch__grid_size"][0])), "source": summary_md}
+    with open(out, "w") as fh:
+        json.dump(db, fh, indent=1, sort_keys=True)
+    print(name, tot)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel, "traffic": lambda p: traffic(p, sys.argv[3], sys.argv[4])}[sys.argv[1]](sys.argv[2])
