@@ -130,101 +130,125 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&r)[2]) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// Tail rows 128..143 of a window on mma.sync: key tiles J0 .. J0+NT-1 (8 keys each, NT even) of one 16-row block,
-// flash-style: running row maxima m, per-thread partial sums l and the output accumulators o are rescaled in place.
+// Code size matters here: five roles run different code on every SM sub-partition at the same time, and a fully unrolled
+// version of the two functions below (58 KB of SASS) made instruction fetch the top stall reason of the kernel (ncu:
+// no_inst 21 % of the samples; the instruction cache holds 32 KB).  Both are therefore written as ROLLED loops over
+// key ranges with register-resident pieces of fixed size.
+
+// Tail rows 128..143 of a window on mma.sync, flash-style over three ranges of 48 keys (6 key tiles, 3 K=16 steps):
+// running row maxima m, per-thread partial sums l and the output accumulators o are rescaled in place.
 // Fragment layout as in mma.m16n8k16: this thread holds rows gq (e = 0,1) and gq + 8 (e = 2,3), columns 2*q4 + {0,1}.
-template <bool kFp16, int J0, int NT>
-__device__ __forceinline__ void tail_keys(uint32_t sk, uint32_t sv, const uint32_t (&qa)[2][4], const float* tb0,
-                                          const float* tb1, float (&o)[4][4], float& m0, float& m1, float& l0, float& l1,
-                                          int lane) {
+template <bool kFp16>
+__device__ __forceinline__ void tail_rows(uint32_t sk, uint32_t sv, const uint32_t (&qa)[2][4], const float* tb0,
+                                          const float* tb1, float (&o)[4][4], float& l0, float& l1, int lane) {
   constexpr float kLog2e = 1.4426950408889634f;
-  float s[NT][4];
+  constexpr int NT = 6;
+  float m0 = -INFINITY, m1 = -INFINITY;
+  l0 = l1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    uint32_t b0, b1, b2, b3;
-    ldsm_x4(sk + att_off(8 * (J0 + j) + (lane & 7), lane >> 3), b0, b1, b2, b3);
-    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-    mma16816<kFp16>(s[j], qa[0], b0, b1);
-    mma16816<kFp16>(s[j], qa[1], b2, b3);
-  }
-  float x0 = -INFINITY, x1 = -INFINITY;
+  for (int n = 0; n < 4; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+#pragma unroll 1
+  for (int j0 = 0; j0 < 18; j0 += NT) {
+    float s[NT][4];
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    const float2 lo = *reinterpret_cast<const float2*>(tb0 + 8 * (J0 + j));
-    const float2 hi = *reinterpret_cast<const float2*>(tb1 + 8 * (J0 + j));
-    s[j][0] = fmaf(s[j][0], kLog2e, lo.x); s[j][1] = fmaf(s[j][1], kLog2e, lo.y);
-    s[j][2] = fmaf(s[j][2], kLog2e, hi.x); s[j][3] = fmaf(s[j][3], kLog2e, hi.y);
-    x0 = max3(x0, s[j][0], s[j][1]);
-    x1 = max3(x1, s[j][2], s[j][3]);
-  }
-  x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
-  x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
-  const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
-  const float c0 = fast_exp2(m0 - n0), c1 = fast_exp2(m1 - n1);      // first range: m = -inf -> factor 0 on zeros
-  m0 = n0; m1 = n1;
-  float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    s[j][0] = fast_exp2(s[j][0] - n0); s[j][1] = fast_exp2(s[j][1] - n0);
-    s[j][2] = fast_exp2(s[j][2] - n1); s[j][3] = fast_exp2(s[j][3] - n1);
-    p0 += s[j][0] + s[j][1];
-    p1 += s[j][2] + s[j][3];
-  }
-  l0 = fmaf(l0, c0, p0);
-  l1 = fmaf(l1, c1, p1);
-#pragma unroll
-  for (int n = 0; n < 4; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
-#pragma unroll
-  for (int kk = 0; kk < NT / 2; ++kk) {
-    uint32_t pa[4];
-    pa[0] = pack16<kFp16>(s[2 * kk][0], s[2 * kk][1]);
-    pa[1] = pack16<kFp16>(s[2 * kk][2], s[2 * kk][3]);
-    pa[2] = pack16<kFp16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    pa[3] = pack16<kFp16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-    for (int np = 0; np < 2; ++np) {
+    for (int j = 0; j < NT; ++j) {
       uint32_t b0, b1, b2, b3;
-      ldsm_x4_t(sv + att_off(8 * J0 + 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * np + (lane >> 4)), b0, b1, b2, b3);
-      mma16816<kFp16>(o[2 * np], pa, b0, b1);
-      mma16816<kFp16>(o[2 * np + 1], pa, b2, b3);
+      ldsm_x4(sk + att_off(8 * (j0 + j) + (lane & 7), lane >> 3), b0, b1, b2, b3);
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      mma16816<kFp16>(s[j], qa[0], b0, b1);
+      mma16816<kFp16>(s[j], qa[1], b2, b3);
+    }
+    float x0 = -INFINITY, x1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const float2 lo = *reinterpret_cast<const float2*>(tb0 + 8 * (j0 + j));
+      const float2 hi = *reinterpret_cast<const float2*>(tb1 + 8 * (j0 + j));
+      s[j][0] = fmaf(s[j][0], kLog2e, lo.x); s[j][1] = fmaf(s[j][1], kLog2e, lo.y);
+      s[j][2] = fmaf(s[j][2], kLog2e, hi.x); s[j][3] = fmaf(s[j][3], kLog2e, hi.y);
+      x0 = max3(x0, s[j][0], s[j][1]);
+      x1 = max3(x1, s[j][2], s[j][3]);
+    }
+    x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+    x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+    const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
+    const float c0 = fast_exp2(m0 - n0), c1 = fast_exp2(m1 - n1);      // first range: m = -inf -> factor 0 on zeros
+    m0 = n0; m1 = n1;
+    float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      s[j][0] = fast_exp2(s[j][0] - n0); s[j][1] = fast_exp2(s[j][1] - n0);
+      s[j][2] = fast_exp2(s[j][2] - n1); s[j][3] = fast_exp2(s[j][3] - n1);
+      p0 += s[j][0] + s[j][1];
+      p1 += s[j][2] + s[j][3];
+    }
+    l0 = fmaf(l0, c0, p0);
+    l1 = fmaf(l1, c1, p1);
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack16<kFp16>(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack16<kFp16>(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack16<kFp16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack16<kFp16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(sv + att_off(8 * j0 + 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * np + (lane >> 4)), b0, b1, b2, b3);
+        mma16816<kFp16>(o[2 * np], pa, b0, b1);
+        mma16816<kFp16>(o[2 * np + 1], pa, b2, b3);
+      }
     }
   }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
 }
 
-// Softmax of one query row over the key range [COL0, COL0 + NK) (NK = 80 or 64: a whole number of 16-key MMA steps).
-// s_base / bias_base: TMEM addresses (lane of this row) of column 0 of the score buffer and of the resident bias' tile.
-// Returns this range's sum of exp2(y - m); P is left, packed 16-bit, in columns [COL0, COL0 + NK/2) of the score buffer.
-template <bool kFp16, int NK, int COL0, class Trace>
-__device__ __forceinline__ float softmax_half(uint32_t s_base, uint32_t bias_base, uint16_t* xm, int half, int pair_bar,
-                                              Trace&& trace) {
-  constexpr int NC = NK / 16;
+// Softmax of one query row over the nc * 16 keys that start at column col0 (nc = 5, col0 = 0 or nc = 4, col0 = 80: whole
+// 16-key MMA steps).  s_base / bias_base: TMEM addresses (lane of this row) of column 0 of the score buffer and of the
+// resident bias' tile.  Returns this range's sum of exp2(y - m); P is left, packed 16-bit, in columns
+// [col0, col0 + 8 nc) of the score buffer.  Pieces of 16 columns alternate between two register buffers (A, B): piece
+// p + 1 is in flight while piece p is processed.
+template <bool kFp16, class Trace>
+__device__ __forceinline__ float softmax_keys(uint32_t s_base, uint32_t bias_base, uint16_t* xm, int half, int pair_bar,
+                                              int col0, int nc, Trace&& trace) {
   constexpr float kLog2e = 1.4426950408889634f;
   const f32x2 l2e2 = pack2(kLog2e, kLog2e);
-  uint32_t sa[2][16], ba[2][16];
-  // ---- pass 1: row maximum of y = S*log2e + bias' over this key range (piece p+1 in flight while piece p is reduced)
-  tmem_ld16(s_base + COL0, sa[0]);
-  tmem_ld16(bias_base + COL0, ba[0]);
-  tmem_ld_wait();
+  const uint32_t sp = s_base + col0, bp = bias_base + col0;
+  uint32_t sa[16], ba[16], sb[16], bb[16];
+  // ---- pass 1: row maximum of y = S*log2e + bias' over this key range
   float pm = -INFINITY;
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int cur = c & 1;
-    if (c + 1 < NC) {
-      tmem_ld16(s_base + COL0 + 16 * (c + 1), sa[cur ^ 1]);
-      tmem_ld16(bias_base + COL0 + 16 * (c + 1), ba[cur ^ 1]);
-    } else {                 // first piece of pass 2: in flight across the row-maximum exchange
-      tmem_ld16(s_base + COL0, sa[cur ^ 1]);
-      tmem_ld16(bias_base + COL0, ba[cur ^ 1]);
-    }
+  auto reduce = [&](const uint32_t (&sx)[16], const uint32_t (&bx)[16]) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float a0, a1;
-      unpack2(fma2(pack2(__uint_as_float(sa[cur][2 * e]), __uint_as_float(sa[cur][2 * e + 1])), l2e2,
-                   pack2(__uint_as_float(ba[cur][2 * e]), __uint_as_float(ba[cur][2 * e + 1]))), a0, a1);
+      unpack2(fma2(pack2(__uint_as_float(sx[2 * e]), __uint_as_float(sx[2 * e + 1])), l2e2,
+                   pack2(__uint_as_float(bx[2 * e]), __uint_as_float(bx[2 * e + 1]))), a0, a1);
       pm = max3(pm, a0, a1);
     }
-    if (c + 1 < NC) tmem_ld_wait();
+  };
+  tmem_ld16(sp, sa);
+  tmem_ld16(bp, ba);
+  tmem_ld_wait();
+  int c = 0;
+#pragma unroll 1
+  for (; c + 2 <= nc; c += 2) {
+    tmem_ld16(sp + 16 * (c + 1), sb);
+    tmem_ld16(bp + 16 * (c + 1), bb);
+    reduce(sa, ba);
+    tmem_ld_wait();
+    if (c + 2 < nc) {
+      tmem_ld16(sp + 16 * (c + 2), sa);
+      tmem_ld16(bp + 16 * (c + 2), ba);
+    }
+    reduce(sb, bb);
+    tmem_ld_wait();
   }
+  if (c < nc) reduce(sa, ba);
+  // first piece of pass 2: in flight across the row-maximum exchange
+  tmem_ld16(sp, sa);
+  tmem_ld16(bp, ba);
   // ---- meet the other key range of this row: any common stabiliser >= max - small is exact for softmax, so the two
   //      maxima travel as bf16 (p <= 2^(|m| 2^-8)) through a 4-byte mailbox and both threads use the same value
   trace(0);
@@ -238,28 +262,40 @@ __device__ __forceinline__ float softmax_half(uint32_t s_base, uint32_t bias_bas
   //      range, which this thread consumed in piece p/2 <= p
   const f32x2 negm2 = pack2(-pm, -pm);
   f32x2 lsum = pack2(0.f, 0.f);
-  tmem_ld_wait();
-  trace(1);
-  constexpr int first = NC & 1;        // buffer that holds piece 0 of pass 2
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int cur = (c + first) & 1;
-    if (c + 1 < NC) {
-      tmem_ld16(s_base + COL0 + 16 * (c + 1), sa[cur ^ 1]);
-      tmem_ld16(bias_base + COL0 + 16 * (c + 1), ba[cur ^ 1]);
-    }
-    uint32_t pk[8];
+  auto expo = [&](const uint32_t (&sx)[16], const uint32_t (&bx)[16], uint32_t (&pk)[8]) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float a0, a1;
-      unpack2(fma2(pack2(__uint_as_float(sa[cur][2 * e]), __uint_as_float(sa[cur][2 * e + 1])), l2e2,
-                   add2(pack2(__uint_as_float(ba[cur][2 * e]), __uint_as_float(ba[cur][2 * e + 1])), negm2)), a0, a1);
+      unpack2(fma2(pack2(__uint_as_float(sx[2 * e]), __uint_as_float(sx[2 * e + 1])), l2e2,
+                   add2(pack2(__uint_as_float(bx[2 * e]), __uint_as_float(bx[2 * e + 1])), negm2)), a0, a1);
       const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
       lsum = add2(lsum, pack2(p0, p1));
       pk[e] = pack16<kFp16>(p0, p1);
     }
-    if (c + 1 < NC) tmem_ld_wait();      // piece c+1 is in registers before any score column is overwritten
-    tmem_st8(s_base + COL0 + 8 * c, pk);
+  };
+  tmem_ld_wait();
+  trace(1);
+  c = 0;
+#pragma unroll 1
+  for (; c + 2 <= nc; c += 2) {
+    uint32_t pk[8];
+    tmem_ld16(sp + 16 * (c + 1), sb);
+    tmem_ld16(bp + 16 * (c + 1), bb);
+    expo(sa, ba, pk);
+    tmem_ld_wait();                     // piece c+1 is in registers before any score column is overwritten
+    tmem_st8(sp + 8 * c, pk);
+    if (c + 2 < nc) {
+      tmem_ld16(sp + 16 * (c + 2), sa);
+      tmem_ld16(bp + 16 * (c + 2), ba);
+    }
+    expo(sb, bb, pk);
+    tmem_ld_wait();
+    tmem_st8(sp + 8 * (c + 1), pk);
+  }
+  if (c < nc) {
+    uint32_t pk[8];
+    expo(sa, ba, pk);
+    tmem_st8(sp + 8 * c, pk);
   }
   trace(2);
   float a0, a1;
@@ -280,12 +316,14 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   uint8_t* misc = smem + ATC_STAGES * ATC_STAGE_BYTES + ATC_TB_BYTES + ATC_XM_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);      // [ATC_STAGES]  TMA bytes landed
   uint64_t* empty_bar = full_bar + ATC_STAGES;                 // [ATC_STAGES]  count 2 (window: PV commit + tail warp;
-                                                               //                        bias: softmax group + tail group)
+                                                               //                        bias: MMA warp for the softmax warps + tail group)
   uint64_t* sfull_bar = empty_bar + ATC_STAGES;                // [2]  S ready in TMEM
   uint64_t* pfull_bar = sfull_bar + 2;                         // [2]  P written (the 256 softmax threads)
   uint64_t* ofull_bar = pfull_bar + 2;                         // [2]  O ready
   uint64_t* oempty_bar = ofull_bar + 2;                        // [2]  O read out (the 256 softmax threads)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oempty_bar + 2);
+  uint64_t* sbias_bar = oempty_bar + 2;                        // [1]  a segment's bias tile has been read out of the ring by all
+                                                               //      8 softmax warps (the MMA warp then frees the 3 slots for them)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sbias_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -297,6 +335,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
       mbar_init(&sfull_bar[b], 1); mbar_init(&pfull_bar[b], 256);
       mbar_init(&ofull_bar[b], 1); mbar_init(&oempty_bar[b], 256);
     }
+    mbar_init(sbias_bar, 8);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -374,8 +413,19 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
       }
     };
     Cur cs{0, 0, min(a.nLon - lw_first, nunits), 3}, cp{0, 3, cs.rem, 0};
+    // third cursor: segments whose bias slots are still to be handed back to the producer on behalf of the softmax warps
+    int br_seg = 0, br_q = 0, br_left = nunits, br_win = cs.rem;
+    auto release_bias = [&]() {
+      if (lane < 3) mbar_arrive(&empty_bar[(br_q + lane) % ATC_STAGES]);
+      __syncwarp();
+      br_q += 3 + br_win; br_left -= br_win; br_win = min(a.nLon, br_left); ++br_seg;
+    };
     while (cp.g < nunits) {
       bool progress = false;
+      if (br_left > 0 && __any_sync(0xffffffffu, mbar_test_wait(sbias_bar, br_seg & 1))) {
+        release_bias();
+        progress = true;
+      }
       if (cs.g < nunits && cs.bias > 0) {
         if (__any_sync(0xffffffffu, mbar_test_wait(&full_bar[cs.q % ATC_STAGES], (cs.q / ATC_STAGES) & 1))) {
           ++cs.q; --cs.bias;
@@ -421,6 +471,10 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         }
       }
       if (!progress) __nanosleep(40);
+    }
+    while (br_left > 0) {          // (every segment's tile was staged before its first P, so these are already complete)
+      mbar_wait(sbias_bar, br_seg & 1);
+      release_bias();
     }
   } else {
     // ============================== tail + softmax warps: walk the segments ==============================
@@ -495,16 +549,10 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) ldsm_x4(sq + att_off(r, ks * 2 + (lane >> 4)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
           }
-          // keys in two ranges ([0,80) and [80,144): whole K=16 steps) with a running maximum, so that only 40 scores
-          // are live at a time: the tail warps share the 128-register budget with everybody else
-          float o[4][4];
-#pragma unroll
-          for (int n = 0; n < 4; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
-          float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-          tail_keys<kFp16, 0, 10>(sk, sv, qa, tb0, tb1, o, m0, m1, l0, l1, lane);
-          tail_keys<kFp16, 10, 8>(sk, sv, qa, tb0, tb1, o, m0, m1, l0, l1, lane);
-          l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-          l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+          // three ranges of 48 keys with a running maximum: 24 scores live at a time (the tail warps share the
+          // 128-register budget with everybody else) and ONE copy of the code
+          float o[4][4], l0, l1;
+          tail_rows<kFp16>(sk, sv, qa, tb0, tb1, o, l0, l1, lane);
           const float i0 = 1.0f / l0, i1 = 1.0f / l1;
           // stage O in this window's Q rows 128..143 (not read by the M=128 MMA), then 64 B stores
           __syncwarp();
@@ -541,9 +589,11 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         const uint32_t lane_addr = tmem + (uint32_t(quad * 32) << 16);
         const int pair_bar = 3 + quad;           // named barrier of the two warps that share this lane quadrant
 
-        // ---- segment start: bias tile -> TMEM (each half moves boxes half, half+2, ... of its rows)
+        // ---- segment start: bias tile -> TMEM.  The 32 bias rows of a lane quadrant are read and written only by the two
+        //      warps of that quadrant, so the pair barrier is all the synchronisation the overwrite needs; the ring slots
+        //      are handed back by the MMA warp once all 8 warps have signalled sbias_bar.
         TR(6, seg, 0, threadIdx.x == 256);
-        named_bar_sync(1, 256);                  // every softmax thread has finished the bias reads of the previous segment
+        named_bar_sync(pair_bar, 64);            // both warps of the quadrant are done with the previous segment's bias rows
 #pragma unroll
         for (int j = 0; j < 3; ++j) mbar_wait(&full_bar[(qb + j) % ATC_STAGES], ((qb + j) / ATC_STAGES) & 1);
 #pragma unroll 1
@@ -559,15 +609,26 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           }
           tmem_st16(lane_addr + ATC_COL_BIAS + 16 * p, v);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sbias_bar);   // this warp has read its share of the tile out of the ring
         tmem_st_wait();
         tc_fence_before();
-        named_bar_sync(1, 256);                  // the other half's boxes of every bias row are in TMEM too
+        named_bar_sync(pair_bar, 64);            // the partner's boxes of these rows are in TMEM too
         tc_fence_after();
-        if (threadIdx.x >= 256 && threadIdx.x < 259) mbar_arrive(&empty_bar[(qb + threadIdx.x - 256) % ATC_STAGES]);
         TR(6, seg, 1, threadIdx.x == 256);
 
+        // Output row of this thread's query row in window lw0 + j: base + off_j rows, off advancing by a fixed step per
+        // window (natural order: 12 longitudes with wrap-around at W; window order: one window of rows) -- no divisions
+        // in the per-window epilogue.
         const int my_base = row_base(r);
-        auto epilogue = [&](int j) {               // j: window index inside the segment; this thread stores 16 of the 32 channels
+        const bool keep = !a.natural || my_base >= 0;     // false: zero pad row of the window, its output is cropped away
+        const size_t rowb = size_t(a.C) * 2;
+        uint8_t* const obase = reinterpret_cast<uint8_t*>(a.out) + head * 64 + 32 * half +
+                               (a.natural ? size_t(my_base < 0 ? 0 : my_base) : size_t(t) * ATT_TOK + r) * rowb;
+        const int ostep = a.natural ? 12 : a.types * ATT_TOK;
+        const int owrap = a.natural ? a.W : 0x7fffffff;
+        int ooff = a.natural ? (12 * lw0 + (r % 12) + (a.roll ? 6 : 0)) % a.W : lw0 * a.types * ATT_TOK;
+        auto epilogue = [&](int j) {               // windows are finished in order j = 0, 1, ...; this thread stores 16 of the 32 channels
           const int g = gbase + j, b = g & 1;
           mbar_wait(&ofull_bar[b], (g >> 1) & 1);
           tc_fence_after();
@@ -577,10 +638,12 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(&oempty_bar[b]);
-          const int orow = out_row(my_base, r, lw0 + j);
-          if (orow < 0) return;                   // zero pad row of the window: its output is cropped away
-          const float inv = 1.0f / (__uint_as_float(ls[0]) + __uint_as_float(ls[1]));
-          uint8_t* dst = reinterpret_cast<uint8_t*>(a.out) + size_t(orow) * (size_t(a.C) * 2) + head * 64 + 32 * half;
+          uint8_t* dst = obase + size_t(ooff) * rowb;
+          ooff += ostep;
+          ooff = ooff >= owrap ? ooff - owrap : ooff;
+          if (!keep) return;
+          float inv;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__uint_as_float(ls[0]) + __uint_as_float(ls[1])));
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             uint4 v;
@@ -604,8 +667,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           // (keys [0,80)); 5 = [pass 1 done, max exchanged, pass 2 done, epilogue done] of its partner warp 12 (keys [80,144))
           auto tr0 = [&](int ev) { TR(ev < 2 ? 3 : 4, g, ev < 2 ? ev + 2 : 0, r == 0); };
           auto tr1 = [&](int ev) { TR(5, g, ev, r == 0); };
-          const float l = half == 0 ? softmax_half<kFp16, 80, 0>(s_base, lane_addr + ATC_COL_BIAS, xm, 0, pair_bar, tr0)
-                                    : softmax_half<kFp16, 64, 80>(s_base, lane_addr + ATC_COL_BIAS, xm, 1, pair_bar, tr1);
+          auto tr = [&](int ev) { if (half == 0) tr0(ev); else tr1(ev); };
+          const float l = softmax_keys<kFp16>(s_base, lane_addr + ATC_COL_BIAS, xm, half, pair_bar, half ? 80 : 0, half ? 4 : 5, tr);
           tmem_st1(lane_addr + ATC_COL_L + 2 * b + half, __float_as_uint(l));
           tmem_st_wait();
           tc_fence_before();

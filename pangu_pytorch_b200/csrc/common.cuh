@@ -76,10 +76,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     ++spins;
+#ifdef PANGU_DEV_SWITCHES      // development builds: say who is stuck (the printf marshalling costs ~35 instructions per call site)
     if (spins == PANGU_SPIN_LIMIT && (blockIdx.x == 5 || threadIdx.x == 0))      // report, keep spinning so that every stuck role gets to report, then trap
       printf("pangu_b200: mbarrier timeout block %d thread %d smem 0x%x parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
-    if (spins > PANGU_SPIN_LIMIT + (PANGU_SPIN_LIMIT >> 1)) __trap();
+#endif
+    if (spins > PANGU_SPIN_LIMIT + (PANGU_SPIN_LIMIT >> 1)) __trap();      // a mis-counted barrier must not hang the GPU
   }
 }
 
