@@ -37,7 +37,6 @@ UNIT = "steps/s"
 FLOPS_PER_STEP = 8.4212e12          # dense-contraction FLOPs of one forward
 FLOPS_BLOCKS = 8.1325e12            # attention + MLP of the 16 blocks
 LAT, LON = 721, 1440
-TRAIN_OPERANDS = "bf16"             # operand format of the secondary finetune / lora steps
 LORA_DROPOUT = 0.0                  # lora_tune's adapter dropout in the secondary record
 STRIP = 96                          # fallback CPU sample (only if oracle/_ref is absent): 96-column strip, 1/15 of the grid
 WORKLOAD = ("PanguModel 24h forward, 0.25deg (upper 5x13x721x1440, surface 4x721x1440), batch 1, random-init weights; "
@@ -479,8 +478,8 @@ def run_secondary(args, model, dev, rank, world, maps, const_h, stats):
     tu = torch.randn(1, 5, 13, LAT, LON, device=dev, generator=gk)
     ts = torch.randn(1, 4, LAT, LON, device=dev, generator=gk)
     steps = 3
+    train_fmt = pb.training_operand_dtype()          # the training path's own default (fp16 + loss scale 2^16)
     for name in ("finetune", "lora"):
-        pb.set_operand_dtype(TRAIN_OPERANDS)
         torch.manual_seed(0)
         m = pb.PanguModel(device=dev).to(dev)
         if name == "lora":          # finetune/lora_tune.py:124-139: r=16, alpha=16, dropout 0.1, output convs trained in full
@@ -516,7 +515,7 @@ def run_secondary(args, model, dev, rank, world, maps, const_h, stats):
         per = float(t[0]) / steps
         out[name] = {"metric": f"{name} steps/s @0.25deg (fwd + weighted-L1 + bwd + grad mean + fused Adam)",
                      "value": round(world * 1e3 / per, 3), "unit": "steps/s", "ms_per_step": round(per, 2), "steps": steps,
-                     "warmup": 2, "dtype": TRAIN_OPERANDS, "loss": float(loss),
+                     "warmup": 2, "dtype": train_fmt, "loss": float(loss),
                      "tflops": round(3 * FLOPS_PER_STEP / (per * 1e-3) / 1e12, 1),
                      "config": ("lora_tune: r=16 adapters on the 67 nn.Linear, lora_dropout %.1f, output convs trained in full" % LORA_DROPOUT
                                 if name == "lora" else "finetune_fully: all 223 tensors") +
@@ -552,6 +551,7 @@ def run_train_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pb.set_operand_dtype(args.operands)
+    pb.set_training_operand_dtype(args.operands)
 
     def barrier():
         if world > 1:
@@ -633,13 +633,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--operands", default=os.environ.get("PANGU_B200_OPERANDS", "bf16"), choices=["bf16", "fp16"])
+    ap.add_argument("--operands", default=None, choices=["bf16", "fp16"],
+                    help="16-bit operand format (default: bf16 for the forecast, the training path's default -- fp16 -- for train / lora)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short finetune / lora steps of the `secondary` record")
     ap.add_argument("--workload", default="forecast", choices=["forecast", "train", "lora"],
                     help="forecast: the BASELINE.json headline (default); train: finetune_fully step (configs[3]); "
                          "lora: lora_tune step (configs[4])")
     args = ap.parse_args()
+    if args.operands is None:
+        if args.workload == "forecast":
+            args.operands = os.environ.get("PANGU_B200_OPERANDS", "bf16")
+        else:
+            args.operands = os.environ.get("PANGU_B200_TRAIN_OPERANDS", "fp16")
     if args.impl == "reference":
         run_reference_arm(args)
     elif args.workload in ("train", "lora"):

@@ -16,8 +16,8 @@
 // Per window:
 //
 //   S[128x144] = Q[0:128] K^T          tcgen05.mma, A/B from smem (K-major), fp32 accum in TMEM
-//   pass 1:  m = max_j (S*log2e + bias')   streamed from TMEM in 16-column pieces, nothing written back
-//   pass 2:  P = exp2(S*log2e + bias' - m) packed 16-bit, written over S columns the thread has already consumed
+//   max warp:  m = max_j (S*log2e + bias')   streamed from TMEM in 16-column pieces, nothing written back
+//   exp warp:  P = exp2(S*log2e + bias' - m) packed 16-bit, written over S columns the thread has already consumed
 //   O[128x32]  = P V                   tcgen05.mma, A = P from TMEM, B = V from smem (MN-major)
 //   rows 128..143 (144 = 128 + 16 does not fit an MMA M) are done by mma.sync "tail" warps that
 //   read the same smem tiles (the SWIZZLE_64B pattern equals the ldmatrix-friendly XOR swizzle).
@@ -25,30 +25,31 @@
 // qkv is stored head-major by the QKV GEMM ([3*heads planes][Tp_pad rows][32]), so every Q/K/V tile is
 // one contiguous 9 KB burst in HBM.
 // TMEM (512 columns = the whole SM, so the allocation starts at address 0):
-//   [0,144) bias' | [144,288) S0/P0 | [288,432) S1/P1 | [432,464) O0 | [464,496) O1 | [496,500) row sums l (buffer, half).
+//   [0,144) bias' | [144,288) S0/P0 | [288,432) S1/P1 | [432,464) O0 | [464,496) O1 | [496,498) row sums l (one per S buffer).
 // S of window g+2 is queued right behind PV of window g (the tensor pipe executes in issue order, so PV
 // has read P before the next S overwrites it).  The MMA warp runs converged with warp-uniform operands
 // (only the tcgen05 instructions are elected) and polls "next S" / "next PV" without blocking on either.
-// Warps (512 threads): 0 TMA producer, 1 MMA issuer, 2-7 tail warps (ring stage s belongs to warp 2 + s%6),
-// 8-15 softmax: all eight on every window; thread = (query row = TMEM lane, key range), warps w and w+4 share a TMEM lane
-// quadrant and split the row: keys [0,80) and [80,144).  Each range is a whole number of K=16 steps of the PV MMA, so each
-// thread writes its P over its OWN score columns ([0,40) resp. [80,112)) and the two never touch the other's columns.
+// Warps (448 threads): 0 TMA producer, 1 MMA issuer, 2-5 tail warps (ring stage s belongs to warp 2 + s%4: ONE tail warp per
+// SM sub-partition -- with six, two sub-partitions hosted two tail warps each and their exp warps ran 1.5-2x slower than
+// the others, which set the pace of the whole CTA), 6-9 "exp" warps, 10-13 "max" warps
+// (see softmax_row_max / softmax_row_exp; warps w and w + 4 own TMEM lane quadrant w % 4): thread = one query row (TMEM lane).
 // Measured on B200 (tools/tmem_bench.cu): a dependent tcgen05.ld + wait costs ~38 clk and 8 warps read ~1 KB/clk, so
-// re-reading S and bias' in pass 2 is cheap; what is NOT cheap is a register spill: with 232 KB of shared memory there is
-// no L1 left and every spill reload is an L2 round trip (a 72-keys-in-registers variant spilled 13 words and ran 20 % slower).
+// re-reading S and bias' in the exp pass is cheap; what is NOT cheap is (a) a register spill: with 232 KB of shared memory
+// there is no L1 left and every spill reload is an L2 round trip, (b) code size: see the note above tail_rows.
 #pragma once
 #include "attention.cuh"
 
 namespace pg {
 
-constexpr int ATC_THREADS = 512;
+constexpr int ATC_THREADS = 448;
+constexpr int ATC_SOFT_WARP0 = 6;                                // first exp warp (6..9), then the max warps (10..13)
 constexpr int ATC_STAGES = 8;
-constexpr int ATC_TAIL_WARPS = 6;                                // warps 2..7: ring stage s belongs to tail warp 2 + s % 6, so
+constexpr int ATC_TAIL_WARPS = 4;                                // warps 2..5: ring stage s belongs to tail warp 2 + s % 4 (two stages each), so
                                                                  // every phase of a stage's mbarriers is seen by one warp, in order
 constexpr int ATC_STAGE_BYTES = ATT_BUF_BYTES;                   // 27648: Q, K, V tiles (or 3 bias boxes) of 9216 B
 constexpr int ATC_TB_PITCH = 148;                                // floats per row of the tail bias tile in smem
 constexpr int ATC_TB_BYTES = 16 * ATC_TB_PITCH * 4;              // rows 128..143
-constexpr int ATC_XM_BYTES = 2 * 128 * 2 * 2;                    // row-maximum mailbox: [S buffer][row][key half] bf16
+constexpr int ATC_XM_BYTES = 2 * 128 * 4;                        // row-maximum mailbox: [S buffer][row] fp32 (max warp -> exp warp)
 constexpr int ATC_SMEM_BYTES = ATC_STAGES * ATC_STAGE_BYTES + ATC_TB_BYTES + ATC_XM_BYTES + 256;   // base is 1024 B aligned (checked)
 constexpr uint32_t ATC_COL_BIAS = 0, ATC_COL_S = 144, ATC_COL_O = 432, ATC_COL_L = 496;
 static_assert(ATC_SMEM_BYTES <= 232448, "attention shared memory budget");
@@ -124,6 +125,9 @@ __device__ __forceinline__ void tmem_ld8p(uint32_t taddr, uint32_t* r) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr)
                : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t (&r)[1]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&r)[2]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
@@ -205,101 +209,144 @@ __device__ __forceinline__ void tail_rows(uint32_t sk, uint32_t sv, const uint32
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
 }
 
-// Softmax of one query row over the nc * 16 keys that start at column col0 (nc = 5, col0 = 0 or nc = 4, col0 = 80: whole
-// 16-key MMA steps).  s_base / bias_base: TMEM addresses (lane of this row) of column 0 of the score buffer and of the
-// resident bias' tile.  Returns this range's sum of exp2(y - m); P is left, packed 16-bit, in columns
-// [col0, col0 + 8 nc) of the score buffer.  Pieces of 16 columns alternate between two register buffers (A, B): piece
-// p + 1 is in flight while piece p is processed.
-template <bool kFp16, class Trace>
-__device__ __forceinline__ float softmax_keys(uint32_t s_base, uint32_t bias_base, uint16_t* xm, int half, int pair_bar,
-                                              int col0, int nc, Trace&& trace) {
+// order-pinned variants of the packed-math helpers (volatile asm keeps their relative program order through nvcc / ptxas)
+__device__ __forceinline__ f32x2 vfma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 vadd2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float vex2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool kFp16>
+__device__ __forceinline__ uint32_t vpack16(float a, float b) {
+  uint32_t r;
+  if constexpr (kFp16) {
+    asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  } else {
+    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  }
+  return r;
+}
+
+// The softmax of a window is split by ROLE between the two warps that own a TMEM lane quadrant (they share an SM
+// sub-partition, i.e. one MUFU and one issue port): the "max" warp computes the row maximum of window g+1 (FMA / ALU work)
+// while the "exp" warp turns window g into probabilities (MUFU work).  With both warps running the same phase of the same
+// window (key-split variants of this kernel) the MUFU sat idle during the max / epilogue phases and was oversubscribed
+// during the exp phase: 3 600 clk per window against a MUFU bound of 1 300.
+// Both functions stream the 144 score columns of one query row (TMEM lane) and the matching columns of the resident
+// bias' tile in 16-column pieces through two register buffers (piece p + 1 in flight while piece p is processed), as
+// ROLLED loops: five roles run different code on every sub-partition and the instruction cache holds 32 KB.
+
+// row maximum of y = S*log2e + bias' over the 144 keys
+__device__ __forceinline__ float softmax_row_max(uint32_t sp, uint32_t bp) {
   constexpr float kLog2e = 1.4426950408889634f;
   const f32x2 l2e2 = pack2(kLog2e, kLog2e);
-  const uint32_t sp = s_base + col0, bp = bias_base + col0;
   uint32_t sa[16], ba[16], sb[16], bb[16];
-  // ---- pass 1: row maximum of y = S*log2e + bias' over this key range
-  float pm = -INFINITY;
+  float m0 = -INFINITY, m1 = -INFINITY;        // two chains: the reduction is latency bound
   auto reduce = [&](const uint32_t (&sx)[16], const uint32_t (&bx)[16]) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float a0, a1;
+    for (int e = 0; e < 8; e += 2) {
+      float a0, a1, a2, a3;
       unpack2(fma2(pack2(__uint_as_float(sx[2 * e]), __uint_as_float(sx[2 * e + 1])), l2e2,
                    pack2(__uint_as_float(bx[2 * e]), __uint_as_float(bx[2 * e + 1]))), a0, a1);
-      pm = max3(pm, a0, a1);
+      unpack2(fma2(pack2(__uint_as_float(sx[2 * e + 2]), __uint_as_float(sx[2 * e + 3])), l2e2,
+                   pack2(__uint_as_float(bx[2 * e + 2]), __uint_as_float(bx[2 * e + 3]))), a2, a3);
+      m0 = max3(m0, a0, a1);
+      m1 = max3(m1, a2, a3);
     }
   };
   tmem_ld16(sp, sa);
   tmem_ld16(bp, ba);
   tmem_ld_wait();
-  int c = 0;
 #pragma unroll 1
-  for (; c + 2 <= nc; c += 2) {
+  for (int c = 0; c < 8; c += 2) {             // pieces 0..7 in pairs, piece 8 after the loop
     tmem_ld16(sp + 16 * (c + 1), sb);
     tmem_ld16(bp + 16 * (c + 1), bb);
     reduce(sa, ba);
     tmem_ld_wait();
-    if (c + 2 < nc) {
-      tmem_ld16(sp + 16 * (c + 2), sa);
-      tmem_ld16(bp + 16 * (c + 2), ba);
-    }
+    tmem_ld16(sp + 16 * (c + 2), sa);
+    tmem_ld16(bp + 16 * (c + 2), ba);
     reduce(sb, bb);
     tmem_ld_wait();
   }
-  if (c < nc) reduce(sa, ba);
-  // first piece of pass 2: in flight across the row-maximum exchange
-  tmem_ld16(sp, sa);
-  tmem_ld16(bp, ba);
-  // ---- meet the other key range of this row: any common stabiliser >= max - small is exact for softmax, so the two
-  //      maxima travel as bf16 (p <= 2^(|m| 2^-8)) through a 4-byte mailbox and both threads use the same value
-  trace(0);
-  xm[half] = __bfloat16_as_ushort(__float2bfloat16_rn(pm));
-  named_bar_sync(pair_bar, 64);
-  {
-    const uint32_t both = *reinterpret_cast<const volatile uint32_t*>(xm);
-    pm = fmaxf(__uint_as_float(both << 16), __uint_as_float(both & 0xFFFF0000u));
-  }
-  // ---- pass 2: P = exp2(y - m) packed 16-bit; piece p of P (8 columns) lands on score columns [8p, 8p+8) of this
-  //      range, which this thread consumed in piece p/2 <= p
-  const f32x2 negm2 = pack2(-pm, -pm);
-  f32x2 lsum = pack2(0.f, 0.f);
+  reduce(sa, ba);
+  return fmaxf(m0, m1);
+}
+
+// P = exp2(y - m), packed 16-bit, written over score columns [0, 72) (piece p of P lands on columns [8p, 8p+8), which
+// this thread consumed in piece p/2 <= p; nobody else reads the row any more); returns the row sum of the unrounded p.
+template <bool kFp16>
+__device__ __forceinline__ float softmax_row_exp(uint32_t sp, uint32_t bp, float m) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  const f32x2 l2e2 = pack2(kLog2e, kLog2e);
+  const f32x2 negm2 = pack2(-m, -m);
+  uint32_t sa[16], ba[16], sb[16], bb[16];
+  f32x2 l0 = pack2(0.f, 0.f), l1 = pack2(0.f, 0.f);
+  // A warp issues in order: sixteen back-to-back MUFU.EX2 (8 clk of the pipe each) followed by the 24 FMA / ALU
+  // instructions of the piece cost 128 + ~80 clk, interleaved they cost ~130 (measured: 2 000 -> clk per window for the
+  // clustered schedule ptxas picked).  The order below is therefore pinned with volatile asm: per pair of keys
+  // MUFU, FADD2 (next pair), MUFU, FFMA2 (next pair), FADD2 (row sum of the previous pair), F2FP (pack previous pair).
   auto expo = [&](const uint32_t (&sx)[16], const uint32_t (&bx)[16], uint32_t (&pk)[8]) {
+    f32x2 t_cur, t_nxt = 0, p_prev = 0;
+    t_cur = vfma2(pack2(__uint_as_float(sx[0]), __uint_as_float(sx[1])), l2e2,
+                  vadd2(pack2(__uint_as_float(bx[0]), __uint_as_float(bx[1])), negm2));
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float a0, a1;
-      unpack2(fma2(pack2(__uint_as_float(sx[2 * e]), __uint_as_float(sx[2 * e + 1])), l2e2,
-                   add2(pack2(__uint_as_float(bx[2 * e]), __uint_as_float(bx[2 * e + 1])), negm2)), a0, a1);
-      const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
-      lsum = add2(lsum, pack2(p0, p1));
-      pk[e] = pack16<kFp16>(p0, p1);
+      unpack2(t_cur, a0, a1);
+      const float p0 = vex2(a0);
+      f32x2 u = 0;
+      if (e + 1 < 8) u = vadd2(pack2(__uint_as_float(bx[2 * e + 2]), __uint_as_float(bx[2 * e + 3])), negm2);
+      const float p1 = vex2(a1);
+      if (e + 1 < 8) t_nxt = vfma2(pack2(__uint_as_float(sx[2 * e + 2]), __uint_as_float(sx[2 * e + 3])), l2e2, u);
+      if (e > 0) {
+        float q0, q1;
+        unpack2(p_prev, q0, q1);
+        if (e & 1) l1 = vadd2(l1, p_prev); else l0 = vadd2(l0, p_prev);
+        pk[e - 1] = vpack16<kFp16>(q0, q1);
+      }
+      p_prev = pack2(p0, p1);
+      t_cur = t_nxt;
+    }
+    {
+      float q0, q1;
+      unpack2(p_prev, q0, q1);
+      l0 = vadd2(l0, p_prev);
+      pk[7] = vpack16<kFp16>(q0, q1);
     }
   };
+  tmem_ld16(sp, sa);
+  tmem_ld16(bp, ba);
   tmem_ld_wait();
-  trace(1);
-  c = 0;
 #pragma unroll 1
-  for (; c + 2 <= nc; c += 2) {
+  for (int c = 0; c < 8; c += 2) {
     uint32_t pk[8];
     tmem_ld16(sp + 16 * (c + 1), sb);
     tmem_ld16(bp + 16 * (c + 1), bb);
     expo(sa, ba, pk);
     tmem_ld_wait();                     // piece c+1 is in registers before any score column is overwritten
     tmem_st8(sp + 8 * c, pk);
-    if (c + 2 < nc) {
-      tmem_ld16(sp + 16 * (c + 2), sa);
-      tmem_ld16(bp + 16 * (c + 2), ba);
-    }
+    tmem_ld16(sp + 16 * (c + 2), sa);
+    tmem_ld16(bp + 16 * (c + 2), ba);
     expo(sb, bb, pk);
     tmem_ld_wait();
     tmem_st8(sp + 8 * (c + 1), pk);
   }
-  if (c < nc) {
+  {
     uint32_t pk[8];
     expo(sa, ba, pk);
-    tmem_st8(sp + 8 * c, pk);
+    tmem_st8(sp + 64, pk);
   }
-  trace(2);
   float a0, a1;
-  unpack2(lsum, a0, a1);
+  unpack2(add2(l0, l1), a0, a1);
   return a0 + a1;
 }
 
@@ -312,18 +359,19 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   uint8_t* smem = atc_raw;
   uint8_t* ring = smem;
   float* s_tbias = reinterpret_cast<float*>(smem + ATC_STAGES * ATC_STAGE_BYTES);     // [16][ATC_TB_PITCH]
-  uint16_t* s_xm = reinterpret_cast<uint16_t*>(smem + ATC_STAGES * ATC_STAGE_BYTES + ATC_TB_BYTES);   // [2][128][2]
+  float* s_xm = reinterpret_cast<float*>(smem + ATC_STAGES * ATC_STAGE_BYTES + ATC_TB_BYTES);   // [2][128]
   uint8_t* misc = smem + ATC_STAGES * ATC_STAGE_BYTES + ATC_TB_BYTES + ATC_XM_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);      // [ATC_STAGES]  TMA bytes landed
   uint64_t* empty_bar = full_bar + ATC_STAGES;                 // [ATC_STAGES]  count 2 (window: PV commit + tail warp;
                                                                //                        bias: MMA warp for the softmax warps + tail group)
   uint64_t* sfull_bar = empty_bar + ATC_STAGES;                // [2]  S ready in TMEM
-  uint64_t* pfull_bar = sfull_bar + 2;                         // [2]  P written (the 256 softmax threads)
+  uint64_t* pfull_bar = sfull_bar + 2;                         // [2]  P written (the 128 threads of the exp warps)
   uint64_t* ofull_bar = pfull_bar + 2;                         // [2]  O ready
-  uint64_t* oempty_bar = ofull_bar + 2;                        // [2]  O read out (the 256 softmax threads)
+  uint64_t* oempty_bar = ofull_bar + 2;                        // [2]  O read out (the 128 threads of the max warps)
   uint64_t* sbias_bar = oempty_bar + 2;                        // [1]  a segment's bias tile has been read out of the ring by all
                                                                //      8 softmax warps (the MMA warp then frees the 3 slots for them)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sbias_bar + 1);
+  uint64_t* mfull_bar = sbias_bar + 1;                         // [2]  row maxima of a window are in the mailbox (128 max-warp threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mfull_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -332,8 +380,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
     tma_prefetch_desc(&tmBias);
     for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&sfull_bar[b], 1); mbar_init(&pfull_bar[b], 256);
-      mbar_init(&ofull_bar[b], 1); mbar_init(&oempty_bar[b], 256);
+      mbar_init(&sfull_bar[b], 1); mbar_init(&pfull_bar[b], 128);
+      mbar_init(&ofull_bar[b], 1); mbar_init(&oempty_bar[b], 128);
+      mbar_init(&mfull_bar[b], 128);
     }
     mbar_init(sbias_bar, 8);
     fence_barrier_init();
@@ -452,15 +501,15 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
       {
         const int st = cp.q % ATC_STAGES, b = cp.g & 1;
         if (__any_sync(0xffffffffu, mbar_test_wait(&pfull_bar[b], (cp.g >> 1) & 1))) {
-          mbar_wait(&oempty_bar[b], ((cp.g >> 1) & 1) ^ 1);   // already true: the owner reads O(g-2) before it writes P(g)
+          mbar_wait(&oempty_bar[b], ((cp.g >> 1) & 1) ^ 1);   // short: the max warps read O(g-2) right after posting the maxima of window g,
+                                                              // which the exp warps needed before they could publish P(g)
           TR(1, cp.g, 2, lane == 0);
           tc_fence_after();
           const uint64_t dv = make_sdesc_sw64(ring_u32 + st * ATC_STAGE_BYTES + 2 * ATT_TILE_BYTES);
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 9; ++kk)   // 144 keys = 9 x K16: P advances 8 TMEM columns, V 16 rows = 1024 B
-              umma_f16_ts(tmem + ATC_COL_O + 32 * b, tmem + ATC_COL_S + 144 * b + (kk < 5 ? 8 * kk : 40 + 8 * kk),
-                          dv + uint64_t(kk * 64), idesc_o, kk);     // P of keys [0,80) at columns [0,40), of keys [80,144) at [80,112)
+              umma_f16_ts(tmem + ATC_COL_O + 32 * b, tmem + ATC_COL_S + 144 * b + 8 * kk, dv + uint64_t(kk * 64), idesc_o, kk);
             umma_commit(&ofull_bar[b]);
             umma_commit(&empty_bar[st]);
           }
@@ -470,7 +519,10 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           progress = true;
         }
       }
-      if (!progress) __nanosleep(40);
+      // Nothing to issue: park on the event that comes next in the steady state (P of window cp.g) instead of spinning.  A
+      // polling loop here costs the exp warp of this sub-partition issue slots: measured 1.5-2x longer exp passes in the
+      // lane quadrant that shares a scheduler with this warp, which set the pace of the CTA.
+      if (!progress) (void)mbar_try_wait_hint(&pfull_bar[cp.g & 1], (cp.g >> 1) & 1, 300);
     }
     while (br_left > 0) {          // (every segment's tile was staged before its first P, so these are already complete)
       mbar_wait(sbias_bar, br_seg & 1);
@@ -513,15 +565,14 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         wp = wp >= a.W ? wp - a.W : wp;
         return base < 0 ? -1 : base + wp;
       };
-      if (warp < 8) {
+      if (warp < ATC_SOFT_WARP0) {
         // ============================== tail warps: rows 128..143 with mma.sync ==============================
-        const int tid = threadIdx.x - 64;        // 0..191
+        const int tid = threadIdx.x - 64;        // 0..127
         named_bar_sync(2, ATC_TAIL_WARPS * 32);  // every tail warp is done with the previous tail bias rows
 #pragma unroll
         for (int j = 0; j < 3; ++j) mbar_wait(&full_bar[(qb + j) % ATC_STAGES], ((qb + j) / ATC_STAGES) & 1);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {            // 16 rows x 36 float4 = 576 pieces over 192 threads
-          const int id = tid + k * (ATC_TAIL_WARPS * 32);
+#pragma unroll 1
+        for (int id = tid; id < 16 * 36; id += ATC_TAIL_WARPS * 32) {      // 16 rows x 36 float4 = 576 pieces
           const int rr = id / 36, c4 = id % 36, ri = 128 + rr, cj = 4 * c4;
           const float4 v = *reinterpret_cast<const float4*>(box_ptr(c4 >> 2) + att_off(ri, c4 & 3));
           const float m = mask_of(ri, cj);
@@ -535,7 +586,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         const int r0 = 128 + gq;
         const float* tb0 = s_tbias + gq * ATC_TB_PITCH + 2 * q4;
         const float* tb1 = tb0 + 8 * ATC_TB_PITCH;
-        // this warp owns the ring stages s with s % 6 == warp - 2: it takes the windows whose slot falls on them
+        // this warp owns the ring stages s with s % 4 == warp - 2: it takes the windows whose slot falls on them
         for (int i = 0; i < nwin; ++i) {
           const int g = gbase + i, q = qb + 3 + i, st = q % ATC_STAGES;
           if (st % ATC_TAIL_WARPS != warp - 2) continue;
@@ -578,22 +629,23 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           if (lane == 0) mbar_arrive(&empty_bar[st]);
         }
       } else {
-        // ============================== softmax + O epilogue (8 warps on every window) ==============================
-        // Warps w and w + 4 share TMEM lane quadrant `quad`; a thread owns one query row (TMEM lane) and one HALF of
-        // its 144 keys: the 72 scores are loaded once and stay in registers from the bias add to the packed P store
-        // (no TMEM write-back of y).  The two halves of a row meet twice: the row maximum goes through a 16-bit
-        // mailbox in shared memory (any common stabiliser >= max - small is exact for softmax; bf16 rounding keeps
-        // p <= 2^(|m| 2^-8)), the row sum through two spare TMEM columns read back with the output accumulator.
-        const int quad = warp & 3, half = (warp - 8) >> 2;
+        // ============================== softmax + O epilogue (8 warps, two roles) ==============================
+        // Warps w (6..9, "exp") and w + 4 (10..13, "max") own TMEM lane quadrant `quad` = w % 4; a thread = one query row.
+        // The max warp runs one window ahead: row maximum of window i -> mailbox, then the output of window i - 2
+        // (O / l read back, normalised, stored); the exp warp turns window i into P and the row sums.
+        const int quad = warp & 3;
+        const bool is_max = warp >= ATC_SOFT_WARP0 + 4;
+        const int half = is_max ? 1 : 0;           // which boxes of the bias tile this warp stages
         const int r = quad * 32 + lane;
         const uint32_t lane_addr = tmem + (uint32_t(quad * 32) << 16);
         const int pair_bar = 3 + quad;           // named barrier of the two warps that share this lane quadrant
 
         // ---- segment start: bias tile -> TMEM.  The 32 bias rows of a lane quadrant are read and written only by the two
-        //      warps of that quadrant, so the pair barrier is all the synchronisation the overwrite needs; the ring slots
-        //      are handed back by the MMA warp once all 8 warps have signalled sbias_bar.
-        TR(6, seg, 0, threadIdx.x == 256);
-        named_bar_sync(pair_bar, 64);            // both warps of the quadrant are done with the previous segment's bias rows
+        //      warps of that quadrant, so the pair barrier is all the synchronisation the overwrite needs (the max warp gets
+        //      here after its last epilogue of the segment, i.e. after the exp warp has published the last P: nobody reads
+        //      the old tile any more); the ring slots are handed back by the MMA warp once all 8 warps have signalled sbias_bar.
+        TR(6, seg, 0, threadIdx.x == 256 /* warp 8, lane 0: the exp warp of quadrant 0 */);
+        named_bar_sync(pair_bar, 64);
 #pragma unroll
         for (int j = 0; j < 3; ++j) mbar_wait(&full_bar[(qb + j) % ATC_STAGES], ((qb + j) / ATC_STAGES) & 1);
 #pragma unroll 1
@@ -615,72 +667,85 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         tc_fence_before();
         named_bar_sync(pair_bar, 64);            // the partner's boxes of these rows are in TMEM too
         tc_fence_after();
-        TR(6, seg, 1, threadIdx.x == 256);
+        TR(6, seg, 1, threadIdx.x == 256 /* warp 8, lane 0: the exp warp of quadrant 0 */);
 
-        // Output row of this thread's query row in window lw0 + j: base + off_j rows, off advancing by a fixed step per
-        // window (natural order: 12 longitudes with wrap-around at W; window order: one window of rows) -- no divisions
-        // in the per-window epilogue.
-        const int my_base = row_base(r);
-        const bool keep = !a.natural || my_base >= 0;     // false: zero pad row of the window, its output is cropped away
-        const size_t rowb = size_t(a.C) * 2;
-        uint8_t* const obase = reinterpret_cast<uint8_t*>(a.out) + head * 64 + 32 * half +
-                               (a.natural ? size_t(my_base < 0 ? 0 : my_base) : size_t(t) * ATT_TOK + r) * rowb;
-        const int ostep = a.natural ? 12 : a.types * ATT_TOK;
-        const int owrap = a.natural ? a.W : 0x7fffffff;
-        int ooff = a.natural ? (12 * lw0 + (r % 12) + (a.roll ? 6 : 0)) % a.W : lw0 * a.types * ATT_TOK;
-        auto epilogue = [&](int j) {               // windows are finished in order j = 0, 1, ...; this thread stores 16 of the 32 channels
-          const int g = gbase + j, b = g & 1;
-          mbar_wait(&ofull_bar[b], (g >> 1) & 1);
-          tc_fence_after();
-          uint32_t o[16], ls[2];
-          tmem_ld16(lane_addr + ATC_COL_O + 32 * b + 16 * half, o);
-          tmem_ld2(lane_addr + ATC_COL_L + 2 * b, ls);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(&oempty_bar[b]);
-          uint8_t* dst = obase + size_t(ooff) * rowb;
-          ooff += ostep;
-          ooff = ooff >= owrap ? ooff - owrap : ooff;
-          if (!keep) return;
-          float inv;
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__uint_as_float(ls[0]) + __uint_as_float(ls[1])));
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            uint4 v;
-            v.x = pack16<kFp16>(__uint_as_float(o[8 * q + 0]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
-            v.y = pack16<kFp16>(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
-            v.z = pack16<kFp16>(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
-            v.w = pack16<kFp16>(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
-            stg16(dst + 16 * q, v);
-          }
-        };
+        if (!is_max) {
+          // ------------------------------ exp warp ------------------------------
 #pragma unroll 1
-        for (int i = 0; i < nwin; ++i) {
-          const int g = gbase + i, b = g & 1;
-          TR(3, g, 0, r == 0 && half == 0);
-          mbar_wait(&sfull_bar[b], (g >> 1) & 1);
-          TR(3, g, 1, r == 0 && half == 0);
-          tc_fence_after();
-          const uint32_t s_base = lane_addr + ATC_COL_S + 144 * b;
-          uint16_t* xm = s_xm + (b * 128 + r) * 2;
-          // trace rows: 3 = [enter, S ready, pass 1 done, max exchanged], 4 = [pass 2 done, P published, epilogue done] of warp 8
-          // (keys [0,80)); 5 = [pass 1 done, max exchanged, pass 2 done, epilogue done] of its partner warp 12 (keys [80,144))
-          auto tr0 = [&](int ev) { TR(ev < 2 ? 3 : 4, g, ev < 2 ? ev + 2 : 0, r == 0); };
-          auto tr1 = [&](int ev) { TR(5, g, ev, r == 0); };
-          auto tr = [&](int ev) { if (half == 0) tr0(ev); else tr1(ev); };
-          const float l = softmax_keys<kFp16>(s_base, lane_addr + ATC_COL_BIAS, xm, half, pair_bar, half ? 80 : 0, half ? 4 : 5, tr);
-          tmem_st1(lane_addr + ATC_COL_L + 2 * b + half, __float_as_uint(l));
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&pfull_bar[b]);
-          TR(4, g, 1, r == 0 && half == 0);
-          // ---- output of the previous window: its PV was queued one window ago
-          if (i > 0) epilogue(i - 1);
-          TR(4, g, 2, r == 0 && half == 0);
-          TR(5, g, 3, r == 0 && half == 1);
+          for (int i = 0; i < nwin; ++i) {
+            const int g = gbase + i, b = g & 1;
+            TR(3, g, 0, r == 0);
+            mbar_wait(&sfull_bar[b], (g >> 1) & 1);
+            tc_fence_after();
+            mbar_wait(&mfull_bar[b], (g >> 1) & 1);
+            TR(3, g, 1, r == 0);
+            const float m = s_xm[b * 128 + r];
+            const float l = softmax_row_exp<kFp16>(lane_addr + ATC_COL_S + 144 * b, lane_addr + ATC_COL_BIAS, m);
+            TR(3, g, 2, r == 0);
+            tmem_st1(lane_addr + ATC_COL_L + b, __float_as_uint(l));
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&pfull_bar[b]);
+            TR(3, g, 3, r == 0);
+            TR(4, g, quad, lane == 0);           // publish time of every exp warp
+          }
+        } else {
+          // ------------------------------ max warp (+ output) ------------------------------
+          // Output row of this thread's query row in window lw0 + j: base + off_j rows, off advancing by a fixed step per
+          // window (natural order: 12 longitudes with wrap-around at W; window order: one window of rows) -- no divisions
+          // in the per-window epilogue.
+          const int my_base = row_base(r);
+          const bool keep = !a.natural || my_base >= 0;     // false: zero pad row of the window, its output is cropped away
+          const size_t rowb = size_t(a.C) * 2;
+          uint8_t* const obase = reinterpret_cast<uint8_t*>(a.out) + head * 64 +
+                                 (a.natural ? size_t(my_base < 0 ? 0 : my_base) : size_t(t) * ATT_TOK + r) * rowb;
+          const int ostep = a.natural ? 12 : a.types * ATT_TOK;
+          const int owrap = a.natural ? a.W : 0x7fffffff;
+          int ooff = a.natural ? (12 * lw0 + (r % 12) + (a.roll ? 6 : 0)) % a.W : lw0 * a.types * ATT_TOK;
+          auto epilogue = [&](int j) {               // windows are finished in order j = 0, 1, ...
+            const int g = gbase + j, b = g & 1;
+            mbar_wait(&ofull_bar[b], (g >> 1) & 1);
+            tc_fence_after();
+            uint32_t o[32], ls[1];
+            tmem_ld32(lane_addr + ATC_COL_O + 32 * b, o);
+            tmem_ld1(lane_addr + ATC_COL_L + b, ls);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&oempty_bar[b]);
+            uint8_t* dst = obase + size_t(ooff) * rowb;
+            ooff += ostep;
+            ooff = ooff >= owrap ? ooff - owrap : ooff;
+            if (!keep) return;
+            float inv;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__uint_as_float(ls[0])));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 v;
+              v.x = pack16<kFp16>(__uint_as_float(o[8 * q + 0]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
+              v.y = pack16<kFp16>(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
+              v.z = pack16<kFp16>(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
+              v.w = pack16<kFp16>(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
+              stg16(dst + 16 * q, v);
+            }
+          };
+#pragma unroll 1
+          for (int i = 0; i < nwin; ++i) {
+            const int g = gbase + i, b = g & 1;
+            TR(5, g, 0, r == 0);
+            mbar_wait(&sfull_bar[b], (g >> 1) & 1);
+            tc_fence_after();
+            TR(5, g, 1, r == 0);
+            s_xm[b * 128 + r] = softmax_row_max(lane_addr + ATC_COL_S + 144 * b, lane_addr + ATC_COL_BIAS);
+            mbar_arrive(&mfull_bar[b]);
+            TR(5, g, 2, r == 0);
+            TR(7, g, quad, lane == 0);           // post time of every max warp
+            if (i >= 2) epilogue(i - 2);
+            TR(5, g, 3, r == 0);
+          }
+          if (nwin >= 2) epilogue(nwin - 2);
+          epilogue(nwin - 1);
         }
-        epilogue(nwin - 1);
-        TR(6, seg, 2, threadIdx.x == 256);
+        TR(6, seg, 2, threadIdx.x == 256 /* warp 8, lane 0: the exp warp of quadrant 0 */);
       }
       gbase += nwin;
       u += nwin;

@@ -45,8 +45,9 @@ if trace is not None:
     tr = trace.view(8, 64, 4)
     t0 = int(tr[tr > 0].min())
     names = {0: "TMA  [slot free]", 1: "MMA  [full, S issued, pfull, oempty]", 2: "TAIL [start, done]",
-             3: "SOFT [enter, sfull, pass1 done, max exchanged]", 4: "SOFT [pass2 done, P published, epilogue done]", 5: "SOFT partner [pass1 done, max exchanged, pass2 done, epilogue done]", 6: "SEG  [start, bias staged, tail-warp0 done, all done]"}
-    for role in range(7):
+             3: "EXP warp [enter, S + max ready, exp done, P published]", 4: "EXP warps [publish time, by lane quadrant]", 5: "MAX warp [enter, S ready, max posted, epilogue(i-2) done]", 6: "SEG  [start, bias staged, tail-warp0 done, all done]"}
+    names[7] = "MAX warps [post time, by lane quadrant]"
+    for role in range(8):
         print(names[role])
         for i in range(0, 64):
             row = [int(x) - t0 if int(x) > 0 else -1 for x in tr[role, i]]

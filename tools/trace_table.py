@@ -8,13 +8,12 @@ for l in txt.splitlines():
     if l.startswith('   win'):
         m = re.match(r'\s+win\s+(\d+): \[(.*)\]', l)
         roles[cur][int(m.group(1))] = [int(x) for x in m.group(2).split(',')]
-    elif l[:4] in ('TMA ', 'MMA ', 'TAIL', 'SOFT', 'SEG '):
+    elif l[:4] in ('TMA ', 'MMA ', 'TAIL', 'SOFT', 'SEG ', 'EXP ', 'MAX ') or l.strip() == '-':
         cur = l.strip(); roles[cur] = {}
 names = list(roles)
 tma, mma, tail, s3, s4, s5, seg = [roles[n] for n in names[:7]]
-print("win | A(keys 0-79): S ready, pass1 done, max exchanged, pass2 done, P published, epilogue done | B: pass1, exchanged, pass2, epilogue | MMA saw P | next window")
+print("win | EXP warp: S+max ready, exp done, P published, next enter | MAX warp (rel. to EXP enter): enter, S ready, max posted, epilogue done | MMA saw P | tail")
 for w in range(lo, hi):
     e = s3[w][0]
-    a = [s3[w][1], s3[w][2], s3[w][3], s4[w][0], s4[w][1], s4[w][2]]
-    print(w, [x - e for x in a], [x - e for x in s5[w]], mma[w][2] - e, s3[w + 1][0] - e, '| tail', tail[w][1] - tail[w][0])
-print("segments [start, bias staged, -, all done]:", [seg[k] for k in sorted(seg) if seg[k][0] >= 0][:6])
+    print(w, [x - e for x in s3[w][1:]] + [s3[w + 1][0] - e], [x - e for x in s5[w]], mma[w][2] - e, '| tail', tail[w][1] - tail[w][0])
+print("segments [start, bias staged, all done]:", [seg[k][:3] for k in sorted(seg) if seg[k][0] >= 0][:6])
