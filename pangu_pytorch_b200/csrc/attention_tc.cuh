@@ -16,8 +16,8 @@
 // Per window:
 //
 //   S[128x144] = Q[0:128] K^T          tcgen05.mma, A/B from smem (K-major), fp32 accum in TMEM
-//   max warp:  m = max_j (S*log2e + bias')   streamed from TMEM in 16-column pieces, nothing written back
-//   exp warp:  P = exp2(S*log2e + bias' - m) packed 16-bit, written over S columns the thread has already consumed
+//   max warp:  y = S*log2e + bias' written back over S, m = max_j y      (16-column pieces through registers)
+//   exp warp:  P = exp2(y - m) packed 16-bit, written over y columns the thread has already consumed
 //   O[128x32]  = P V                   tcgen05.mma, A = P from TMEM, B = V from smem (MN-major)
 //   rows 128..143 (144 = 128 + 16 does not fit an MMA M) are done by mma.sync "tail" warps that
 //   read the same smem tiles (the SWIZZLE_64B pattern equals the ldmatrix-friendly XOR swizzle).
@@ -29,9 +29,13 @@
 // S of window g+2 is queued right behind PV of window g (the tensor pipe executes in issue order, so PV
 // has read P before the next S overwrites it).  The MMA warp runs converged with warp-uniform operands
 // (only the tcgen05 instructions are elected) and polls "next S" / "next PV" without blocking on either.
-// Warps (448 threads): 0 TMA producer, 1 MMA issuer, 2-5 tail warps (ring stage s belongs to warp 2 + s%4: ONE tail warp per
-// SM sub-partition -- with six, two sub-partitions hosted two tail warps each and their exp warps ran 1.5-2x slower than
-// the others, which set the pace of the whole CTA), 6-9 "exp" warps, 10-13 "max" warps
+// Warps (448 threads) and the SM sub-partition (warp % 4) they run on -- placement matters, measured with the clock64 trace:
+//   0, 1, 4, 5  tail warps (sub-partitions 0, 1, 0, 1; ring stage s belongs to tail warp s % 4)
+//   2 TMA producer, 3 MMA issuer (sub-partitions 2, 3: they share a scheduler with no tail warp)
+//   6-9 "exp" warps, 10-13 "max" warps (one of each per sub-partition = per TMEM lane quadrant)
+// With six tail warps two sub-partitions hosted two of them, with the MMA issuer next to a tail warp its sub-partition hosted
+// four busy warps: in both layouts the exp warp of the crowded sub-partition ran 1.5-2x slower than the others and,
+// since P of a window is published by all four, set the pace of the whole CTA.
 // (see softmax_row_max / softmax_row_exp; warps w and w + 4 own TMEM lane quadrant w % 4): thread = one query row (TMEM lane).
 // Measured on B200 (tools/tmem_bench.cu): a dependent tcgen05.ld + wait costs ~38 clk and 8 warps read ~1 KB/clk, so
 // re-reading S and bias' in the exp pass is cheap; what is NOT cheap is (a) a register spill: with 232 KB of shared memory
@@ -44,7 +48,8 @@ namespace pg {
 constexpr int ATC_THREADS = 448;
 constexpr int ATC_SOFT_WARP0 = 6;                                // first exp warp (6..9), then the max warps (10..13)
 constexpr int ATC_STAGES = 8;
-constexpr int ATC_TAIL_WARPS = 4;                                // warps 2..5: ring stage s belongs to tail warp 2 + s % 4 (two stages each), so
+constexpr int ATC_TMA_WARP = 2, ATC_MMA_WARP = 3;                // on the sub-partitions that host no tail warp
+constexpr int ATC_TAIL_WARPS = 4;                                // warps 0, 1, 4, 5: ring stage s belongs to tail warp s % 4 (two stages each), so
                                                                  // every phase of a stage's mbarriers is seen by one warp, in order
 constexpr int ATC_STAGE_BYTES = ATT_BUF_BYTES;                   // 27648: Q, K, V tiles (or 3 bias boxes) of 9216 B
 constexpr int ATC_TB_PITCH = 148;                                // floats per row of the tail bias tile in smem
@@ -209,33 +214,6 @@ __device__ __forceinline__ void tail_rows(uint32_t sk, uint32_t sv, const uint32
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
 }
 
-// order-pinned variants of the packed-math helpers (volatile asm keeps their relative program order through nvcc / ptxas)
-__device__ __forceinline__ f32x2 vfma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 vadd2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ float vex2(float x) {
-  float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-template <bool kFp16>
-__device__ __forceinline__ uint32_t vpack16(float a, float b) {
-  uint32_t r;
-  if constexpr (kFp16) {
-    asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  } else {
-    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  }
-  return r;
-}
-
 // The softmax of a window is split by ROLE between the two warps that own a TMEM lane quadrant (they share an SM
 // sub-partition, i.e. one MUFU and one issue port): the "max" warp computes the row maximum of window g+1 (FMA / ALU work)
 // while the "exp" warp turns window g into probabilities (MUFU work).  With both warps running the same phase of the same
@@ -245,13 +223,13 @@ __device__ __forceinline__ uint32_t vpack16(float a, float b) {
 // bias' tile in 16-column pieces through two register buffers (piece p + 1 in flight while piece p is processed), as
 // ROLLED loops: five roles run different code on every sub-partition and the instruction cache holds 32 KB.
 
-// row maximum of y = S*log2e + bias' over the 144 keys
+// max warp: y = S*log2e + bias' written back over S (fp32, in place) and its row maximum over the 144 keys
 __device__ __forceinline__ float softmax_row_max(uint32_t sp, uint32_t bp) {
   constexpr float kLog2e = 1.4426950408889634f;
   const f32x2 l2e2 = pack2(kLog2e, kLog2e);
   uint32_t sa[16], ba[16], sb[16], bb[16];
   float m0 = -INFINITY, m1 = -INFINITY;        // two chains: the reduction is latency bound
-  auto reduce = [&](const uint32_t (&sx)[16], const uint32_t (&bx)[16]) {
+  auto reduce = [&](uint32_t (&sx)[16], const uint32_t (&bx)[16]) {      // sx: S in, y out
 #pragma unroll
     for (int e = 0; e < 8; e += 2) {
       float a0, a1, a2, a3;
@@ -261,6 +239,8 @@ __device__ __forceinline__ float softmax_row_max(uint32_t sp, uint32_t bp) {
                    pack2(__uint_as_float(bx[2 * e + 2]), __uint_as_float(bx[2 * e + 3]))), a2, a3);
       m0 = max3(m0, a0, a1);
       m1 = max3(m1, a2, a3);
+      sx[2 * e] = __float_as_uint(a0); sx[2 * e + 1] = __float_as_uint(a1);
+      sx[2 * e + 2] = __float_as_uint(a2); sx[2 * e + 3] = __float_as_uint(a3);
     }
   };
   tmem_ld16(sp, sa);
@@ -272,79 +252,71 @@ __device__ __forceinline__ float softmax_row_max(uint32_t sp, uint32_t bp) {
     tmem_ld16(bp + 16 * (c + 1), bb);
     reduce(sa, ba);
     tmem_ld_wait();
+    tmem_st16(sp + 16 * c, sa);
+    tmem_st_wait();                            // sa is reloaded below: the store must have read it
     tmem_ld16(sp + 16 * (c + 2), sa);
     tmem_ld16(bp + 16 * (c + 2), ba);
     reduce(sb, bb);
     tmem_ld_wait();
+    tmem_st16(sp + 16 * (c + 1), sb);
+    tmem_st_wait();
   }
   reduce(sa, ba);
+  tmem_st16(sp + 128, sa);
+  tmem_st_wait();
   return fmaxf(m0, m1);
 }
 
-// P = exp2(y - m), packed 16-bit, written over score columns [0, 72) (piece p of P lands on columns [8p, 8p+8), which
-// this thread consumed in piece p/2 <= p; nobody else reads the row any more); returns the row sum of the unrounded p.
+// exp warp: P = exp2(y - m), packed 16-bit, written over columns [0, 72) of the row (piece p of P lands on columns
+// [8p, 8p+8), which this thread consumed in piece p/2 <= p; nobody else reads the row any more); returns the row sum of
+// the unrounded p.  Per pair of keys: one FADD2, two MUFU, one FADD2 (sum), one F2FP -- a warp issues in order, so every
+// non-MUFU instruction here adds to the 8 clk each MUFU.EX2 holds the pipe (the bias add lives in the max warp for that reason).
 template <bool kFp16>
-__device__ __forceinline__ float softmax_row_exp(uint32_t sp, uint32_t bp, float m) {
-  constexpr float kLog2e = 1.4426950408889634f;
-  const f32x2 l2e2 = pack2(kLog2e, kLog2e);
+__device__ __forceinline__ float softmax_row_exp(uint32_t sp, float m) {
+  // Software pipelined over the 16-column pieces: the MUFUs of piece c+1 (stage A) share a basic block with the row-sum
+  // adds, the packing and the store of piece c (stage B), so that ptxas can interleave them.  Piece by piece
+  // (A then B of the same piece, separated by the TMEM wait / store) the pass took 222 clk per piece against 128 clk of
+  // MUFU time: fill and drain of the MUFU pipeline were paid nine times per row.
   const f32x2 negm2 = pack2(-m, -m);
-  uint32_t sa[16], ba[16], sb[16], bb[16];
+  uint32_t ya[16], yb[16];
+  float pa[16], pb[16];
   f32x2 l0 = pack2(0.f, 0.f), l1 = pack2(0.f, 0.f);
-  // A warp issues in order: sixteen back-to-back MUFU.EX2 (8 clk of the pipe each) followed by the 24 FMA / ALU
-  // instructions of the piece cost 128 + ~80 clk, interleaved they cost ~130 (measured: 2 000 -> clk per window for the
-  // clustered schedule ptxas picked).  The order below is therefore pinned with volatile asm: per pair of keys
-  // MUFU, FADD2 (next pair), MUFU, FFMA2 (next pair), FADD2 (row sum of the previous pair), F2FP (pack previous pair).
-  auto expo = [&](const uint32_t (&sx)[16], const uint32_t (&bx)[16], uint32_t (&pk)[8]) {
-    f32x2 t_cur, t_nxt = 0, p_prev = 0;
-    t_cur = vfma2(pack2(__uint_as_float(sx[0]), __uint_as_float(sx[1])), l2e2,
-                  vadd2(pack2(__uint_as_float(bx[0]), __uint_as_float(bx[1])), negm2));
+  auto stage_a = [&](const uint32_t (&yx)[16], float (&px)[16]) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float a0, a1;
-      unpack2(t_cur, a0, a1);
-      const float p0 = vex2(a0);
-      f32x2 u = 0;
-      if (e + 1 < 8) u = vadd2(pack2(__uint_as_float(bx[2 * e + 2]), __uint_as_float(bx[2 * e + 3])), negm2);
-      const float p1 = vex2(a1);
-      if (e + 1 < 8) t_nxt = vfma2(pack2(__uint_as_float(sx[2 * e + 2]), __uint_as_float(sx[2 * e + 3])), l2e2, u);
-      if (e > 0) {
-        float q0, q1;
-        unpack2(p_prev, q0, q1);
-        if (e & 1) l1 = vadd2(l1, p_prev); else l0 = vadd2(l0, p_prev);
-        pk[e - 1] = vpack16<kFp16>(q0, q1);
-      }
-      p_prev = pack2(p0, p1);
-      t_cur = t_nxt;
-    }
-    {
-      float q0, q1;
-      unpack2(p_prev, q0, q1);
-      l0 = vadd2(l0, p_prev);
-      pk[7] = vpack16<kFp16>(q0, q1);
+      unpack2(add2(pack2(__uint_as_float(yx[2 * e]), __uint_as_float(yx[2 * e + 1])), negm2), a0, a1);
+      px[2 * e] = ex2_approx(a0);
+      px[2 * e + 1] = ex2_approx(a1);
     }
   };
-  tmem_ld16(sp, sa);
-  tmem_ld16(bp, ba);
+  auto stage_b = [&](const float (&px)[16], uint32_t taddr) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      l0 = add2(l0, pack2(px[2 * e], px[2 * e + 1]));
+      l1 = add2(l1, pack2(px[2 * e + 2], px[2 * e + 3]));
+      pk[e] = pack16<kFp16>(px[2 * e], px[2 * e + 1]);
+      pk[e + 1] = pack16<kFp16>(px[2 * e + 2], px[2 * e + 3]);
+    }
+    tmem_st8(taddr, pk);
+  };
+  tmem_ld16(sp, ya);
   tmem_ld_wait();
+  tmem_ld16(sp + 16, yb);
+  stage_a(ya, pa);
 #pragma unroll 1
-  for (int c = 0; c < 8; c += 2) {
-    uint32_t pk[8];
-    tmem_ld16(sp + 16 * (c + 1), sb);
-    tmem_ld16(bp + 16 * (c + 1), bb);
-    expo(sa, ba, pk);
-    tmem_ld_wait();                     // piece c+1 is in registers before any score column is overwritten
-    tmem_st8(sp + 8 * c, pk);
-    tmem_ld16(sp + 16 * (c + 2), sa);
-    tmem_ld16(bp + 16 * (c + 2), ba);
-    expo(sb, bb, pk);
+  for (int c = 0; c < 8; c += 2) {      // invariant: pa = p of piece c, piece c+1 in flight into yb
     tmem_ld_wait();
-    tmem_st8(sp + 8 * (c + 1), pk);
+    tmem_ld16(sp + 16 * (c + 2), ya);
+    stage_a(yb, pb);
+    stage_b(pa, sp + 8 * c);            // columns [8c, 8c+8) were consumed in piece c/2
+    tmem_ld_wait();
+    if (c + 3 < 9) tmem_ld16(sp + 16 * (c + 3), yb);
+    stage_a(ya, pa);
+    stage_b(pb, sp + 8 * (c + 1));
   }
-  {
-    uint32_t pk[8];
-    expo(sa, ba, pk);
-    tmem_st8(sp + 64, pk);
-  }
+  stage_b(pa, sp + 64);
   float a0, a1;
   unpack2(add2(l0, l1), a0, a1);
   return a0 + a1;
@@ -375,7 +347,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == ATC_TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmBias);
     for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
@@ -387,7 +359,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
     mbar_init(sbias_bar, 8);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == ATC_MMA_WARP) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -410,7 +382,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
 #endif
   constexpr float kLog2e = 1.4426950408889634f;
 
-  if (warp == 0) {
+  if (warp == ATC_TMA_WARP) {
     // ============================== TMA producer ==============================
     // ring slot sequence: per segment 3 bias slots, then one slot per window
     if (lane == 0) {
@@ -442,7 +414,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         u += nwin; lw = 0; ++th;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == ATC_MMA_WARP) {
     // ============================== MMA issuer ==============================
     // The whole warp walks the loop (uniform control flow and operands); one elected lane issues.
     constexpr uint32_t idesc_s = make_idesc_f16_ex(128, 144, kFp16, false);
@@ -567,7 +539,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
       };
       if (warp < ATC_SOFT_WARP0) {
         // ============================== tail warps: rows 128..143 with mma.sync ==============================
-        const int tid = threadIdx.x - 64;        // 0..127
+        const int tix = warp < 2 ? warp : warp - 2;   // tail warp index 0..3 (warps 0, 1, 4, 5)
+        const int tid = tix * 32 + lane;         // 0..127
         named_bar_sync(2, ATC_TAIL_WARPS * 32);  // every tail warp is done with the previous tail bias rows
 #pragma unroll
         for (int j = 0; j < 3; ++j) mbar_wait(&full_bar[(qb + j) % ATC_STAGES], ((qb + j) / ATC_STAGES) & 1);
@@ -586,10 +559,10 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         const int r0 = 128 + gq;
         const float* tb0 = s_tbias + gq * ATC_TB_PITCH + 2 * q4;
         const float* tb1 = tb0 + 8 * ATC_TB_PITCH;
-        // this warp owns the ring stages s with s % 4 == warp - 2: it takes the windows whose slot falls on them
+        // this warp owns the ring stages s with s % 4 == tix: it takes the windows whose slot falls on them
         for (int i = 0; i < nwin; ++i) {
           const int g = gbase + i, q = qb + 3 + i, st = q % ATC_STAGES;
-          if (st % ATC_TAIL_WARPS != warp - 2) continue;
+          if (st % ATC_TAIL_WARPS != tix) continue;
           mbar_wait(&full_bar[st], (q / ATC_STAGES) & 1);
           uint8_t* tile = ring + st * ATC_STAGE_BYTES;
           TR(2, g, 0, lane == 0);
@@ -675,12 +648,11 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           for (int i = 0; i < nwin; ++i) {
             const int g = gbase + i, b = g & 1;
             TR(3, g, 0, r == 0);
-            mbar_wait(&sfull_bar[b], (g >> 1) & 1);
+            mbar_wait(&mfull_bar[b], (g >> 1) & 1);      // y of this window is in TMEM (which implies S was), maxima in the mailbox
             tc_fence_after();
-            mbar_wait(&mfull_bar[b], (g >> 1) & 1);
             TR(3, g, 1, r == 0);
             const float m = s_xm[b * 128 + r];
-            const float l = softmax_row_exp<kFp16>(lane_addr + ATC_COL_S + 144 * b, lane_addr + ATC_COL_BIAS, m);
+            const float l = softmax_row_exp<kFp16>(lane_addr + ATC_COL_S + 144 * b, m);
             TR(3, g, 2, r == 0);
             tmem_st1(lane_addr + ATC_COL_L + b, __float_as_uint(l));
             tmem_st_wait();
@@ -706,8 +678,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             const int g = gbase + j, b = g & 1;
             mbar_wait(&ofull_bar[b], (g >> 1) & 1);
             tc_fence_after();
-            uint32_t o[32], ls[1];
-            tmem_ld32(lane_addr + ATC_COL_O + 32 * b, o);
+            uint32_t o0[16], o1[16], ls[1];
+            tmem_ld16(lane_addr + ATC_COL_O + 32 * b, o0);
+            tmem_ld16(lane_addr + ATC_COL_O + 32 * b + 16, o1);
             tmem_ld1(lane_addr + ATC_COL_L + b, ls);
             tmem_ld_wait();
             tc_fence_before();
@@ -718,15 +691,19 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             if (!keep) return;
             float inv;
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__uint_as_float(ls[0])));
+            auto put = [&](const uint32_t (&o)[16], uint8_t* d) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 v;
-              v.x = pack16<kFp16>(__uint_as_float(o[8 * q + 0]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
-              v.y = pack16<kFp16>(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
-              v.z = pack16<kFp16>(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
-              v.w = pack16<kFp16>(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
-              stg16(dst + 16 * q, v);
-            }
+              for (int q = 0; q < 2; ++q) {
+                uint4 v;
+                v.x = pack16<kFp16>(__uint_as_float(o[8 * q + 0]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
+                v.y = pack16<kFp16>(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
+                v.z = pack16<kFp16>(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
+                v.w = pack16<kFp16>(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
+                stg16(d + 16 * q, v);
+              }
+            };
+            put(o0, dst);
+            put(o1, dst + 32);
           };
 #pragma unroll 1
           for (int i = 0; i < nwin; ++i) {
@@ -736,6 +713,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             tc_fence_after();
             TR(5, g, 1, r == 0);
             s_xm[b * 128 + r] = softmax_row_max(lane_addr + ATC_COL_S + 144 * b, lane_addr + ATC_COL_BIAS);
+            tc_fence_before();                          // the y stores (already waited for) before the hand-over
             mbar_arrive(&mfull_bar[b]);
             TR(5, g, 2, r == 0);
             TR(7, g, quad, lane == 0);           // post time of every max warp
@@ -756,7 +734,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == ATC_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }

@@ -21,7 +21,10 @@ ws.qkv.normal_()
 ebias = torch.randn(1, ws.types, heads, 144, 144, device=dev) * 0.02
 trace = None
 if os.environ.get('ATTN_TRACE'):
-    trace = torch.zeros(8 * 64 * 4, dtype=torch.int64).pin_memory()   # host-mapped: readable even after a device trap
+    # device memory by default (a store to pinned host memory per event slows the traced warp down by ~1.5x and with it
+    # the whole CTA); ATTN_TRACE=host keeps the buffer readable even after a device trap
+    trace = (torch.zeros(8 * 64 * 4, dtype=torch.int64).pin_memory() if os.environ['ATTN_TRACE'] == 'host'
+             else torch.zeros(8 * 64 * 4, dtype=torch.int64, device=dev))
     os.environ['PANGU_B200_ATTN_TRACE'] = str(trace.data_ptr())
 def run():
   for roll in (0, 1):
@@ -42,7 +45,7 @@ except Exception as e:
     print('FAILED:', str(e)[:100])
 
 if trace is not None:
-    tr = trace.view(8, 64, 4)
+    tr = trace.cpu().view(8, 64, 4)
     t0 = int(tr[tr > 0].min())
     names = {0: "TMA  [slot free]", 1: "MMA  [full, S issued, pfull, oempty]", 2: "TAIL [start, done]",
              3: "EXP warp [enter, S + max ready, exp done, P published]", 4: "EXP warps [publish time, by lane quadrant]", 5: "MAX warp [enter, S ready, max posted, epilogue(i-2) done]", 6: "SEG  [start, bias staged, tail-warp0 done, all done]"}
