@@ -132,20 +132,26 @@ struct CfgBase {
   static constexpr bool TMA16 = false;   // 16-bit row-major output written with TMA bulk stores
   static constexpr int CLUSTER = 1;      // 2: CTA pairs share every weight (B) tile by TMA multicast
   static constexpr bool NSPLIT = false;  // CTA pair splits the LayerNorm row (N) instead of M; stats via DSMEM
+  static constexpr bool CTA2 = false;    // CTA pair runs ONE tcgen05.mma.cta_group::2 (M = 256), B tile split between the two SMs
   static constexpr bool HEADMAJOR = false;  // TMA16: output stored as [N/32 planes][plane_rows][32]
   static constexpr bool RESTMA = false;  // LN + residual epilogue whose fp32 stream moves by TMA (identity row map)
   static constexpr int EPI_WARPS = 8;    // 4 x column groups (TMA16 configs may use 12 / 16: latency-bound epilogues)
 };
+#ifndef PANGU_CTA2
+#define PANGU_CTA2 1            // 1: CfgQKV / CfgMLP1 / CfgLin16 use tcgen05.mma.cta_group::2 (see profiles/r02_cta2.md); 0: cta_group::1 + multicast
+#endif
 struct CfgQKV : CfgBase {      // linear1 of attention: bias, q-scale, 16-bit out
-  static constexpr int BN = 192, UN = 192, STAGES = 4;
+  static constexpr int BN = 192, UN = 192, STAGES = PANGU_CTA2 ? 6 : 4;
   static constexpr bool SCALEQ = true, OUT16 = true, TMA16 = true, HEADMAJOR = true;
-  static constexpr int CLUSTER = PANGU_CLUSTER_M;
+  static constexpr int CLUSTER = 2;
+  static constexpr bool CTA2 = PANGU_CTA2 != 0;
   static constexpr int EPI_WARPS = PANGU_EPI_WARPS_QKV;
 };
 struct CfgMLP1 : CfgBase {     // Mlp.linear1: bias + exact GELU, 16-bit out
-  static constexpr int BN = 256, UN = 256, STAGES = 3;
+  static constexpr int BN = 256, UN = 256, STAGES = PANGU_CTA2 ? 4 : 3;
   static constexpr bool GELU = true, OUT16 = true, TMA16 = true;
-  static constexpr int CLUSTER = PANGU_CLUSTER_M;
+  static constexpr int CLUSTER = 2;
+  static constexpr bool CTA2 = PANGU_CTA2 != 0;
   static constexpr int EPI_WARPS = PANGU_EPI_WARPS_MLP1;
 };
 struct CfgLNRes192 : CfgBase { // bias + LayerNorm(192) + residual, fp32 + 16-bit out
@@ -177,9 +183,10 @@ struct CfgRecS : CfgBase {     // _output_layer.conv_surface
 };
 
 struct CfgLin16 : CfgBase {    // (bias) -> 16-bit row-major (pre-activation recompute, d hidden)
-  static constexpr int BN = 256, UN = 256, STAGES = 3;
+  static constexpr int BN = 256, UN = 256, STAGES = PANGU_CTA2 ? 4 : 3;
   static constexpr bool OUT16 = true, TMA16 = true;
-  static constexpr int CLUSTER = PANGU_CLUSTER_M;
+  static constexpr int CLUSTER = 2;
+  static constexpr bool CTA2 = PANGU_CTA2 != 0;
   static constexpr int EPI_WARPS = PANGU_EPI_WARPS_MLP1;
 };
 struct CfgAcc192 : CfgBase {   // fp32 out = residual + acc (dgrad accumulating into the gradient stream), row maps

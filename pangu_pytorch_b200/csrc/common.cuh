@@ -178,6 +178,46 @@ __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) 
                : "memory");
 }
 
+// ------------------------------------------------------------------ CTA pairs (tcgen05 cta_group::2)
+// One tcgen05.mma.cta_group::2 spans the two SMs of a cluster pair: M = 256 (rows 0..127 from the A tile and into the TMEM of
+// CTA 0, rows 128..255 from / into CTA 1), and each CTA holds HALF of the B tile (N/2 rows) at the same shared-memory offset.
+// Only CTA 0 issues the MMA; both CTAs load their tiles with the cta_group::2 form of the TMA load, whose completion bytes
+// are counted on CTA 0's mbarrier.
+__device__ __forceinline__ void tma_load_2d_cta2(const CUtensorMap* m, uint32_t leader_bar, void* smem, int c0, int c1,
+                                                 uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_cta2(uint32_t* dst_smem) {      // one warp (same warp index) in EACH CTA of the pair
+  static_assert(kCols == 32 || kCols == 64 || kCols == 128 || kCols == 256 || kCols == 512, "pow2 >= 32");
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_cta2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_cta2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior tcgen05 ops of this thread -> one arrival on the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_cta2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(uint16_t(3))
+               : "memory");
+}
+
 // smem tile -> global (bulk async group); out-of-bounds rows/columns of the box are clipped
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

@@ -69,12 +69,14 @@ struct GemmTraits {
   static constexpr int STAGES = Cfg::STAGES;
   static constexpr int CL = Cfg::CLUSTER;            // CTAs per cluster sharing each B tile by TMA multicast
   static constexpr bool NSPLIT = Cfg::NSPLIT;        // cluster pair splits the N (LayerNorm) dimension instead of M
+  static constexpr bool CTA2 = Cfg::CTA2;            // CTA pair = ONE tcgen05.mma.cta_group::2 (M = 256): each CTA holds its own 128
+                                                     // A rows and HALF of the B tile, so a stage is A + B/2 and the ring gets deeper
   static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS_RAW = ACC_STAGES * BN;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                    : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_BYTES = (CTA2 ? BN / 2 : BN) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_PITCH = CH * 4 + 16;      // bytes; == 16 (mod 128) -> conflict-free 16 B rows
   // per-warp staging slab: [32 rows][STG_PITCH] fp32, or (TMA16) two [32 rows][64 B] SWIZZLE_64B tiles, or
@@ -97,6 +99,7 @@ struct GemmTraits {
   static_assert(BN % UN == 0 && UN % 16 == 0 && UN <= 256, "bad N tiling");
   static_assert(CL == 1 || ((CL == 2 || CL == 4) && (BN / CL) % 8 == 0 && BN / CL <= 256), "bad cluster B split");
   static_assert(!NSPLIT || CL == 2, "NSPLIT: a CTA pair");
+  static_assert(!CTA2 || (CL == 2 && !NSPLIT && NUM_B == 1 && BN % 32 == 0), "CTA2: a CTA pair, one MMA per K step, N/2 % 16 == 0");
   static_assert(!NSPLIT || (CL == 2 && Cfg::LN && NUM_B == 1), "NSPLIT: LayerNorm row split over a CTA pair");
   static_assert(BN % CH == 0 && (CH == 16 || CH == 32), "bad epilogue chunk");
   static_assert(EPI_WARPS % 4 == 0 && (EPI_WARPS == 8 || Cfg::TMA16), "more than 8 epilogue warps: TMA16 epilogue only");
@@ -105,6 +108,7 @@ struct GemmTraits {
                                  Cfg::RECOVER == 0 && !Cfg::TMA16), "RESTMA: LayerNorm + residual epilogue");
   static_assert(SLAB_BYTES % 1024 == 0 || !Cfg::RESTMA, "SWIZZLE_128B tiles need 1024 B alignment");
   static_assert(!Cfg::TMA16 || (CH == 32 && !Cfg::LN && !Cfg::OUT32 && Cfg::RECOVER == 0), "TMA16: plain 16-bit output");
+  static_assert(!CTA2 || Cfg::TMA16, "CTA2 is wired for the plain 16-bit (TMA16) epilogue only");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024 B alignment");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
@@ -155,11 +159,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if constexpr (Cfg::TMA16 || Cfg::RESTMA) tma_prefetch_desc(&tmOut);
     for (int s = 0; s < T::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);     // one tcgen05.commit arrival per CTA of the cluster
+      mbar_init(&empty_bar[s], T::CTA2 ? 1 : CL);     // one tcgen05.commit arrival per CTA of the cluster (CTA2: one commit, multicast)
     }
     for (int a = 0; a < T::ACC_STAGES; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], kEpiThreads);
+      mbar_init(&tempty_bar[a], T::CTA2 ? 2 * kEpiThreads : kEpiThreads);   // CTA2: both CTAs' epilogues release CTA 0's accumulator stage
       if constexpr (T::NSPLIT) { mbar_init(&xfull_bar[a], 1); mbar_init(&xempty_bar[a], kEpiThreads); }
     }
     if constexpr (Cfg::RESTMA) {
@@ -167,7 +171,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<T::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (T::CTA2) tmem_alloc_cta2<T::TMEM_COLS>(tmem_slot); else tmem_alloc<T::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
   if constexpr (CL == 1) __syncthreads(); else cluster_sync_all();   // peer barriers initialised before any remote arrive
   tc_fence_after();
@@ -186,6 +192,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + stage * T::STAGE_BYTES;
           uint8_t* sb = sa + T::A_BYTES;
+          if constexpr (T::CTA2) {
+            // both CTAs' bytes are counted on CTA 0's barrier (armed by CTA 0 alone; a completion that lands before the
+            // arming only makes the signed transaction count dip below zero for a moment)
+            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * T::STAGE_BYTES);
+            tma_load_2d_cta2(&tmA, lbar, sa, kb * BLOCK_K, m_blk * BLOCK_M, kEvictFirst);
+            tma_load_2d_cta2(&tmB, lbar, sb, kb * BLOCK_K, n_blk * BN + cta_rank * (BN / 2), kEvictLast);
+            if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], T::STAGE_BYTES);
           if constexpr (T::NSPLIT) {
             // the pair shares the A tile: each CTA fetches 64 of its 128 rows and multicasts them;
@@ -215,8 +231,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, UN, kFp16);
+    if (lane == 0 && (!T::CTA2 || cta_rank == 0)) {
+      constexpr uint32_t idesc = make_idesc_f16(T::CTA2 ? 2 * BLOCK_M : BLOCK_M, UN, kFp16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -235,14 +251,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int j = 0; j < T::NUM_B; ++j) {
               const uint64_t db = make_sdesc_sw128(sa + T::A_BYTES + j * UN * 128);
               // advancing K by 16 elements = 32 B inside the swizzle row: +2 in the (addr>>4) field
+              if constexpr (T::CTA2)
+                umma_f16_ss_cta2(tmem_base + acc * BN, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              else
               umma_f16_ss(tmem_base + acc * BN + j * UN, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc,
                           (kb | k) != 0 ? 1u : 0u);
             }
           }
           // frees the ring slot (in every CTA of the cluster: the peer multicasts into it) once read
-          if constexpr (CL == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], uint16_t((1 << CL) - 1));
+          if constexpr (T::CTA2) umma_commit_cta2(&empty_bar[stage]);
+          else if constexpr (CL == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], uint16_t((1 << CL) - 1));
           if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
         }
+        if constexpr (T::CTA2) umma_commit_cta2(&tfull_bar[acc]); else
         umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
         if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
@@ -343,6 +364,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (ci + 1 < NCH) tmem_ld_wait();
         }
         tc_fence_before();
+        if constexpr (T::CTA2) {          // the issuing CTA (rank 0) waits for both halves of the M = 256 accumulator to be drained
+          if (cta_rank == 0) mbar_arrive(&tempty_bar[acc]);
+          else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        } else
         mbar_arrive(&tempty_bar[acc]);
         if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         continue;
@@ -722,7 +747,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if constexpr (CL == 1) __syncthreads(); else cluster_sync_all();   // no remote arrive / multicast may target an exited CTA
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<T::TMEM_COLS>(tmem_base);
+    if constexpr (T::CTA2) tmem_dealloc_cta2<T::TMEM_COLS>(tmem_base); else tmem_dealloc<T::TMEM_COLS>(tmem_base);
   }
 }
 
