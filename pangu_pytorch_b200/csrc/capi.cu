@@ -165,6 +165,14 @@ struct CfgLNRes384 : CfgBase { // bias + LayerNorm(384) + residual: a CTA pair, 
   static constexpr int CLUSTER = 2;
   static constexpr bool NSPLIT = true;
 };
+struct CfgLNRes384F : CfgBase { // bias + LayerNorm(384) + residual with the FULL 384-wide row per CTA: a CTA pair runs M = 256 x N = 2 x 192
+                                // cta_group::2 MMAs, each CTA streams its 128 A rows and half of every weight tile (157 FLOP per L2
+                                // byte instead of 96), LayerNorm statistics are thread-local (no DSMEM exchange); one accumulator stage
+  static constexpr int BN = 384, UN = 192, STAGES = 4;
+  static constexpr bool LN = true, RESID = true, OUT32 = true, OUT16 = true;
+  static constexpr int CLUSTER = 2;
+  static constexpr bool CTA2 = true;
+};
 struct CfgPlain192 : CfgBase { // (bias) -> fp32 + 16-bit (embed, downsample.linear, upsample.linear2, tests)
   static constexpr int BN = 192, UN = 192, STAGES = 4;
   static constexpr bool OUT32 = true, OUT16 = true;
@@ -190,14 +198,16 @@ struct CfgLin16 : CfgBase {    // (bias) -> 16-bit row-major (pre-activation rec
   static constexpr int EPI_WARPS = PANGU_EPI_WARPS_MLP1;
 };
 struct CfgAcc192 : CfgBase {   // fp32 out = residual + acc (dgrad accumulating into the gradient stream), row maps
-  static constexpr int BN = 192, UN = 192, STAGES = 4;
+  static constexpr int BN = 192, UN = 192, STAGES = PANGU_CTA2 ? 6 : 4;
   static constexpr bool RESID = true, OUT32 = true;
-  static constexpr int CLUSTER = PANGU_CLUSTER_M;
+  static constexpr int CLUSTER = 2;
+  static constexpr bool CTA2 = PANGU_CTA2 != 0;
 };
 struct CfgOut16Map : CfgBase { // 16-bit out, destination row map (dgrad scattered into window order)
-  static constexpr int BN = 192, UN = 192, STAGES = 4;
+  static constexpr int BN = 192, UN = 192, STAGES = PANGU_CTA2 ? 6 : 4;
   static constexpr bool OUT16 = true;
-  static constexpr int CLUSTER = PANGU_CLUSTER_M;
+  static constexpr int CLUSTER = 2;
+  static constexpr bool CTA2 = PANGU_CTA2 != 0;
 };
 
 struct GemmOperands {
@@ -220,7 +230,8 @@ static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t 
   CUtensorMap ma, ma2, mb;
   PG_TRY(make_map(&ma, o.a, o.M, o.k1, o.a_pitch, Cfg::NSPLIT ? 64 : BLOCK_M));
   if (o.k2 > 0) PG_TRY(make_map(&ma2, o.a2, o.M, o.k2, o.a2_pitch, BLOCK_M)); else ma2 = ma;
-  PG_TRY(make_map(&mb, o.b, o.N, o.k1 + o.k2, o.b_pitch, (Cfg::CLUSTER > 1 && !Cfg::NSPLIT) ? Cfg::BN / Cfg::CLUSTER : Cfg::UN));
+  PG_TRY(make_map(&mb, o.b, o.N, o.k1 + o.k2, o.b_pitch,
+                  Cfg::CTA2 ? Cfg::UN / 2 : (Cfg::CLUSTER > 1 && !Cfg::NSPLIT) ? Cfg::BN / Cfg::CLUSTER : Cfg::UN));
   CUtensorMap mo = ma;
   if constexpr (Cfg::RESTMA) {
     // residual stream == fp32 output, [M, ld32] fp32 in natural row order: 32-column x 32-row SWIZZLE_128B tiles
@@ -529,7 +540,12 @@ extern "C" int pangu_proj_ln_residual(const void* att16, const void* w16, const 
   ep.rowmap = RM_IDENT; ep.dstmap = DM_IDENT;
   ep.res_scale = res_scale;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return C == 192 ? launch_gemm<CfgLNRes192>(o, ep, fp16, s) : launch_gemm<CfgLNRes384>(o, ep, fp16, s);
+  int full_row = 0;
+#ifdef PANGU_DEV_SWITCHES
+  if (const char* e = getenv("PANGU_B200_LN384")) full_row = atoi(e);
+#endif
+  return C == 192 ? launch_gemm<CfgLNRes192>(o, ep, fp16, s)
+                  : (full_row & 2) ? launch_gemm<CfgLNRes384F>(o, ep, fp16, s) : launch_gemm<CfgLNRes384>(o, ep, fp16, s);
 }
 
 extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, const float* b1, const void* w2_16,
@@ -577,7 +593,15 @@ extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, cons
     ep.dstmap = roll_out < 0 ? DM_IDENT : DM_TOK2WIN;
     ep.roll_out = roll_out > 0 ? 1 : 0;
     ep.res_scale = res_scale;
-    PG_TRY(C == 192 ? launch_gemm<CfgLNRes192>(o, ep, fp16, s) : launch_gemm<CfgLNRes384>(o, ep, fp16, s));
+    // CfgLNRes384F (full 384-wide row per CTA, cta_group::2) was measured at the same speed as the N-split pair for
+    // Mlp.linear2 (228 vs 231 us: the lower L2 traffic is paid for with an epilogue that no longer overlaps the mainloop) and
+    // slower for the projection (165 vs 120 us), profiles/r02_cta2.md; development builds can select it with PANGU_B200_LN384.
+    int full_row = 0;
+#ifdef PANGU_DEV_SWITCHES
+    if (const char* e = getenv("PANGU_B200_LN384")) full_row = atoi(e);
+#endif
+    PG_TRY(C == 192 ? launch_gemm<CfgLNRes192>(o, ep, fp16, s)
+                    : (full_row & 1) ? launch_gemm<CfgLNRes384F>(o, ep, fp16, s) : launch_gemm<CfgLNRes384>(o, ep, fp16, s));
   }
   return 0;
 }

@@ -99,7 +99,7 @@ struct GemmTraits {
   static_assert(BN % UN == 0 && UN % 16 == 0 && UN <= 256, "bad N tiling");
   static_assert(CL == 1 || ((CL == 2 || CL == 4) && (BN / CL) % 8 == 0 && BN / CL <= 256), "bad cluster B split");
   static_assert(!NSPLIT || CL == 2, "NSPLIT: a CTA pair");
-  static_assert(!CTA2 || (CL == 2 && !NSPLIT && NUM_B == 1 && BN % 32 == 0), "CTA2: a CTA pair, one MMA per K step, N/2 % 16 == 0");
+  static_assert(!CTA2 || (CL == 2 && !NSPLIT && UN % 32 == 0), "CTA2: a CTA pair, N/2 of every MMA % 16 == 0");
   static_assert(!NSPLIT || (CL == 2 && Cfg::LN && NUM_B == 1), "NSPLIT: LayerNorm row split over a CTA pair");
   static_assert(BN % CH == 0 && (CH == 16 || CH == 32), "bad epilogue chunk");
   static_assert(EPI_WARPS % 4 == 0 && (EPI_WARPS == 8 || Cfg::TMA16), "more than 8 epilogue warps: TMA16 epilogue only");
@@ -108,7 +108,7 @@ struct GemmTraits {
                                  Cfg::RECOVER == 0 && !Cfg::TMA16), "RESTMA: LayerNorm + residual epilogue");
   static_assert(SLAB_BYTES % 1024 == 0 || !Cfg::RESTMA, "SWIZZLE_128B tiles need 1024 B alignment");
   static_assert(!Cfg::TMA16 || (CH == 32 && !Cfg::LN && !Cfg::OUT32 && Cfg::RECOVER == 0), "TMA16: plain 16-bit output");
-  static_assert(!CTA2 || Cfg::TMA16, "CTA2 is wired for the plain 16-bit (TMA16) epilogue only");
+  static_assert(!CTA2 || !Cfg::RESTMA, "CTA2 is wired for the TMA16 and the generic epilogues");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024 B alignment");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
@@ -198,7 +198,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * T::STAGE_BYTES);
             tma_load_2d_cta2(&tmA, lbar, sa, kb * BLOCK_K, m_blk * BLOCK_M, kEvictFirst);
-            tma_load_2d_cta2(&tmB, lbar, sb, kb * BLOCK_K, n_blk * BN + cta_rank * (BN / 2), kEvictLast);
+#pragma unroll
+            for (int j = 0; j < T::NUM_B; ++j)     // this CTA's half (UN/2 rows) of the B tile of every MMA of the K step
+              tma_load_2d_cta2(&tmB, lbar, sb + j * (UN / 2) * 128, kb * BLOCK_K, n_blk * BN + j * UN + cta_rank * (UN / 2), kEvictLast);
             if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -249,10 +251,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
 #pragma unroll
             for (int j = 0; j < T::NUM_B; ++j) {
-              const uint64_t db = make_sdesc_sw128(sa + T::A_BYTES + j * UN * 128);
+              const uint64_t db = make_sdesc_sw128(sa + T::A_BYTES + j * (T::CTA2 ? UN / 2 : UN) * 128);
               // advancing K by 16 elements = 32 B inside the swizzle row: +2 in the (addr>>4) field
               if constexpr (T::CTA2)
-                umma_f16_ss_cta2(tmem_base + acc * BN, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_f16_ss_cta2(tmem_base + acc * BN + j * UN, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
               else
               umma_f16_ss(tmem_base + acc * BN + j * UN, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc,
                           (kb | k) != 0 ? 1u : 0u);
@@ -735,6 +737,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       // accumulator drained by this thread
       tc_fence_before();
+      if constexpr (T::CTA2) {          // the issuing CTA (rank 0) waits for both halves of the M = 256 accumulator
+        if (cta_rank == 0) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      } else
       mbar_arrive(&tempty_bar[acc]);
       if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
