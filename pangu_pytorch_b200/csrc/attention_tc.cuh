@@ -381,6 +381,11 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   auto TR = [](int, int, int, bool) {};
 #endif
   constexpr float kLog2e = 1.4426950408889634f;
+#ifdef PANGU_DEV_SWITCHES   // timing ablations (results invalid): bit0 no tail-warp math, bit1 no exp pass, bit2 no output stores, bit3 no max pass
+  const int dbg = a.debug;
+#else
+  constexpr int dbg = 0;
+#endif
 
   if (warp == ATC_TMA_WARP) {
     // ============================== TMA producer ==============================
@@ -576,6 +581,11 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           // three ranges of 48 keys with a running maximum: 24 scores live at a time (the tail warps share the
           // 128-register budget with everybody else) and ONE copy of the code
           float o[4][4], l0, l1;
+          if (dbg & 1) {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+            l0 = l1 = 1.f;
+          } else
           tail_rows<kFp16>(sk, sv, qa, tb0, tb1, o, l0, l1, lane);
           const float i0 = 1.0f / l0, i1 = 1.0f / l1;
           // stage O in this window's Q rows 128..143 (not read by the M=128 MMA), then 64 B stores
@@ -652,7 +662,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             tc_fence_after();
             TR(3, g, 1, r == 0);
             const float m = s_xm[b * 128 + r];
-            const float l = softmax_row_exp<kFp16>(lane_addr + ATC_COL_S + 144 * b, m);
+            const float l = (dbg & 2) ? 1.f : softmax_row_exp<kFp16>(lane_addr + ATC_COL_S + 144 * b, m);
             TR(3, g, 2, r == 0);
             tmem_st1(lane_addr + ATC_COL_L + b, __float_as_uint(l));
             tmem_st_wait();
@@ -688,7 +698,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             uint8_t* dst = obase + size_t(ooff) * rowb;
             ooff += ostep;
             ooff = ooff >= owrap ? ooff - owrap : ooff;
-            if (!keep) return;
+            if (!keep || (dbg & 4)) return;
             float inv;
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__uint_as_float(ls[0])));
             auto put = [&](const uint32_t (&o)[16], uint8_t* d) {
@@ -712,7 +722,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             mbar_wait(&sfull_bar[b], (g >> 1) & 1);
             tc_fence_after();
             TR(5, g, 1, r == 0);
-            s_xm[b * 128 + r] = softmax_row_max(lane_addr + ATC_COL_S + 144 * b, lane_addr + ATC_COL_BIAS);
+            s_xm[b * 128 + r] = (dbg & 8) ? 0.f : softmax_row_max(lane_addr + ATC_COL_S + 144 * b, lane_addr + ATC_COL_BIAS);
             tc_fence_before();                          // the y stores (already waited for) before the hand-over
             mbar_arrive(&mfull_bar[b]);
             TR(5, g, 2, r == 0);

@@ -46,17 +46,19 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
-static int g_num_sms = 0;
+// Per-DEVICE state (one process may drive several GPUs): SM count, compute capability and the "attribute already set" flags of
+// every kernel instantiation are indexed by the CUDA device that is current when the entry point is called.
+constexpr int kMaxDevices = 64;
+static int g_sms[kMaxDevices] = {0};
+static int g_ccs[kMaxDevices] = {0};
+static std::mutex g_dev_mutex;
+static inline int cur_dev() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < kMaxDevices) ? d : 0; }
+#define g_num_sms (g_sms[cur_dev()])
 static const bool g_pdl = getenv("PANGU_B200_PDL") != nullptr;     // programmatic dependent launch: measured +-0 (17.62 vs 17.56 ms), off by default
-static int g_cc_major = 0;
 static std::once_flag g_once;
 static int g_init_status = 0;
 
 static void init_once() {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) { g_init_status = -3; return; }
-  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&g_cc_major, cudaDevAttrComputeCapabilityMajor, dev);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
@@ -69,7 +71,14 @@ static void init_once() {
 static int ensure_init() {
   std::call_once(g_once, init_once);
   if (g_init_status != 0) return fail(g_init_status, "pangu_b200: CUDA device / driver entry point unavailable");
-  if (g_cc_major != 10) return fail(-5, "pangu_b200: requires an sm_100 (B200) device, found sm_%d*", g_cc_major);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return fail(-3, "pangu_b200: no current CUDA device");
+  if (g_ccs[dev] == 0) {
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&g_ccs[dev], cudaDevAttrComputeCapabilityMajor, dev);
+  }
+  if (g_ccs[dev] != 10) return fail(-5, "pangu_b200: requires an sm_100 (B200) device, found sm_%d* on device %d", g_ccs[dev], dev);
   return 0;
 }
 
@@ -264,10 +273,10 @@ static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t 
   sh.num_k_blocks = (o.k1 + o.k2) / 64;
   sh.k_split = o.k1 / 64;
   auto kern = gemm_kernel<Cfg, kFp16>;
-  static bool attr_done = false;   // per instantiation
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {false};   // per instantiation and device (cudaFuncSetAttribute is per device)
+  if (!attr_done[cur_dev()]) {
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-    attr_done = true;
+    attr_done[cur_dev()] = true;
   }
   constexpr int CL = Cfg::CLUSTER;
   const int units = Cfg::NSPLIT ? sh.num_m_blocks : ((sh.num_m_blocks + CL - 1) / CL) * sh.num_n_blocks;
@@ -286,7 +295,8 @@ static int launch_gemm_t(const GemmOperands& o, const EpiArgs& ep, cudaStream_t 
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl ? 2 : 1;
   // persistent grid: as many clusters as can be co-resident (GPC boundaries may leave a few SMs out for CL = 4)
-  static int max_clusters = 0;     // per instantiation
+  static int max_clusters_dev[kMaxDevices] = {0};     // per instantiation and device
+  int& max_clusters = max_clusters_dev[cur_dev()];
   if (max_clusters == 0) {
     cfg.gridDim = dim3((g_num_sms / CL) * CL);
     int n = 0;
@@ -324,10 +334,10 @@ static int launch_mlp_fused_t(const void* x16_in, const void* w1_16, const void*
     if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled(mlp residual) failed (%d)", int(r));
   }
   auto kern = mlp_fused_kernel<C, kFp16>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {false};
+  if (!attr_done[cur_dev()]) {
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-    attr_done = true;
+    attr_done[cur_dev()] = true;
   }
   const int units = (a.num_tiles + 1) / 2;
   const int max_pairs = g_num_sms / 2;
@@ -462,6 +472,9 @@ extern "C" int pangu_window_attention(const void* qkv16, const float* earth_bias
   a.H = H; a.W = W; a.natural = window_order_out ? 0 : 1;
   a.lon_per_cta = g.nLon;
   a.debug = 0;
+#ifdef PANGU_DEV_SWITCHES
+  if (const char* e = getenv("PANGU_B200_ATTN_DEBUG")) a.debug = atoi(e);
+#endif
   a.trace = nullptr;
 #ifdef PANGU_ATTN_TRACE       // development builds only (-DPANGU_ATTN_TRACE): device pointer of a clock64 timeline buffer
   if (const char* e = getenv("PANGU_B200_ATTN_TRACE")) a.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
@@ -497,7 +510,8 @@ extern "C" int pangu_window_attention(const void* qkv16, const float* earth_bias
   // persistent: one CTA per SM, each takes an equal contiguous share of the (type, head, lon window) units
   const long long units = (long long)g.types * heads * g.nLon;
   const int pgrid = int(units < g_num_sms ? units : g_num_sms);
-  static bool tc_attr[2] = {false, false};
+  static bool tc_attr_dev[kMaxDevices][2] = {{false, false}};
+  bool* tc_attr = tc_attr_dev[cur_dev()];
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(pgrid);
@@ -846,7 +860,8 @@ extern "C" int pangu_wgrad(const void* dy16, int ld_dy, const void* x16, int ld_
   a.splits = splits;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = a.n_tiles * a.k_tiles * a.splits;
-  static bool attr_done[2] = {false, false};
+  static bool attr_done_dev[kMaxDevices][2] = {{false, false}};
+  bool* attr_done = attr_done_dev[cur_dev()];
   if (fp16) {
     if (!attr_done[1]) { PG_CUDA(cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES)); attr_done[1] = true; }
     wgrad_kernel<true><<<grid, WG_THREADS, WG_SMEM_BYTES, s>>>(mdy, mx, a);
@@ -937,7 +952,8 @@ extern "C" int pangu_window_attention_bwd(const void* qkv16, const void* datt16w
   const long long units = (long long)g.types * heads * g.nLon;
   const int grid = int(units < g_num_sms ? units : g_num_sms);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static bool attr_done[2] = {false, false};
+  static bool attr_done_dev[kMaxDevices][2] = {{false, false}};
+  bool* attr_done = attr_done_dev[cur_dev()];
   if (fp16) {
     if (!attr_done[1]) { PG_CUDA(cudaFuncSetAttribute(window_attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_SMEM_BYTES)); attr_done[1] = true; }
     window_attention_bwd_kernel<true><<<grid, ATB_THREADS, ATB_SMEM_BYTES, s>>>(a);

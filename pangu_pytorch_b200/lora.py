@@ -169,7 +169,24 @@ def add_lora(model, r: int = 16, lora_alpha: float = 16.0, lora_dropout: float =
     return model
 
 
-def peft_state_dict(model, prefix: str = "base_model.model.") -> Dict[str, torch.Tensor]:
-    """``state_dict`` with peft's key prefix, i.e. what the reference saves for a LoRA run
-    (models/pangu_sample.py:94-98); ``merge_lora_state_dict`` reads it back."""
-    return {prefix + k: v for k, v in model.state_dict().items()}
+def peft_state_dict(model, prefix: str = "base_model.model.", adapter: str = "default",
+                    modules_to_save=("_output_layer.conv_surface", "_output_layer.conv"),
+                    originals: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """``peft_model.state_dict()`` as the reference saves it for a LoRA run (models/pangu_sample.py:94-98), so that
+    the checkpoint loads into the reference's ``peft_model`` (inference/test_lora.py:72) as well as back into this
+    package (``merge_lora_state_dict``).  peft's ``ModulesToSaveWrapper`` stores every ``modules_to_save`` module twice:
+    ``<path>.original_module.<p>`` (the frozen tensor the run started from) and ``<path>.modules_to_save.<adapter>.<p>``
+    (the trained copy).  Here the module holds only the trained tensor; ``originals`` may supply the start values
+    (``{"<path>.<p>": tensor}``), otherwise the trained values are written to both entries."""
+    saved = tuple(modules_to_save)
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in model.state_dict().items():
+        mod = next((m for m in saved if k.startswith(m + ".")), None)
+        if mod is None:
+            out[prefix + k] = v
+            continue
+        p = k[len(mod) + 1:]
+        orig = v if originals is None or k not in originals else originals[k]
+        out[f"{prefix}{mod}.original_module.{p}"] = orig
+        out[f"{prefix}{mod}.modules_to_save.{adapter}.{p}"] = v
+    return out

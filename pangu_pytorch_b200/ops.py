@@ -43,6 +43,10 @@ def _p(t: Optional[Tensor], dtype=None, name: str = "tensor"):
         raise ValueError(f"{name} must be contiguous")
     if dtype is not None and t.dtype != dtype:
         raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if _DEVICE[0] is None:
+        _DEVICE[0] = t.device.index
+    elif _DEVICE[0] != t.device.index:
+        raise ValueError(f"{name} is on cuda:{t.device.index}, other operands of the call on cuda:{_DEVICE[0]}")
     return c_void_p(t.data_ptr())
 
 
@@ -80,7 +84,28 @@ def set_tag(tag: str) -> None:
     _TAG[0] = tag
 
 
+_DEVICE = [None]         # device of the tensors of the call being marshalled (set by _p)
+
+
 def _call(name, *args, kernels=None):
+    # The library launches on the CURRENT CUDA device: make sure that is the device the tensors live on (a model on
+    # cuda:1 while cuda:0 is current would otherwise get wrong-device launches).
+    dev, _DEVICE[0] = _DEVICE[0], None
+    if dev is not None and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return _call_on_current(name, *_restream(args), kernels=kernels)
+    return _call_on_current(name, *args, kernels=kernels)
+
+
+def _restream(args):
+    """The stream argument was taken on the previously current device: re-take it on the tensors' device."""
+    args = list(args)
+    if args and isinstance(args[-1], c_void_p):
+        args[-1] = _stream()
+    return args
+
+
+def _call_on_current(name, *args, kernels=None):
     prof = _PROFILE[0]
     if prof is None:
         _lib.call(name, *args)

@@ -220,7 +220,16 @@ def test_add_lora_wraps_67_linears_and_round_trips():
     mod.invalidate()                                                                    # ... so such writers must say so
     eff = mod.base_layer.weight + mod.scaling * (mod.B @ mod.A)
     assert torch.allclose(mod.weight, eff.detach(), atol=1e-5)
-    merged = lora.merge_lora_state_dict(lora.peft_state_dict(m))
+    peft_sd = lora.peft_state_dict(m)
+    # peft's key layout: wrapped linears as base_layer / lora_A / lora_B, modules_to_save stored twice (ModulesToSaveWrapper)
+    pre = "base_model.model."
+    assert pre + n0 + ".base_layer.weight" in peft_sd and pre + n0 + ".lora_A.default.weight" in peft_sd
+    for conv in ("_output_layer.conv", "_output_layer.conv_surface"):
+        for pname in ("weight", "bias"):
+            assert f"{pre}{conv}.original_module.{pname}" in peft_sd and f"{pre}{conv}.modules_to_save.default.{pname}" in peft_sd
+            assert f"{pre}{conv}.{pname}" not in peft_sd
+    assert len(peft_sd) == 223 + 2 * 67 + 4
+    merged = lora.merge_lora_state_dict(peft_sd)
     assert sorted(merged) == sorted(plain_keys)
     assert torch.allclose(merged[n0 + ".weight"], eff.detach(), atol=1e-6)
     pb.PanguModel(device="cpu").load_state_dict(merged, strict=True)
