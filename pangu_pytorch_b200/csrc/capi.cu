@@ -15,6 +15,7 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "mlp_fused.cuh"
+#include "mlp_fused2.cuh"
 #include "wgrad.cuh"
 
 using namespace pg;
@@ -360,6 +361,45 @@ static int launch_mlp_fused_t(const void* x16_in, const void* w1_16, const void*
   return 0;
 }
 
+// C = 384: CTA pairs on tcgen05.mma.cta_group::2 (csrc/mlp_fused2.cuh)
+template <bool kFp16>
+static int launch_mlp_fused2_t(const void* x16_in, const void* w1_16, const void* w2_16, const MlpArgs& a, cudaStream_t stream) {
+  using T = Mlp2Traits;
+  constexpr int C = T::C;
+  CUtensorMap mx, m1, m2;
+  PG_TRY(make_map(&mx, x16_in, a.T, C, C, 128));
+  PG_TRY(make_map(&m1, w1_16, 4 * C, C, C, 32));          // W1 [4C, C]: this CTA's 32 of a chunk's 64 hidden rows
+  PG_TRY(make_map(&m2, w2_16, C, 4 * C, 4 * C, 96));      // W2 [C, 4C]: this CTA's 96 of the 192 output rows of an N half
+  PG_REQUIRE((reinterpret_cast<uintptr_t>(a.x32) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out16) & 7) == 0 &&
+             (reinterpret_cast<uintptr_t>(a.b2) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.gamma) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(a.beta) & 15) == 0, "mlp: residual stream / LayerNorm parameters not 16 B aligned");
+  auto kern = mlp_fused2_kernel<kFp16>;
+  static bool attr_done[kMaxDevices] = {false};
+  if (!attr_done[cur_dev()]) {
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+    attr_done[cur_dev()] = true;
+  }
+  const int units = (a.num_tiles + 1) / 2;
+  const int max_pairs = g_num_sms / 2;
+  const int pairs = units < max_pairs ? units : max_pairs;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(T::THREADS);
+  cfg.dynamicSmemBytes = T::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PG_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, m1, m2, a));
+  PG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static EpiArgs epi_defaults() {
   EpiArgs e;
   memset(&e, 0, sizeof(e));
@@ -574,7 +614,7 @@ extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, cons
   // Y accumulator), loses at C = 384 (TMEM holds a single Y).  It is taken when the caller does not ask for the hidden
   // activation (ws_hidden == NULL; the training tape does ask).  PANGU_B200_MLP_FUSED = 0: never, 1: whenever allowed.
   static const int fused_mode = getenv("PANGU_B200_MLP_FUSED") ? atoi(getenv("PANGU_B200_MLP_FUSED")) : -1;
-  const bool fused = ws_hidden == nullptr && C == 192 && fused_mode != 0;
+  const bool fused = ws_hidden == nullptr && fused_mode != 0;
   PG_REQUIRE(fused || ws_hidden != nullptr, "mlp_ln_residual: ws_hidden is required on the two-kernel path (C=%d)", C);
   if (fused) {
     // one kernel: the hidden activation stays in tensor memory (ws_hidden is not touched)
@@ -589,6 +629,7 @@ extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, cons
 #ifdef PANGU_DEV_SWITCHES
     if (const char* d = getenv("PANGU_B200_GEMM_DEBUG")) a.debug = atoi(d);
 #endif
+    if (C == 384) return fp16 ? launch_mlp_fused2_t<true>(x16_in, w1_16, w2_16, a, s) : launch_mlp_fused2_t<false>(x16_in, w1_16, w2_16, a, s);
     return fp16 ? launch_mlp_fused_t<192, true>(x16_in, w1_16, w2_16, a, s) : launch_mlp_fused_t<192, false>(x16_in, w1_16, w2_16, a, s);
   }
   {

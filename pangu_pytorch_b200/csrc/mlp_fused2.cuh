@@ -1,0 +1,427 @@
+// Single-kernel Mlp + LayerNorm + residual at C = 384 on CTA PAIRS (reference models/layers.py:250-251, 264-270):
+//
+//     x <- x + s * LN2( GELU(x16 W1^T + b1) W2^T + b2 )
+//
+// The C = 192 kernel (mlp_fused.cuh) keeps X, two weight rings and the H operand in one SM's shared memory and two Y
+// accumulators in its TMEM; at C = 384 neither fits (X alone is 96 KB, one Y is 384 of the 512 TMEM columns).  Here a CTA
+// pair works on 256 tokens with tcgen05.mma.cta_group::2: every MMA has M = 256 (rows 0..127 in CTA 0, 128..255 in CTA 1)
+// and each CTA holds only HALF of every weight tile, which is what makes the shared-memory budget close:
+//
+//   X tile     [128 x 384] 16-bit, own rows                                  96 KB   (resident for the tile)
+//   W1 ring    2 units [32 of the 64 hidden rows of a chunk x 384 k]      2 x 24 KB
+//   W2 ring    3 units [96 of the 192 output rows of an N half x 64 k]    3 x 12 KB
+//   H operand  2 buffers [128 x 64] 16-bit (GELU output, A of GEMM2)      2 x 16 KB
+//   b1, b2, gamma, beta 10.5 KB, barriers; the LayerNorm epilogue stages its chunks in the (then idle) H buffers     total 222.9 KB
+//
+// TMEM (per CTA, its 128 rows): Y [0,384) | Hacc0 [384,448) | Hacc1 [448,512).
+// Per chunk c of 64 hidden units (24 per tile):  G1(c): Hacc[c&1] = X W1[c]^T  (M 256, N 64, K 384);  GELU warps:
+// Hacc -> registers -> bias + exact GELU -> H[c&1] in shared memory (K-major SWIZZLE_128B);  G2(c): Y += H W2[:, c]^T
+// (M 256, N 2 x 192, K 64).  With a single Y accumulator the LayerNorm epilogue of a tile overlaps only the first two
+// G1 chunks of the next one (~10 % of a tile).
+//
+// Only CTA 0 (the leader) issues MMAs.  Hand-overs that involve both CTAs:
+//   * TMA loads of both CTAs complete on the LEADER's full barriers (cta_group::2 form of cp.async.bulk.tensor);
+//   * "slot / buffer free" and "accumulator ready" signals are tcgen05.commit.cta_group::2 multicasts to both CTAs;
+//   * "my threads are done with X" goes straight to the LEADER's barrier from both CTAs (the peer's threads arrive
+//     remotely): relaxed arrives where only reads have to be finished (Hacc in registers, Y drained: tcgen05.wait::ld has
+//     completed them), one release.cluster arrive per GELU warp for the H tile it wrote to its shared memory.
+//     (A first version relayed the peer's local barriers through its idle issuer warps: 461 us per launch.)
+// Warps (480 threads): 0 TMA producer, 1 GEMM1 issuer (leader only), 2 GEMM2 issuer (leader only),
+// 3-6 LayerNorm epilogue, 7-14 GELU (two warpgroups alternate chunks) + their share of the epilogue.
+#pragma once
+#include "common.cuh"
+#include "geometry.cuh"
+#include "mlp_fused.cuh"
+
+namespace pg {
+
+struct Mlp2Traits {
+  static constexpr int C = 384, KX = 6, NCH = 24, NB = 2, NHS = 2, S1 = 2, S2 = 3, LNW = 4;
+  static constexpr int X_BYTES = KX * 16384;
+  static constexpr int R1_UNIT = KX * 4096;            // 32 hidden rows x 64 k per slab, 6 slabs
+  static constexpr int R2_UNIT = 96 * 128;             // 96 output rows x 64 k
+  static constexpr int OFF_R1 = X_BYTES;
+  static constexpr int OFF_R2 = OFF_R1 + S1 * R1_UNIT;
+  static constexpr int OFF_H = OFF_R2 + S2 * R2_UNIT;
+  // The LayerNorm epilogue stages its [32 rows x 32 fp32] chunks in the H operand buffers (2 x 4 KB per epilogue warp = the
+  // 32 KB of the two H buffers): between "Y complete" and the end of the epilogue no GEMM2 reads H, and the GELU warps wait
+  // for the epilogue (lnfree) before they write the first H chunks of the next tile.
+  static constexpr int OFF_PAR = OFF_H + NHS * 16384;  // b1 [4C], b2 / gamma / beta [C] fp32
+  static constexpr int OFF_BAR = OFF_PAR + 7 * C * 4;
+  static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + 2 * NB + 2 * NHS + 2 + 1;
+  static constexpr int SMEM_BYTES = OFF_BAR + ((NUM_BARS * 8 + 16 + 127) / 128) * 128;
+  static constexpr int THREADS = 32 * (3 + LNW + 8);
+  static_assert(OFF_R1 % 1024 == 0 && OFF_R2 % 1024 == 0 && OFF_H % 1024 == 0 && R1_UNIT % 1024 == 0 && R2_UNIT % 1024 == 0,
+                "operand alignment");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t rbar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+
+template <bool kFp16>
+__global__ void __launch_bounds__(Mlp2Traits::THREADS, 1)
+mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                  const __grid_constant__ CUtensorMap tmW2, const MlpArgs a) {
+  using T = Mlp2Traits;
+  constexpr int C = T::C, KX = T::KX, NCH = T::NCH, S1 = T::S1, S2 = T::S2, NB = T::NB, NHS = T::NHS;
+  extern __shared__ __align__(1024) uint8_t mf2_raw[];
+  if ((smem_u32(mf2_raw) & 1023u) != 0u) __trap();     // SWIZZLE_128B tiles need 1024 B alignment; there is no slack to fix it up
+  uint8_t* smem = mf2_raw;
+  uint8_t* xs = smem;
+  uint8_t* r1 = smem + T::OFF_R1;
+  uint8_t* r2 = smem + T::OFF_R2;
+  uint8_t* hs = smem + T::OFF_H;
+  float* s_b1 = reinterpret_cast<float*>(smem + T::OFF_PAR);
+  float* s_b2 = s_b1 + 4 * C;
+  float* s_gamma = s_b2 + C;
+  float* s_beta = s_gamma + C;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T::OFF_BAR);
+  uint64_t* xfull = bars;                      // [KX]  leader: X slabs of both CTAs landed
+  uint64_t* xempty = xfull + KX;               // [KX]  each CTA: GEMM1 of the tile no longer reads the slab (commit multicast)
+  uint64_t* r1full = xempty + KX;              // [S1]  leader
+  uint64_t* r1empty = r1full + S1;             // [S1]  each CTA (commit multicast)
+  uint64_t* r2full = r1empty + S1;             // [S2]  leader
+  uint64_t* r2empty = r2full + S2;             // [S2]  each CTA
+  uint64_t* hfull = r2empty + S2;              // [NB]  each CTA: Hacc ready (commit multicast)
+  uint64_t* hempty = hfull + NB;               // [NB]  leader: the 2 x 128 GELU threads of the pair hold Hacc in registers
+  uint64_t* sfull = hempty + NB;               // [NHS] leader: the 2 x 4 GELU warps of the pair have written H
+  uint64_t* sempty = sfull + NHS;              // [NHS] each CTA: GEMM2 has read H (commit multicast)
+  uint64_t* yfull = sempty + NHS;              // [1]   each CTA: Y complete (commit multicast)
+  uint64_t* yempty = yfull + 1;                // [1]   leader: the 2 x 384 epilogue threads of the pair have drained Y
+  uint64_t* lnfree = yempty + 1;               // [1]   each CTA: its 384 epilogue threads no longer use the H buffers as staging
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lnfree + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta_rank = int(cluster_ctarank());
+  const bool leader = cta_rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_units = (a.num_tiles + 1) >> 1;        // a unit = two consecutive 128-token tiles, one per CTA of the pair
+  const int my_units = (num_units - pair + num_pairs - 1) / num_pairs;
+  const int total = my_units * NCH;                    // chunks this pair walks
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    for (int k = 0; k < KX; ++k) { mbar_init(&xfull[k], 1); mbar_init(&xempty[k], 1); }
+    for (int s = 0; s < S1; ++s) { mbar_init(&r1full[s], 1); mbar_init(&r1empty[s], 1); }
+    for (int s = 0; s < S2; ++s) { mbar_init(&r2full[s], 1); mbar_init(&r2empty[s], 1); }
+    for (int b = 0; b < NB; ++b) { mbar_init(&hfull[b], 1); mbar_init(&hempty[b], 256); }
+    for (int b = 0; b < NHS; ++b) { mbar_init(&sfull[b], 8); mbar_init(&sempty[b], 1); }
+    mbar_init(yfull, 1); mbar_init(yempty, 768); mbar_init(lnfree, 384);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_cta2<512>(tmem_slot);
+  for (int i = threadIdx.x; i < 4 * C; i += T::THREADS) s_b1[i] = a.b1[i];
+  for (int i = threadIdx.x; i < C; i += T::THREADS) { s_b2[i] = a.b2[i]; s_gamma[i] = a.gamma[i]; s_beta[i] = a.beta[i]; }
+  tc_fence_before();
+  cluster_sync_all();          // peer barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  if (*tmem_slot != 0u) __trap();      // all 512 columns: the allocation starts at TMEM address 0
+  constexpr uint32_t tmem = 0u;
+  constexpr uint32_t COL_H = 384;
+#ifdef PANGU_DEV_SWITCHES     // timing ablations (results invalid): bit2 LayerNorm epilogue reduced to its handshakes, bit3 no GELU arithmetic,
+  const int dbg = a.debug;    // bit4 no GEMM1 MMAs, bit5 no GEMM2 MMAs
+#else
+  constexpr int dbg = 0;
+#endif
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    // issue order == consumption order of the MMA warps:  X(tile), W1(0), then per chunk  W1(c+1), W2(c)
+    if (lane == 0) {
+      int p1 = 0, p2 = 0;
+      auto lbar = [&](uint64_t* b) { return mapa_u32(smem_u32(b), 0); };
+      auto load_w1 = [&](int c) {
+        const int s = p1 % S1;
+        mbar_wait(&r1empty[s], ((p1 / S1) & 1) ^ 1);
+        if (leader) mbar_arrive_expect_tx(&r1full[s], 2 * T::R1_UNIT);
+        for (int k = 0; k < KX; ++k)     // this CTA's 32 of the chunk's 64 hidden rows
+          tma_load_2d_cta2(&tmW1, lbar(&r1full[s]), r1 + s * T::R1_UNIT + k * 4096, k * 64, c * 64 + cta_rank * 32, kEvictLast);
+        ++p1;
+      };
+      auto load_w2 = [&](int c) {
+        for (int h = 0; h < 2; ++h, ++p2) {
+          const int s = p2 % S2;
+          mbar_wait(&r2empty[s], ((p2 / S2) & 1) ^ 1);
+          if (leader) mbar_arrive_expect_tx(&r2full[s], 2 * T::R2_UNIT);
+          tma_load_2d_cta2(&tmW2, lbar(&r2full[s]), r2 + s * T::R2_UNIT, c * 64, h * 192 + cta_rank * 96, kEvictLast);
+        }
+      };
+      auto load_x = [&](int tile, int use) {
+        for (int k = 0; k < KX; ++k) {
+          mbar_wait(&xempty[k], (use & 1) ^ 1);
+          if (leader) mbar_arrive_expect_tx(&xfull[k], 2 * 16384);
+          tma_load_2d_cta2(&tmX, lbar(&xfull[k]), xs + k * 16384, k * 64, tile * 128, kEvictFirst);   // rows >= T read as zero
+        }
+      };
+      // The epilogue reads and rewrites this CTA's 128 x 384 fp32 residual rows (196 KB, contiguous).  All CTAs reach their
+      // epilogues at about the same time and nothing else of the kernel touches HBM then, so the rows are pulled into L2
+      // while the second half of the mainloop runs: the epilogue then works out of L2 and its write-back overlaps the next tile.
+      auto prefetch_resid = [&](int tile) {
+        const long long row0 = (long long)tile * 128;
+        const long long rows = row0 + 128 <= a.T ? 128 : (a.T > row0 ? a.T - row0 : 0);
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(a.x32 + row0 * C);
+        for (long long off = 0; off < rows * C * 4; off += 16384)
+          bulk_prefetch_l2(p + off, uint32_t(rows * C * 4 - off < 16384 ? rows * C * 4 - off : 16384));
+      };
+      for (int cgx = 0; cgx < total + NB - 1; ++cgx) {
+        if (cgx < total) {
+          const int tu = cgx / NCH, c = cgx % NCH;
+          if (c == 0) load_x(2 * (pair + tu * num_pairs) + cta_rank, tu);
+          if (c == NCH / 2) prefetch_resid(2 * (pair + tu * num_pairs) + cta_rank);
+          load_w1(c);
+        }
+        if (cgx >= NB - 1) load_w2((cgx - (NB - 1)) % NCH);
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ================================ GEMM1 issuer ================================
+      constexpr uint32_t idesc1 = make_idesc_f16(256, 64, kFp16);
+      const uint32_t xs_u32 = smem_u32(xs), r1_u32 = smem_u32(r1);
+      for (int cgx = 0; cgx < total; ++cgx) {
+        const int c = cgx % NCH, tu = cgx / NCH, hb = cgx % NB, s = cgx % S1;
+        mbar_wait(&hempty[hb], ((cgx / NB) & 1) ^ 1);        // both CTAs' GELU warps hold the buffer's previous contents
+        if (c == 0) {
+          for (int k = 0; k < KX; ++k) mbar_wait(&xfull[k], tu & 1);
+        }
+        mbar_wait(&r1full[s], (cgx / S1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < KX; ++k) {
+            const uint64_t da = make_sdesc_sw128(xs_u32 + k * 16384);
+            const uint64_t db = make_sdesc_sw128(r1_u32 + s * T::R1_UNIT + k * 4096);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              if (!(dbg & 16))
+              umma_f16_ss_cta2(tmem + COL_H + 64 * hb, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc1, (k | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit_cta2(&r1empty[s]);
+          if (c == NCH - 1) {
+            for (int k = 0; k < KX; ++k) umma_commit_cta2(&xempty[k]);     // last reader of the X slabs
+          }
+          umma_commit_cta2(&hfull[hb]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 2) {
+    if (leader) {
+      // ================================ GEMM2 issuer ================================
+      constexpr uint32_t idesc2 = make_idesc_f16(256, 192, kFp16);
+      const uint32_t hs_u32 = smem_u32(hs), r2_u32 = smem_u32(r2);
+      int p2 = 0;
+      for (int cgx = 0; cgx < total; ++cgx) {
+        const int c = cgx % NCH, tu = cgx / NCH, sb = cgx % NHS;
+        if (c == 0) {                                        // both CTAs' LayerNorm warps have drained Y of the previous tile
+          mbar_wait(yempty, (tu & 1) ^ 1);
+        }
+        mbar_wait_cluster(&sfull[sb], (cgx / NHS) & 1);      // GELU(H) of this chunk is in both CTAs' shared memory
+        tc_fence_after();
+        const uint64_t da = make_sdesc_sw128(hs_u32 + sb * 16384);
+        for (int h = 0; h < 2; ++h, ++p2) {
+          const int s = p2 % S2;
+          mbar_wait(&r2full[s], (p2 / S2) & 1);
+          tc_fence_after();
+          const uint64_t db = make_sdesc_sw128(r2_u32 + s * T::R2_UNIT);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)     // K = 64 hidden units
+              if (!(dbg & 32))
+              umma_f16_ss_cta2(tmem + h * 192, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc2, (c | kk) != 0 ? 1u : 0u);
+            umma_commit_cta2(&r2empty[s]);
+            if (h == 1) umma_commit_cta2(&sempty[sb]);
+            if (c == NCH - 1 && h == 1) umma_commit_cta2(yfull);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ================================ GELU + LayerNorm warps (both CTAs, own 128 rows) ================================
+    // Warps 7-14 (two warpgroups, alternate chunks): Hacc -> registers (the TMEM buffer goes straight back to GEMM1) ->
+    // bias + exact GELU -> 16-bit H tile in shared memory (K-major SWIZZLE_128B A operand of GEMM2).
+    // At the end of a tile ALL twelve warps (3-6 and 7-14: three per TMEM lane quadrant) run the LayerNorm + residual
+    // epilogue: every warp computes the row statistics of its 32 rows (thread = row) and normalises every third 16-column
+    // chunk, staged through a swizzled [32 x 16] fp32 tile in the then idle H buffers so that global accesses are 64 B row
+    // segments (4 lanes per row).  With the four LayerNorm warps alone the epilogue took 40 000 clk per tile (1 warp per
+    // scheduler, latency bound), half as long as the 24 chunks of the mainloop.
+    const bool is_gelu = warp >= 3 + T::LNW;
+    const int quad = warp & 3;
+    const int wgp = is_gelu ? (warp - (3 + T::LNW)) >> 2 : 0;
+    const int part = is_gelu ? 1 + wgp : 0;              // which third of the 16-column chunks this warp normalises
+    const uint32_t haddr = tmem + (uint32_t(quad * 32) << 16) + COL_H + 64 * wgp;
+    const uint32_t tacc = tmem + (uint32_t(quad * 32) << 16);
+    const int row = quad * 32 + lane;
+    uint8_t* hrow = hs + wgp * 16384 + row * 128;
+    uint8_t* stage = hs + (part * 4 + quad) * 2048;
+    const Geo geo = make_geo(a.Z, a.H, a.W);
+    const int pc = lane & 3;                             // 16 B piece of a 64 B row segment handled by this lane in phase B
+    int n = 0;           // chunks this GELU warpgroup has processed
+    for (int tu = 0; tu < my_units; ++tu) {
+      if (is_gelu) {
+        for (int c = wgp; c < NCH; c += 2, ++n) {
+          mbar_wait(&hfull[wgp], n & 1);
+          tc_fence_after();
+          uint32_t r[2][32];
+          tmem_ld32(haddr, r[0]);
+          tmem_ld32(haddr + 32, r[1]);
+          tmem_ld_wait();
+          tc_fence_before();
+          if (leader) mbar_arrive(&hempty[wgp]); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&hempty[wgp]), 0));
+          uint32_t pk[32];
+          const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 64);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[hh * 8 + j4];
+              float v0 = __uint_as_float(r[hh][4 * j4]) + bb.x, v1 = __uint_as_float(r[hh][4 * j4 + 1]) + bb.y;
+              float v2 = __uint_as_float(r[hh][4 * j4 + 2]) + bb.z, v3 = __uint_as_float(r[hh][4 * j4 + 3]) + bb.w;
+              if (!(dbg & 8)) {
+                gelu_erf2(v0, v1);
+                gelu_erf2(v2, v3);
+              }
+              pk[hh * 16 + 2 * j4] = pack16<kFp16>(v0, v1);
+              pk[hh * 16 + 2 * j4 + 1] = pack16<kFp16>(v2, v3);
+            }
+          }
+          mbar_wait(&sempty[wgp], (n & 1) ^ 1);        // GEMM2 of this warpgroup's previous chunk has read the buffer
+          if (c == wgp && tu > 0) mbar_wait(lnfree, (tu - 1) & 1);   // ... and nobody stages the previous tile's epilogue in it
+#pragma unroll
+          for (int q = 0; q < 8; ++q)                  // 8 x 16 B = this row's 64 hidden units, XOR-swizzled 16 B chunks
+            *reinterpret_cast<uint4*>(hrow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {          // one arrival per warp: its 32 rows of H are written and visible to the async proxy
+            if (leader) mbar_arrive(&sfull[wgp]); else mbar_arrive_remote_release(mapa_u32(smem_u32(&sfull[wgp]), 0));
+          }
+        }
+      }
+      // ------------------------------ LayerNorm + residual epilogue of tile tu (this warp's third of the chunks) ------------------------------
+      const int tile = 2 * (pair + tu * num_pairs) + cta_rank;
+      const int g = tile * 128 + quad * 32 + lane;
+      const int my_tok = g < a.T ? g : -1;
+      const int my_dst = (my_tok >= 0 && a.roll_out >= 0) ? token_to_win_row(geo, my_tok, a.roll_out) : my_tok;
+      // phase-B items of this lane: row rr = it * 8 + (lane >> 2), it = 0..3
+      int toks[4], dsts[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        toks[it] = __shfl_sync(0xffffffffu, my_tok, it * 8 + (lane >> 2));
+        dsts[it] = __shfl_sync(0xffffffffu, my_dst, it * 8 + (lane >> 2));
+      }
+      auto load_resid = [&](int c0, uint4 (&dst)[4]) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          dst[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (toks[it] >= 0) dst[it] = ldg16(a.x32 + size_t(toks[it]) * C + c0 + pc * 4);
+        }
+      };
+      uint4 resq[4];
+      load_resid(16 * part, resq);
+      mbar_wait(yfull, tu & 1);
+      tc_fence_after();
+      if (dbg & 4) {
+        tc_fence_before();
+        if (leader) mbar_arrive(yempty); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(yempty), 0));
+        mbar_arrive(lnfree);
+        continue;
+      }
+      float mean, rstd;
+      {
+        float shift = 0.f;
+        f32x2 s1 = pack2(0.f, 0.f), s2 = pack2(0.f, 0.f);
+#pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tacc + c0, r);
+          tmem_ld_wait();
+          if (c0 == 0) shift = __uint_as_float(r[0]) + s_b2[0];
+          const f32x2 nshift = pack2(-shift, -shift);
+          const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = b4[j4];
+            const f32x2 v01 = add2(add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y)), nshift);
+            const f32x2 v23 = add2(add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w)), nshift);
+            s1 = add2(s1, add2(v01, v23));
+            s2 = fma2(v01, v01, s2);
+            s2 = fma2(v23, v23, s2);
+          }
+        }
+        float s1a, s1b, s2a, s2b;
+        unpack2(s1, s1a, s1b);
+        unpack2(s2, s2a, s2b);
+        const float inv_n = 1.0f / float(C);
+        const float m = (s1a + s1b) * inv_n;
+        const float var = fmaxf((s2a + s2b) * inv_n - m * m, 0.f);
+        mean = shift + m;
+        rstd = rsqrtf(var + a.eps);
+      }
+      const f32x2 ln_a = pack2(rstd, rstd), ln_b = pack2(-mean * rstd, -mean * rstd);
+#pragma unroll 1
+      for (int c0 = 16 * part; c0 < C; c0 += 48) {
+        {
+          // phase A: TMEM -> registers -> (acc + b2 - mean) * rstd * gamma + beta -> tile (row per lane)
+          uint32_t r[16];
+          tmem_ld16(tacc + c0, r);
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
+          const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
+          const float4* e4 = reinterpret_cast<const float4*>(s_beta + c0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bb = b4[j4], gg = g4[j4], ee = e4[j4];
+            f32x2 v01 = add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y));
+            f32x2 v23 = add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w));
+            v01 = fma2(fma2(v01, ln_a, ln_b), pack2(gg.x, gg.y), pack2(ee.x, ee.y));
+            v23 = fma2(fma2(v23, ln_a, ln_b), pack2(gg.z, gg.w), pack2(ee.z, ee.w));
+            float v0, v1, v2, v3;
+            unpack2(v01, v0, v1);
+            unpack2(v23, v2, v3);
+            *reinterpret_cast<uint4*>(stage + lane * 64 + ((j4 ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+          }
+        }
+        if (c0 + 48 >= C) {          // this thread has read the accumulator for the last time: hand Y back
+          tc_fence_before();
+          if (leader) mbar_arrive(yempty); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(yempty), 0));
+        }
+        __syncwarp();
+        // phase B: tile -> global (4 lanes per row), + residual; fp32 stream (in place) and 16-bit shadow
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          if (toks[it] < 0) continue;
+          const int rr = it * 8 + (lane >> 2);
+          const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4));
+          const uint4 q = resq[it];
+          const float f0 = fmaf(a.res_scale, __uint_as_float(v.x), __uint_as_float(q.x));
+          const float f1 = fmaf(a.res_scale, __uint_as_float(v.y), __uint_as_float(q.y));
+          const float f2 = fmaf(a.res_scale, __uint_as_float(v.z), __uint_as_float(q.z));
+          const float f3 = fmaf(a.res_scale, __uint_as_float(v.w), __uint_as_float(q.w));
+          const int col = c0 + pc * 4;
+          stg16(a.x32 + size_t(toks[it]) * C + col,
+                make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)));
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.out16) + size_t(dsts[it]) * C + col) =
+              make_uint2(pack16<kFp16>(f0, f1), pack16<kFp16>(f2, f3));
+        }
+        __syncwarp();                 // the tile is rewritten by the next chunk's phase A
+        if (c0 + 48 < C) load_resid(c0 + 48, resq);     // residual of this warp's next chunk: in flight during its phase A
+      }
+      mbar_arrive(lnfree);           // this thread no longer touches the H buffers
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // no multicast commit / remote arrive may target an exited CTA
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cta2<512>(tmem);
+  }
+}
+
+}  // namespace pg

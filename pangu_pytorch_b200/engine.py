@@ -9,7 +9,7 @@ HBM layout of one resolution (``GridWorkspace``), T = Z*H*W real tokens, Tp = wi
                              pad rows are zeroed once here and never written again
     qkv      [3C/32, Tp', 32] 16-bit, one plane per (q|k|v, head), window order rows, q pre-scaled
     att      [Tp, C ] 16-bit heads merged; the block path uses the first T rows in NATURAL token order
-    hidden   [T , 4C] 16-bit GELU(linear1) activations (C = 384 only: at C = 192 they stay in tensor memory)
+    hidden   [T , 4C] 16-bit GELU(linear1) activations: training tape only (inference keeps them on the SM)
 """
 from __future__ import annotations
 
@@ -101,8 +101,9 @@ class GridWorkspace:
         # head-major: [3*heads planes][Tp rounded up to 128][32] (csrc/attention_tc.cuh)
         self.qkv = torch.empty(3 * C // 32, (Tp + 127) // 128 * 128, 32, dtype=h, device=device)
         self.att = torch.empty(Tp, C, dtype=h, device=device)
-        # Mlp hidden activations: not materialised at C = 192 (single-kernel Mlp); the training tape supplies its own
-        self.hidden = None if C == 192 else torch.empty(T, 4 * C, dtype=h, device=device)
+        # Mlp hidden activations are never materialised on the inference path (single-kernel Mlp at both resolutions:
+        # csrc/mlp_fused.cuh at C = 192, the CTA-pair kernel csrc/mlp_fused2.cuh at C = 384); the training tape supplies its own
+        self.hidden = None
 
 
 _WORKSPACES: Dict[tuple, GridWorkspace] = {}

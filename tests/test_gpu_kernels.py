@@ -245,20 +245,25 @@ def test_full_025_forward_against_reference_golden(fmt, kind):
 
 @pytest.mark.parametrize("fmt", FORMATS)
 @pytest.mark.parametrize("roll_out", [-1, 0, 1])
-def test_mlp_single_kernel_matches_two_kernel_path(fmt, roll_out):
-    """pangu_mlp_ln_residual at C=192: the single-kernel path (no hidden-activation workspace; GELU output kept on the
-    SM) against the two-GEMM path (hidden activation through HBM) on the same operands -- same fp32 accumulation, same
-    16-bit rounding of the hidden activation, so only the summation order inside GEMM2 differs."""
+@pytest.mark.parametrize("grid", [(8, 181, 24, 192), (8, 91, 24, 384), (8, 91, 180, 384)], ids=["hi", "lo", "lo-full"])
+def test_mlp_single_kernel_matches_two_kernel_path(fmt, roll_out, grid):
+    """pangu_mlp_ln_residual: the single-kernel path (no hidden-activation workspace; GELU output kept on the SM --
+    csrc/mlp_fused.cuh at C=192, the CTA-pair cta_group::2 kernel csrc/mlp_fused2.cuh at C=384) against the two-GEMM path
+    (hidden activation through HBM) on the same operands -- same fp32 accumulation, same 16-bit rounding of the hidden
+    activation, so only the summation order inside GEMM2 differs.  "lo-full" is the whole 0.25 degree C=384 grid: every
+    CTA pair walks seven tile pairs, so all barrier phases wrap."""
     from pangu_pytorch_b200 import engine, ops
     fp16 = _fmt(fmt)
-    Z, H, W, C = 8, 181, 24, 192
+    Z, H, W, C = grid
+    if W > 24 and roll_out == 0:
+        pytest.skip("the full grid is run for one window-order and the natural-order output only")
     ws = engine.workspace(DEV, Z, H, W, C)
     g = torch.Generator().manual_seed(21 + roll_out)
     h16 = ops.dtype16(fp16)
     x16 = _round16(torch.randn(ws.T, C, generator=g), fp16).to(DEV)
     x32 = torch.randn(ws.T, C, generator=g).to(DEV)
-    w1 = _round16(torch.randn(4 * C, C, generator=g) * 0.08, fp16).to(DEV)
-    w2 = _round16(torch.randn(C, 4 * C, generator=g) * 0.05, fp16).to(DEV)
+    w1 = _round16(torch.randn(4 * C, C, generator=g) * (0.08 if C == 192 else 0.057), fp16).to(DEV)
+    w2 = _round16(torch.randn(C, 4 * C, generator=g) * (0.05 if C == 192 else 0.035), fp16).to(DEV)
     b1, b2 = torch.randn(4 * C, generator=g).to(DEV) * 0.1, torch.randn(C, generator=g).to(DEV) * 0.1
     gam, bet = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV), torch.randn(C, generator=g).to(DEV) * 0.1
     outs = []
@@ -271,6 +276,9 @@ def test_mlp_single_kernel_matches_two_kernel_path(fmt, roll_out):
     torch.cuda.synchronize()
     (xa, oa), (xb, ob) = outs
     assert torch.isfinite(xb).all()
-    assert rel_l2(xb, xa) < 2e-5
-    assert rel_l2(ob.float(), oa.float()) < (1e-3 if fp16 else 6e-3)
-    assert torch.equal(ob == 0, oa == 0)                     # same rows written (window scatter / pad rows untouched)
+    e32, e16 = rel_l2(xb, xa), rel_l2(ob.float(), oa.float())
+    print(f"mlp single kernel vs two kernels {grid} {fmt} roll_out={roll_out}: fp32 stream {e32:.2e}, 16-bit shadow {e16:.2e}")
+    assert e32 < 2e-5
+    assert e16 < (1e-3 if fp16 else 6e-3)
+    # same rows written (window scatter / pad rows untouched); per row, because a single element may round to exactly 0 in one path only
+    assert torch.equal((ob != 0).any(dim=1), (oa != 0).any(dim=1))
