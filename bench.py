@@ -431,7 +431,7 @@ def run_gpu_arm(args):
 
 # kernels behind each entry point (names as ncu prints them, pg:: stripped), for roofline.traffic
 ENTRY_KERNELS = {
-    "pangu_mlp_ln_residual[lo]": ["gemm_kernel<CfgMLP1, {f}>|lo", "gemm_kernel<CfgLNRes384, {f}>|lo"],
+    "pangu_mlp_ln_residual[lo]": ["mlp_fused2_kernel<{f}>|lo"],
     "pangu_mlp_ln_residual[hi]": ["mlp_fused_kernel<192, {f}>|hi"],
     "pangu_window_attention[lo]": ["window_attention_tc_kernel<{f}>|lo"],
     "pangu_window_attention[hi]": ["window_attention_tc_kernel<{f}>|hi"],

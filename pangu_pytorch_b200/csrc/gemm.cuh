@@ -660,10 +660,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __syncwarp();
         // ---------------- phase B: slab -> global, coalesced (PPR lanes per row), row-remapped
         if constexpr (Cfg::RECOVER != RC_NONE) {
+          // lane = token row, one 16 B piece (4 longitudes of one (c, dz, dh) plane) per iteration: the 32 consecutive tokens of a
+          // warp lie next to each other along the longitude, so each store instruction writes one contiguous 512 B run of an
+          // output plane (8 lanes per row would scatter every instruction over 32 different planes)
 #pragma unroll
           for (int it = 0; it < PPR; ++it) {
-            const int id = it * 32 + lane;
-            const int rr = id / PPR, pc = id % PPR;
+            const int rr = lane, pc = it;
             const int tok = s_tok[rr];
             if (tok < 0) continue;
             const int grp = (c0 >> 2) + pc;        // (c, dz, dh) for upper, (c, dh) for surface
