@@ -370,9 +370,20 @@ static int launch_mlp_fused2_t(const void* x16_in, const void* w1_16, const void
   PG_TRY(make_map(&mx, x16_in, a.T, C, C, 128));
   PG_TRY(make_map(&m1, w1_16, 4 * C, C, C, 32));          // W1 [4C, C]: this CTA's 32 of a chunk's 64 hidden rows
   PG_TRY(make_map(&m2, w2_16, C, 4 * C, 4 * C, 96));      // W2 [C, 4C]: this CTA's 96 of the 192 output rows of an N half
-  PG_REQUIRE((reinterpret_cast<uintptr_t>(a.x32) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out16) & 7) == 0 &&
+  PG_REQUIRE((reinterpret_cast<uintptr_t>(a.x32) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out16) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(a.b2) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.gamma) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(a.beta) & 15) == 0, "mlp: residual stream / LayerNorm parameters not 16 B aligned");
+  CUtensorMap mr;       // fp32 residual stream [T, C]: 32-column x 32-row SWIZZLE_128B pieces (loaded, updated in place, stored)
+  {
+    cuuint64_t dims[2] = {cuuint64_t(C), cuuint64_t(a.T)};
+    cuuint64_t strides[1] = {cuuint64_t(C) * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.x32, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled(mlp residual) failed (%d)", int(r));
+  }
   auto kern = mlp_fused2_kernel<kFp16>;
   static bool attr_done[kMaxDevices] = {false};
   if (!attr_done[cur_dev()]) {
@@ -380,7 +391,10 @@ static int launch_mlp_fused2_t(const void* x16_in, const void* w1_16, const void
     attr_done[cur_dev()] = true;
   }
   const int units = (a.num_tiles + 1) / 2;
-  const int max_pairs = g_num_sms / 2;
+  int max_pairs = g_num_sms / 2;
+#ifdef PANGU_DEV_SWITCHES     // per-SM or chip-wide limit?  run the same per-pair schedule on fewer SMs
+  if (const char* e = getenv("PANGU_B200_MLP_PAIRS")) max_pairs = atoi(e);
+#endif
   const int pairs = units < max_pairs ? units : max_pairs;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -395,7 +409,7 @@ static int launch_mlp_fused2_t(const void* x16_in, const void* w1_16, const void
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PG_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, m1, m2, a));
+  PG_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, m1, m2, mr, a));
   PG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -510,7 +524,6 @@ extern "C" int pangu_window_attention(const void* qkv16, const float* earth_bias
   a.qkv = qkv16; a.bias = earth_bias; a.out = att16;
   a.C = C; a.heads = heads; a.types = g.types; a.nLon = g.nLon; a.nH = g.nH; a.roll = roll ? 1 : 0;
   a.H = H; a.W = W; a.natural = window_order_out ? 0 : 1;
-  a.lon_per_cta = g.nLon;
   a.debug = 0;
 #ifdef PANGU_DEV_SWITCHES
   if (const char* e = getenv("PANGU_B200_ATTN_DEBUG")) a.debug = atoi(e);
@@ -594,12 +607,11 @@ extern "C" int pangu_proj_ln_residual(const void* att16, const void* w16, const 
   ep.rowmap = RM_IDENT; ep.dstmap = DM_IDENT;
   ep.res_scale = res_scale;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int full_row = 0;
 #ifdef PANGU_DEV_SWITCHES
-  if (const char* e = getenv("PANGU_B200_LN384")) full_row = atoi(e);
+  if (const char* e = getenv("PANGU_B200_LN384"))
+    if (C == 384 && (atoi(e) & 2)) return launch_gemm<CfgLNRes384F>(o, ep, fp16, s);
 #endif
-  return C == 192 ? launch_gemm<CfgLNRes192>(o, ep, fp16, s)
-                  : (full_row & 2) ? launch_gemm<CfgLNRes384F>(o, ep, fp16, s) : launch_gemm<CfgLNRes384>(o, ep, fp16, s);
+  return C == 192 ? launch_gemm<CfgLNRes192>(o, ep, fp16, s) : launch_gemm<CfgLNRes384>(o, ep, fp16, s);
 }
 
 extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, const float* b1, const void* w2_16,
@@ -626,6 +638,10 @@ extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, cons
     a.roll_out = roll_out < 0 ? -1 : (roll_out > 0 ? 1 : 0);
     a.res_scale = res_scale; a.eps = 1e-5f;
     a.debug = 0;
+    a.trace = nullptr;
+#ifdef PANGU_ATTN_TRACE
+    if (const char* e = getenv("PANGU_B200_MLP_TRACE")) a.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+#endif
 #ifdef PANGU_DEV_SWITCHES
     if (const char* d = getenv("PANGU_B200_GEMM_DEBUG")) a.debug = atoi(d);
 #endif
@@ -651,12 +667,11 @@ extern "C" int pangu_mlp_ln_residual(const void* x16_in, const void* w1_16, cons
     // CfgLNRes384F (full 384-wide row per CTA, cta_group::2) was measured at the same speed as the N-split pair for
     // Mlp.linear2 (228 vs 231 us: the lower L2 traffic is paid for with an epilogue that no longer overlaps the mainloop) and
     // slower for the projection (165 vs 120 us), profiles/r02_cta2.md; development builds can select it with PANGU_B200_LN384.
-    int full_row = 0;
 #ifdef PANGU_DEV_SWITCHES
-    if (const char* e = getenv("PANGU_B200_LN384")) full_row = atoi(e);
+    if (const char* e = getenv("PANGU_B200_LN384"))
+      if (C == 384 && (atoi(e) & 1)) return launch_gemm<CfgLNRes384F>(o, ep, fp16, s);
 #endif
-    PG_TRY(C == 192 ? launch_gemm<CfgLNRes192>(o, ep, fp16, s)
-                    : (full_row & 1) ? launch_gemm<CfgLNRes384F>(o, ep, fp16, s) : launch_gemm<CfgLNRes384>(o, ep, fp16, s));
+    PG_TRY(C == 192 ? launch_gemm<CfgLNRes192>(o, ep, fp16, s) : launch_gemm<CfgLNRes384>(o, ep, fp16, s));
   }
   return 0;
 }

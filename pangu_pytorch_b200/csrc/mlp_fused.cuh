@@ -86,6 +86,7 @@ struct MlpArgs {
   float eps;
   int debug;            // development ablations (timing only): bit2 LayerNorm epilogue reduced to its barrier handshakes,
                         // bit3 GELU arithmetic skipped
+  long long* trace;     // development only (-DPANGU_ATTN_TRACE): clock64 timeline of one CTA, [role 8][chunk 64][event 4]
 };
 
 // D[tmem] (+)= A[tmem, 16-bit packed] * B[smem]

@@ -26,8 +26,8 @@
 //     remotely): relaxed arrives where only reads have to be finished (Hacc in registers, Y drained: tcgen05.wait::ld has
 //     completed them), one release.cluster arrive per GELU warp for the H tile it wrote to its shared memory.
 //     (A first version relayed the peer's local barriers through its idle issuer warps: 461 us per launch.)
-// Warps (480 threads): 0 TMA producer, 1 GEMM1 issuer (leader only), 2 GEMM2 issuer (leader only),
-// 3-6 LayerNorm epilogue, 7-14 GELU (two warpgroups alternate chunks) + their share of the epilogue.
+// Warps (512 threads): 0 TMA producer (X, W1, residual rows), 1 GEMM1 issuer (leader only), 2 GEMM2 issuer (leader only),
+// 3-6 LayerNorm epilogue, 7-14 GELU (two warpgroups alternate chunks) + their share of the epilogue, 15 W2 producer.
 #pragma once
 #include "common.cuh"
 #include "geometry.cuh"
@@ -47,12 +47,14 @@ struct Mlp2Traits {
   // 32 KB of the two H buffers): between "Y complete" and the end of the epilogue no GEMM2 reads H, and the GELU warps wait
   // for the epilogue (lnfree) before they write the first H chunks of the next tile.
   static constexpr int OFF_PAR = OFF_H + NHS * 16384;  // b1 [4C], b2 / gamma / beta [C] fp32
-  static constexpr int OFF_BAR = OFF_PAR + 7 * C * 4;
-  static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + 2 * NB + 2 * NHS + 2 + 1;
+  static constexpr int OFF_STAT = OFF_PAR + 7 * C * 4; // LayerNorm partial sums [3 column thirds][128 rows] float2
+  static constexpr int OFF_BAR = OFF_STAT + 3 * 128 * 8;
+  static constexpr int NUM_BARS = 4 * KX + 2 * S1 + 2 * S2 + (6 + NB) + (NHS + 6) + 2 + 1;
   static constexpr int SMEM_BYTES = OFF_BAR + ((NUM_BARS * 8 + 16 + 127) / 128) * 128;
-  static constexpr int THREADS = 32 * (3 + LNW + 8);
+  static constexpr int THREADS = 32 * (3 + LNW + 8 + 1);     // + the W2 producer warp
   static_assert(OFF_R1 % 1024 == 0 && OFF_R2 % 1024 == 0 && OFF_H % 1024 == 0 && R1_UNIT % 1024 == 0 && R2_UNIT % 1024 == 0,
                 "operand alignment");
+  static_assert(NCH % 6 == 0, "three warpgroups x two buffers");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
 
@@ -63,7 +65,7 @@ __device__ __forceinline__ void mbar_arrive_remote_release(uint32_t rbar) {
 template <bool kFp16>
 __global__ void __launch_bounds__(Mlp2Traits::THREADS, 1)
 mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                  const __grid_constant__ CUtensorMap tmW2, const MlpArgs a) {
+                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmR, const MlpArgs a) {
   using T = Mlp2Traits;
   constexpr int C = T::C, KX = T::KX, NCH = T::NCH, S1 = T::S1, S2 = T::S2, NB = T::NB, NHS = T::NHS;
   extern __shared__ __align__(1024) uint8_t mf2_raw[];
@@ -77,6 +79,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   float* s_b2 = s_b1 + 4 * C;
   float* s_gamma = s_b2 + C;
   float* s_beta = s_gamma + C;
+  float2* s_stat = reinterpret_cast<float2*>(smem + T::OFF_STAT);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T::OFF_BAR);
   uint64_t* xfull = bars;                      // [KX]  leader: X slabs of both CTAs landed
   uint64_t* xempty = xfull + KX;               // [KX]  each CTA: GEMM1 of the tile no longer reads the slab (commit multicast)
@@ -84,14 +87,19 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* r1empty = r1full + S1;             // [S1]  each CTA (commit multicast)
   uint64_t* r2full = r1empty + S1;             // [S2]  leader
   uint64_t* r2empty = r2full + S2;             // [S2]  each CTA
-  uint64_t* hfull = r2empty + S2;              // [NB]  each CTA: Hacc ready (commit multicast)
-  uint64_t* hempty = hfull + NB;               // [NB]  leader: the 2 x 128 GELU threads of the pair hold Hacc in registers
+  // hfull / sempty are waited for by the GELU warpgroups, which rotate over the chunks (chunk c -> warpgroup c % 3) while
+  // the buffers alternate (c % 2): one barrier per c % 6, so that a barrier always has the same waiting warpgroup and a
+  // parity wait can never be more than one phase behind.
+  uint64_t* hfull = r2empty + S2;              // [6]   each CTA: Hacc[c % 2] holds chunk c (commit multicast)
+  uint64_t* hempty = hfull + 6;                // [NB]  leader: the 2 x 4 GELU warps of the pair hold Hacc in registers
   uint64_t* sfull = hempty + NB;               // [NHS] leader: the 2 x 4 GELU warps of the pair have written H
-  uint64_t* sempty = sfull + NHS;              // [NHS] each CTA: GEMM2 has read H (commit multicast)
-  uint64_t* yfull = sempty + NHS;              // [1]   each CTA: Y complete (commit multicast)
-  uint64_t* yempty = yfull + 1;                // [1]   leader: the 2 x 384 epilogue threads of the pair have drained Y
-  uint64_t* lnfree = yempty + 1;               // [1]   each CTA: its 384 epilogue threads no longer use the H buffers as staging
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lnfree + 1);
+  uint64_t* sempty = sfull + NHS;              // [6]   each CTA: GEMM2 of chunk c has read H[c % 2] (commit multicast)
+  uint64_t* yfull = sempty + 6;                // [1]   each CTA: Y complete (commit multicast)
+  uint64_t* yempty = yfull + 1;                // [1]   leader: the 2 x 12 epilogue warps of the pair have drained Y
+  uint64_t* lnfree = yempty + 1;               // [1]   each CTA: its 12 epilogue warps no longer use the H buffers as staging
+  uint64_t* rfull = lnfree + 1;                // [KX]  each CTA: a [128 x 32] fp32 block of the residual rows landed in X slab k
+  uint64_t* rfree = rfull + KX;                // [KX]  each CTA: the 4 epilogue warps of the block have stored it (smem read finished)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfree + KX);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta_rank = int(cluster_ctarank());
@@ -105,12 +113,14 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
-    for (int k = 0; k < KX; ++k) { mbar_init(&xfull[k], 1); mbar_init(&xempty[k], 1); }
+    tma_prefetch_desc(&tmR);
+    for (int k = 0; k < KX; ++k) { mbar_init(&xfull[k], 1); mbar_init(&xempty[k], 1); mbar_init(&rfull[k], 1); mbar_init(&rfree[k], 4); }
     for (int s = 0; s < S1; ++s) { mbar_init(&r1full[s], 1); mbar_init(&r1empty[s], 1); }
     for (int s = 0; s < S2; ++s) { mbar_init(&r2full[s], 1); mbar_init(&r2empty[s], 1); }
-    for (int b = 0; b < NB; ++b) { mbar_init(&hfull[b], 1); mbar_init(&hempty[b], 256); }
-    for (int b = 0; b < NHS; ++b) { mbar_init(&sfull[b], 8); mbar_init(&sempty[b], 1); }
-    mbar_init(yfull, 1); mbar_init(yempty, 768); mbar_init(lnfree, 384);
+    for (int b = 0; b < 6; ++b) { mbar_init(&hfull[b], 1); mbar_init(&sempty[b], 1); }
+    for (int b = 0; b < NB; ++b) mbar_init(&hempty[b], 8);
+    for (int b = 0; b < NHS; ++b) mbar_init(&sfull[b], 8);
+    mbar_init(yfull, 1); mbar_init(yempty, 24); mbar_init(lnfree, 12);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_cta2<512>(tmem_slot);
@@ -122,12 +132,23 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (*tmem_slot != 0u) __trap();      // all 512 columns: the allocation starts at TMEM address 0
   constexpr uint32_t tmem = 0u;
   constexpr uint32_t COL_H = 384;
+#ifdef PANGU_ATTN_TRACE       // development builds only: per-role clock64 timeline of CTA `a.debug >> 8` ([role 8][chunk 64][event 4])
+  const bool tracing = a.trace != nullptr && int(blockIdx.x) == (a.debug >> 8);
+  auto TR = [&](int role, int g, int ev) { if (tracing && g < 64) a.trace[(role * 64 + g) * 4 + ev] = clock64(); };
+#else
+  auto TR = [](int, int, int) {};
+#endif
 #ifdef PANGU_DEV_SWITCHES     // timing ablations (results invalid): bit2 LayerNorm epilogue reduced to its handshakes, bit3 no GELU arithmetic,
   const int dbg = a.debug;    // bit4 no GEMM1 MMAs, bit5 no GEMM2 MMAs
 #else
   constexpr int dbg = 0;
 #endif
 
+  // one lane waits, the warp follows: 32 lanes in mbarrier.try_wait on one barrier are served one after the other (~250 clk)
+  auto warp_wait = [&](uint64_t* bar, uint32_t parity) {
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+  };
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ================================
     // issue order == consumption order of the MMA warps:  X(tile), W1(0), then per chunk  W1(c+1), W2(c)
@@ -137,29 +158,35 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       auto load_w1 = [&](int c) {
         const int s = p1 % S1;
         mbar_wait(&r1empty[s], ((p1 / S1) & 1) ^ 1);
+        TR(0, p1, 0);
         if (leader) mbar_arrive_expect_tx(&r1full[s], 2 * T::R1_UNIT);
         for (int k = 0; k < KX; ++k)     // this CTA's 32 of the chunk's 64 hidden rows
           tma_load_2d_cta2(&tmW1, lbar(&r1full[s]), r1 + s * T::R1_UNIT + k * 4096, k * 64, c * 64 + cta_rank * 32, kEvictLast);
+        TR(0, p1, 1);
         ++p1;
       };
-      auto load_w2 = [&](int c) {
-        for (int h = 0; h < 2; ++h, ++p2) {
-          const int s = p2 % S2;
-          mbar_wait(&r2empty[s], ((p2 / S2) & 1) ^ 1);
-          if (leader) mbar_arrive_expect_tx(&r2full[s], 2 * T::R2_UNIT);
-          tma_load_2d_cta2(&tmW2, lbar(&r2full[s]), r2 + s * T::R2_UNIT, c * 64, h * 192 + cta_rank * 96, kEvictLast);
-        }
-      };
-      auto load_x = [&](int tile, int use) {
+      auto tile_of = [&](int tu) { return 2 * (pair + tu * num_pairs) + cta_rank; };
+      auto load_x = [&](int tile, bool first) {
         for (int k = 0; k < KX; ++k) {
-          mbar_wait(&xempty[k], (use & 1) ^ 1);
+          if (!first) mbar_wait(&rfree[k], 1);          // the epilogue has stored its second block out of this slab
           if (leader) mbar_arrive_expect_tx(&xfull[k], 2 * 16384);
           tma_load_2d_cta2(&tmX, lbar(&xfull[k]), xs + k * 16384, k * 64, tile * 128, kEvictFirst);   // rows >= T read as zero
         }
       };
-      // The epilogue reads and rewrites this CTA's 128 x 384 fp32 residual rows (196 KB, contiguous).  All CTAs reach their
-      // epilogues at about the same time and nothing else of the kernel touches HBM then, so the rows are pulled into L2
-      // while the second half of the mainloop runs: the epilogue then works out of L2 and its write-back overlaps the next tile.
+      // The LayerNorm epilogue reads and rewrites this CTA's 128 x 384 fp32 residual rows (196 KB, contiguous).  They stream
+      // through the X slabs, which are idle from the tile's last GEMM1 to the next tile's first: twelve [128 x 32] fp32
+      // blocks (16 KB, SWIZZLE_128B: the geometry of an X slab) in two rounds of six.  Round 0 is issued as soon as GEMM1 has
+      // released the slabs (two chunks before Y is complete), round 1 / the next X slab as soon as the four epilogue warps of
+      // the block before have stored theirs.  All CTAs reach their epilogues at about the same time and nothing else of the
+      // kernel touches HBM then, so the rows are also pulled into L2 half a tile earlier.
+      auto resid_round = [&](int tile, int tu, int round) {
+        for (int k = 0; k < KX; ++k) {
+          if (round == 0) mbar_wait(&xempty[k], tu & 1); else mbar_wait(&rfree[k], 0);
+          mbar_arrive_expect_tx(&rfull[k], 16384);
+          for (int q = 0; q < 4; ++q)
+            tma_load_2d(&tmR, &rfull[k], xs + k * 16384 + q * 4096, 32 * (k + KX * round), tile * 128 + 32 * q);
+        }
+      };
       auto prefetch_resid = [&](int tile) {
         const long long row0 = (long long)tile * 128;
         const long long rows = row0 + 128 <= a.T ? 128 : (a.T > row0 ? a.T - row0 : 0);
@@ -167,14 +194,40 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (long long off = 0; off < rows * C * 4; off += 16384)
           bulk_prefetch_l2(p + off, uint32_t(rows * C * 4 - off < 16384 ? rows * C * 4 - off : 16384));
       };
-      for (int cgx = 0; cgx < total + NB - 1; ++cgx) {
-        if (cgx < total) {
-          const int tu = cgx / NCH, c = cgx % NCH;
-          if (c == 0) load_x(2 * (pair + tu * num_pairs) + cta_rank, tu);
-          if (c == NCH / 2) prefetch_resid(2 * (pair + tu * num_pairs) + cta_rank);
+      // X(0), then W1(g) per chunk g.  At a tile boundary the W1 ring is primed for the next tile (W1(0), W1(1): neither
+      // waits for the epilogue) before this thread blocks on the epilogue's progress.  The W2 ring has its own producer
+      // warp: with one in-order thread for both rings a W2 unit that waited for GEMM2(g-1) held back W1(g+2), which closed a
+      // three-chunk loop GEMM2 -> W2 -> W1 -> GEMM1 -> GELU -> GEMM2 (3 400 clk per chunk against 1 900 of MMA work).
+      for (int g = 0; g <= total; ++g) {
+        const int tu = g / NCH, c = g % NCH;
+        if (g == 0) load_x(tile_of(0), true);
+        if (g < total) {
+          if (c == NCH / 2) {
+            prefetch_resid(tile_of(tu));
+            if (tu + 1 < my_units)               // the next X tile too: its load is issued after the epilogue and should hit L2
+              for (int k = 0; k < KX; ++k) tma_prefetch_2d(&tmX, k * 64, tile_of(tu + 1) * 128);
+          }
           load_w1(c);
         }
-        if (cgx >= NB - 1) load_w2((cgx - (NB - 1)) % NCH);
+        if (c == 0 && g > 0) resid_round(tile_of(tu - 1), tu - 1, 0);
+        if (c == 1 && tu > 0) {
+          resid_round(tile_of(tu - 1), tu - 1, 1);
+          load_x(tile_of(tu), false);
+        }
+      }
+      resid_round(tile_of(my_units - 1), my_units - 1, 1);
+    }
+  } else if (warp == 3 + T::LNW + 8) {
+    // ================================ W2 producer (both CTAs) ================================
+    if (lane == 0) {
+      auto lbar = [&](uint64_t* b) { return mapa_u32(smem_u32(b), 0); };
+      for (int p2 = 0; p2 < 2 * total; ++p2) {
+        const int s = p2 % S2, c = (p2 >> 1) % NCH, h = p2 & 1;
+        mbar_wait(&r2empty[s], ((p2 / S2) & 1) ^ 1);
+        TR(1, p2 >> 1, 2 * h);
+        if (leader) mbar_arrive_expect_tx(&r2full[s], 2 * T::R2_UNIT);
+        tma_load_2d_cta2(&tmW2, lbar(&r2full[s]), r2 + s * T::R2_UNIT, c * 64, h * 192 + cta_rank * 96, kEvictLast);
+        TR(1, p2 >> 1, 2 * h + 1);
       }
     }
   } else if (warp == 1) {
@@ -185,10 +238,12 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int cgx = 0; cgx < total; ++cgx) {
         const int c = cgx % NCH, tu = cgx / NCH, hb = cgx % NB, s = cgx % S1;
         mbar_wait(&hempty[hb], ((cgx / NB) & 1) ^ 1);        // both CTAs' GELU warps hold the buffer's previous contents
+        if (lane == 0) TR(2, cgx, 0);
         if (c == 0) {
           for (int k = 0; k < KX; ++k) mbar_wait(&xfull[k], tu & 1);
         }
         mbar_wait(&r1full[s], (cgx / S1) & 1);
+        if (lane == 0) TR(2, cgx, 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -204,7 +259,8 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           if (c == NCH - 1) {
             for (int k = 0; k < KX; ++k) umma_commit_cta2(&xempty[k]);     // last reader of the X slabs
           }
-          umma_commit_cta2(&hfull[hb]);
+          umma_commit_cta2(&hfull[cgx % 6]);
+          TR(2, cgx, 2);
         }
         __syncwarp();
       }
@@ -221,11 +277,13 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           mbar_wait(yempty, (tu & 1) ^ 1);
         }
         mbar_wait_cluster(&sfull[sb], (cgx / NHS) & 1);      // GELU(H) of this chunk is in both CTAs' shared memory
+        if (lane == 0) TR(3, cgx, 0);
         tc_fence_after();
         const uint64_t da = make_sdesc_sw128(hs_u32 + sb * 16384);
         for (int h = 0; h < 2; ++h, ++p2) {
           const int s = p2 % S2;
           mbar_wait(&r2full[s], (p2 / S2) & 1);
+          if (lane == 0) TR(3, cgx, 1 + h);
           tc_fence_after();
           const uint64_t db = make_sdesc_sw128(r2_u32 + s * T::R2_UNIT);
           if (elect_one()) {
@@ -234,8 +292,9 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               if (!(dbg & 32))
               umma_f16_ss_cta2(tmem + h * 192, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc2, (c | kk) != 0 ? 1u : 0u);
             umma_commit_cta2(&r2empty[s]);
-            if (h == 1) umma_commit_cta2(&sempty[sb]);
+            if (h == 1) umma_commit_cta2(&sempty[cgx % 6]);
             if (c == NCH - 1 && h == 1) umma_commit_cta2(yfull);
+            if (h == 1) TR(3, cgx, 3);
           }
           __syncwarp();
         }
@@ -243,36 +302,39 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   } else {
     // ================================ GELU + LayerNorm warps (both CTAs, own 128 rows) ================================
-    // Warps 7-14 (two warpgroups, alternate chunks): Hacc -> registers (the TMEM buffer goes straight back to GEMM1) ->
-    // bias + exact GELU -> 16-bit H tile in shared memory (K-major SWIZZLE_128B A operand of GEMM2).
-    // At the end of a tile ALL twelve warps (3-6 and 7-14: three per TMEM lane quadrant) run the LayerNorm + residual
-    // epilogue: every warp computes the row statistics of its 32 rows (thread = row) and normalises every third 16-column
-    // chunk, staged through a swizzled [32 x 16] fp32 tile in the then idle H buffers so that global accesses are 64 B row
-    // segments (4 lanes per row).  With the four LayerNorm warps alone the epilogue took 40 000 clk per tile (1 warp per
-    // scheduler, latency bound), half as long as the 24 chunks of the mainloop.
-    const bool is_gelu = warp >= 3 + T::LNW;
+    // Warps 3-14: three warpgroups take the chunks in turn (chunk c -> warpgroup c % 3, Hacc / H buffer c % 2):
+    // Hacc -> registers (the TMEM buffer goes straight back to GEMM1) -> bias + exact GELU -> 16-bit H tile in shared memory
+    // (K-major SWIZZLE_128B A operand of GEMM2).  One chunk costs a warp ~2 200 clk (a dependent Horner chain per pair,
+    // ~0.4 IPC) plus ~1 500 for the hand-over; with two warpgroups that cycle was longer than two chunks of MMA work, and the
+    // three warps per scheduler also hide each other's latencies.
+    // At the end of a tile the same twelve warps (three per TMEM lane quadrant) run the LayerNorm + residual epilogue.
     const int quad = warp & 3;
-    const int wgp = is_gelu ? (warp - (3 + T::LNW)) >> 2 : 0;
-    const int part = is_gelu ? 1 + wgp : 0;              // which third of the 16-column chunks this warp normalises
-    const uint32_t haddr = tmem + (uint32_t(quad * 32) << 16) + COL_H + 64 * wgp;
+    const int wgp = (warp - 3) >> 2;                     // warpgroup 0..2
+    const int part = wgp;                                // which third of the columns this warp owns in the epilogue
     const uint32_t tacc = tmem + (uint32_t(quad * 32) << 16);
     const int row = quad * 32 + lane;
-    uint8_t* hrow = hs + wgp * 16384 + row * 128;
     uint8_t* stage = hs + (part * 4 + quad) * 2048;
     const Geo geo = make_geo(a.Z, a.H, a.W);
     const int pc = lane & 3;                             // 16 B piece of a 64 B row segment handled by this lane in phase B
-    int n = 0;           // chunks this GELU warpgroup has processed
     for (int tu = 0; tu < my_units; ++tu) {
-      if (is_gelu) {
-        for (int c = wgp; c < NCH; c += 2, ++n) {
-          mbar_wait(&hfull[wgp], n & 1);
+      {
+        for (int c = wgp; c < NCH; c += 3) {
+          const int hb = c & 1;                          // NCH is even: buffer index and use count follow from the chunk number
+          const int cgx = tu * NCH + c;
+          const uint32_t haddr = tacc + COL_H + 64 * hb;
+          uint8_t* hrow = hs + hb * 16384 + row * 128;
+          warp_wait(&hfull[c % 6], (cgx / 6) & 1);
+          if (lane == 0 && quad == 3) TR(4 + hb, tu * NCH + c, 0);
           tc_fence_after();
           uint32_t r[2][32];
           tmem_ld32(haddr, r[0]);
           tmem_ld32(haddr + 32, r[1]);
           tmem_ld_wait();
           tc_fence_before();
-          if (leader) mbar_arrive(&hempty[wgp]); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&hempty[wgp]), 0));
+          __syncwarp();
+          if (lane == 0) {        // one arrival per warp: all its lanes hold their Hacc values in registers
+            if (leader) mbar_arrive(&hempty[hb]); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&hempty[hb]), 0));
+          }
           uint32_t pk[32];
           const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 64);
 #pragma unroll
@@ -290,58 +352,50 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               pk[hh * 16 + 2 * j4 + 1] = pack16<kFp16>(v2, v3);
             }
           }
-          mbar_wait(&sempty[wgp], (n & 1) ^ 1);        // GEMM2 of this warpgroup's previous chunk has read the buffer
-          if (c == wgp && tu > 0) mbar_wait(lnfree, (tu - 1) & 1);   // ... and nobody stages the previous tile's epilogue in it
+          if (lane == 0 && quad == 3) TR(4 + hb, tu * NCH + c, 1);
+          if (cgx >= 2) warp_wait(&sempty[(cgx - 2) % 6], ((cgx - 2) / 6) & 1);     // GEMM2 of chunk c - 2 has read the buffer
+          if (lane == 0 && quad == 3) TR(4 + hb, tu * NCH + c, 2);
+          if (c < 2 && tu > 0) warp_wait(lnfree, (tu - 1) & 1);      // ... and nobody stages the previous tile's epilogue in it
 #pragma unroll
           for (int q = 0; q < 8; ++q)                  // 8 x 16 B = this row's 64 hidden units, XOR-swizzled 16 B chunks
             *reinterpret_cast<uint4*>(hrow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {          // one arrival per warp: its 32 rows of H are written and visible to the async proxy
-            if (leader) mbar_arrive(&sfull[wgp]); else mbar_arrive_remote_release(mapa_u32(smem_u32(&sfull[wgp]), 0));
+            if (leader) mbar_arrive(&sfull[hb]); else mbar_arrive_remote_release(mapa_u32(smem_u32(&sfull[hb]), 0));
+            if (quad == 3) TR(4 + hb, tu * NCH + c, 3);
           }
         }
       }
-      // ------------------------------ LayerNorm + residual epilogue of tile tu (this warp's third of the chunks) ------------------------------
+      // ------------------------------ LayerNorm + residual epilogue of tile tu ------------------------------
+      // Three warps per TMEM lane quadrant (thread = row).  Statistics: each warp sums its third of the 384 columns, the
+      // partial sums meet in shared memory.  Then the warp walks four of the twelve 32-column blocks: accumulator ->
+      // registers -> normalise -> add to the fp32 residual block that TMA put into X slab b % 6 (in place, row per lane,
+      // conflict-free under SWIZZLE_128B) -> TMA store of the warp's [32 x 32] piece; the 16-bit shadow goes through a
+      // swizzled [32 x 64 B] tile in the idle H buffers so that its global stores are 64 B row segments (4 lanes per row).
       const int tile = 2 * (pair + tu * num_pairs) + cta_rank;
       const int g = tile * 128 + quad * 32 + lane;
       const int my_tok = g < a.T ? g : -1;
       const int my_dst = (my_tok >= 0 && a.roll_out >= 0) ? token_to_win_row(geo, my_tok, a.roll_out) : my_tok;
-      // phase-B items of this lane: row rr = it * 8 + (lane >> 2), it = 0..3
-      int toks[4], dsts[4];
+      int dsts[4];         // shadow rows of this lane's phase-B items: row rr = it * 8 + (lane >> 2)
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        toks[it] = __shfl_sync(0xffffffffu, my_tok, it * 8 + (lane >> 2));
-        dsts[it] = __shfl_sync(0xffffffffu, my_dst, it * 8 + (lane >> 2));
-      }
-      auto load_resid = [&](int c0, uint4 (&dst)[4]) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          dst[it] = make_uint4(0u, 0u, 0u, 0u);
-          if (toks[it] >= 0) dst[it] = ldg16(a.x32 + size_t(toks[it]) * C + c0 + pc * 4);
-        }
-      };
-      uint4 resq[4];
-      load_resid(16 * part, resq);
-      mbar_wait(yfull, tu & 1);
+      for (int it = 0; it < 4; ++it) dsts[it] = __shfl_sync(0xffffffffu, my_dst, it * 8 + (lane >> 2));
+      warp_wait(yfull, tu & 1);
+      if (lane == 0 && warp == 6) TR(6, tu * 8, 0);
       tc_fence_after();
-      if (dbg & 4) {
-        tc_fence_before();
-        if (leader) mbar_arrive(yempty); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(yempty), 0));
-        mbar_arrive(lnfree);
-        continue;
-      }
-      float mean, rstd;
-      {
-        float shift = 0.f;
+      float mean = 0.f, rstd = 0.f;
+      if (!(dbg & 4)) {
+        uint32_t r0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r0) : "r"(tacc) : "memory");
+        tmem_ld_wait();
+        const float shift = __uint_as_float(r0) + s_b2[0];       // any value near the row mean: keeps the one-pass variance exact enough
+        const f32x2 nshift = pack2(-shift, -shift);
         f32x2 s1 = pack2(0.f, 0.f), s2 = pack2(0.f, 0.f);
 #pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 32) {
+        for (int c0 = 128 * part; c0 < 128 * part + 128; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(tacc + c0, r);
           tmem_ld_wait();
-          if (c0 == 0) shift = __uint_as_float(r[0]) + s_b2[0];
-          const f32x2 nshift = pack2(-shift, -shift);
           const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
@@ -356,66 +410,92 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         float s1a, s1b, s2a, s2b;
         unpack2(s1, s1a, s1b);
         unpack2(s2, s2a, s2b);
+        s_stat[part * 128 + row] = make_float2(s1a + s1b, s2a + s2b);
+        named_bar_sync(1 + quad, 96);                // the quadrant's three warps
+        const float2 p0 = s_stat[row], p1 = s_stat[128 + row], p2 = s_stat[256 + row];
         const float inv_n = 1.0f / float(C);
-        const float m = (s1a + s1b) * inv_n;
-        const float var = fmaxf((s2a + s2b) * inv_n - m * m, 0.f);
+        const float m = (p0.x + p1.x + p2.x) * inv_n;
+        const float var = fmaxf((p0.y + p1.y + p2.y) * inv_n - m * m, 0.f);
         mean = shift + m;
         rstd = rsqrtf(var + a.eps);
       }
       const f32x2 ln_a = pack2(rstd, rstd), ln_b = pack2(-mean * rstd, -mean * rstd);
+      const f32x2 rs2 = pack2(a.res_scale, a.res_scale);
 #pragma unroll 1
-      for (int c0 = 16 * part; c0 < C; c0 += 48) {
-        {
-          // phase A: TMEM -> registers -> (acc + b2 - mean) * rstd * gamma + beta -> tile (row per lane)
-          uint32_t r[16];
-          tmem_ld16(tacc + c0, r);
+      for (int i = 0; i < 4; ++i) {
+        const int b = part + 3 * i, k = part + 3 * (i & 1);      // column block, X slab that holds its residual rows
+        uint8_t* srow = xs + k * 16384 + row * 128;
+        if (lane == 0 && warp == 6) TR(6, tu * 8 + 1 + i, 0);
+        warp_wait(&rfull[k], i >> 1);
+        if (lane == 0 && warp == 6) TR(6, tu * 8 + 1 + i, 1);
+        if (!(dbg & 4)) {
+          uint32_t r[32];
+          tmem_ld32(tacc + 32 * b, r);
           tmem_ld_wait();
-          const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
-          const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
-          const float4* e4 = reinterpret_cast<const float4*>(s_beta + c0);
+          if (i == 3) {          // this warp has read the accumulator for the last time: hand Y back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (leader) mbar_arrive(yempty); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(yempty), 0));
+            }
+          }
+          const float4* b4 = reinterpret_cast<const float4*>(s_b2 + 32 * b);
+          const float4* g4 = reinterpret_cast<const float4*>(s_gamma + 32 * b);
+          const float4* e4 = reinterpret_cast<const float4*>(s_beta + 32 * b);
+          uint32_t pk[16];
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 bb = b4[j4], gg = g4[j4], ee = e4[j4];
-            f32x2 v01 = add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y));
-            f32x2 v23 = add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w));
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j], gg = g4[j], ee = e4[j];
+            uint4* cell = reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4));
+            const uint4 q = *cell;
+            f32x2 v01 = add2(pack2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), pack2(bb.x, bb.y));
+            f32x2 v23 = add2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), pack2(bb.z, bb.w));
             v01 = fma2(fma2(v01, ln_a, ln_b), pack2(gg.x, gg.y), pack2(ee.x, ee.y));
             v23 = fma2(fma2(v23, ln_a, ln_b), pack2(gg.z, gg.w), pack2(ee.z, ee.w));
-            float v0, v1, v2, v3;
-            unpack2(v01, v0, v1);
-            unpack2(v23, v2, v3);
-            *reinterpret_cast<uint4*>(stage + lane * 64 + ((j4 ^ ((lane >> 1) & 3)) << 4)) =
-                make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
+            v01 = fma2(rs2, v01, pack2(__uint_as_float(q.x), __uint_as_float(q.y)));
+            v23 = fma2(rs2, v23, pack2(__uint_as_float(q.z), __uint_as_float(q.w)));
+            float f0, f1, f2, f3;
+            unpack2(v01, f0, f1);
+            unpack2(v23, f2, f3);
+            *cell = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3));
+            pk[2 * j] = pack16<kFp16>(f0, f1);
+            pk[2 * j + 1] = pack16<kFp16>(f2, f3);
           }
-        }
-        if (c0 + 48 >= C) {          // this thread has read the accumulator for the last time: hand Y back
-          tc_fence_before();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          fence_proxy_async_smem();
+        } else if (i == 3 && lane == 0) {
           if (leader) mbar_arrive(yempty); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(yempty), 0));
         }
         __syncwarp();
-        // phase B: tile -> global (4 lanes per row), + residual; fp32 stream (in place) and 16-bit shadow
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          if (toks[it] < 0) continue;
-          const int rr = it * 8 + (lane >> 2);
-          const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4));
-          const uint4 q = resq[it];
-          const float f0 = fmaf(a.res_scale, __uint_as_float(v.x), __uint_as_float(q.x));
-          const float f1 = fmaf(a.res_scale, __uint_as_float(v.y), __uint_as_float(q.y));
-          const float f2 = fmaf(a.res_scale, __uint_as_float(v.z), __uint_as_float(q.z));
-          const float f3 = fmaf(a.res_scale, __uint_as_float(v.w), __uint_as_float(q.w));
-          const int col = c0 + pc * 4;
-          stg16(a.x32 + size_t(toks[it]) * C + col,
-                make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)));
-          *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.out16) + size_t(dsts[it]) * C + col) =
-              make_uint2(pack16<kFp16>(f0, f1), pack16<kFp16>(f2, f3));
+        if (lane == 0 && !(dbg & 4)) {       // rows >= T are clipped by the tensor map
+          tma_store_2d(&tmR, xs + k * 16384 + quad * 4096, 32 * b, tile * 128 + quad * 32);
+          bulk_commit();
         }
-        __syncwarp();                 // the tile is rewritten by the next chunk's phase A
-        if (c0 + 48 < C) load_resid(c0 + 48, resq);     // residual of this warp's next chunk: in flight during its phase A
+        if (!(dbg & 4)) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            if (dsts[it] < 0) continue;
+            const int rr = it * 8 + (lane >> 2);
+            const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4));
+            stg16(reinterpret_cast<uint16_t*>(a.out16) + size_t(dsts[it]) * C + 32 * b + pc * 8, v);
+          }
+        }
+        if (lane == 0 && warp == 6) TR(6, tu * 8 + 1 + i, 2);
+        if (lane == 0) {
+          bulk_wait_read<0>();               // the store has read the slab piece: it may be overwritten
+          mbar_arrive(&rfree[k]);
+        }
+        if (lane == 0 && warp == 6) TR(6, tu * 8 + 1 + i, 3);
+        __syncwarp();                        // the shadow tile is rewritten by the next block
       }
-      mbar_arrive(lnfree);           // this thread no longer touches the H buffers
+      if (lane == 0) mbar_arrive(lnfree);           // this warp no longer touches the H buffers (the block loop ends in a __syncwarp)
     }
   }
 
+  if (warp >= 3 && lane == 0) bulk_wait_all();      // this thread's residual stores have been written
   tc_fence_before();
   cluster_sync_all();          // no multicast commit / remote arrive may target an exited CTA
   if (warp == 1) {
