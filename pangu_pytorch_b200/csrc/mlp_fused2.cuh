@@ -8,8 +8,9 @@
 // and each CTA holds only HALF of every weight tile, which is what makes the shared-memory budget close:
 //
 //   X tile     [128 x 384] 16-bit, own rows                                  96 KB   (resident for the tile)
-//   W1 ring    2 units [32 of the 64 hidden rows of a chunk x 384 k]      2 x 24 KB
-//   W2 ring    3 units [96 of the 192 output rows of an N half x 64 k]    3 x 12 KB
+//   W1 ring    3 units [32 of the 64 hidden rows of a chunk x 192 k]      3 x 12 KB   (1.5 chunks: GEMM1 runs two chunks ahead anyway)
+//   W2 ring    4 units [96 of the 192 output rows of an N half x 64 k]    4 x 12 KB   (2 chunks: with 3 units a load could only be
+//              issued one GEMM2 half before it was needed and its ~900 clk latency stalled every chunk)
 //   H operand  2 buffers [128 x 64] 16-bit (GELU output, A of GEMM2)      2 x 16 KB
 //   b1, b2, gamma, beta 10.5 KB, barriers; the LayerNorm epilogue stages its chunks in the (then idle) H buffers     total 222.9 KB
 //
@@ -36,9 +37,9 @@
 namespace pg {
 
 struct Mlp2Traits {
-  static constexpr int C = 384, KX = 6, NCH = 24, NB = 2, NHS = 2, S1 = 2, S2 = 3, LNW = 4;
+  static constexpr int C = 384, KX = 6, NCH = 24, NB = 2, NHS = 2, S1 = 3, S2 = 4, LNW = 4;
   static constexpr int X_BYTES = KX * 16384;
-  static constexpr int R1_UNIT = KX * 4096;            // 32 hidden rows x 64 k per slab, 6 slabs
+  static constexpr int R1_UNIT = 3 * 4096;             // 32 hidden rows x 64 k per slab, 3 slabs = half of a chunk's K
   static constexpr int R2_UNIT = 96 * 128;             // 96 output rows x 64 k
   static constexpr int OFF_R1 = X_BYTES;
   static constexpr int OFF_R2 = OFF_R1 + S1 * R1_UNIT;
@@ -58,8 +59,14 @@ struct Mlp2Traits {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
 
-__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t rbar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+// "My H rows are written" from the peer CTA's GELU warps to the leader's barrier.  The rows live in the PEER's shared memory
+// and are read there, by the peer's own tensor core (cta_group::2: each CTA supplies its 128 rows of A), through the async
+// proxy: fence.proxy.async + __syncwarp have made them visible before lane 0 sends the arrive, and the MMA is dispatched
+// only after the arrive has reached the leader.  So the default (CTA-scope release) remote arrive that CUTLASS's
+// ClusterBarrier::arrive(cta_id) uses is enough; the .release.cluster form costs an ERRBAR + CCTL.IVALL pair, ~1 400 clk
+// on the GEMM2 critical path of every chunk.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t rbar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
 }
 
 template <bool kFp16>
@@ -153,17 +160,18 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // ================================ TMA producer (both CTAs) ================================
     // issue order == consumption order of the MMA warps:  X(tile), W1(0), then per chunk  W1(c+1), W2(c)
     if (lane == 0) {
-      int p1 = 0, p2 = 0;
+      int p1 = 0;
       auto lbar = [&](uint64_t* b) { return mapa_u32(smem_u32(b), 0); };
       auto load_w1 = [&](int c) {
-        const int s = p1 % S1;
-        mbar_wait(&r1empty[s], ((p1 / S1) & 1) ^ 1);
-        TR(0, p1, 0);
-        if (leader) mbar_arrive_expect_tx(&r1full[s], 2 * T::R1_UNIT);
-        for (int k = 0; k < KX; ++k)     // this CTA's 32 of the chunk's 64 hidden rows
-          tma_load_2d_cta2(&tmW1, lbar(&r1full[s]), r1 + s * T::R1_UNIT + k * 4096, k * 64, c * 64 + cta_rank * 32, kEvictLast);
-        TR(0, p1, 1);
-        ++p1;
+        for (int h = 0; h < 2; ++h, ++p1) {     // two units per chunk: k slabs 0..2 and 3..5
+          const int s = p1 % S1;
+          mbar_wait(&r1empty[s], ((p1 / S1) & 1) ^ 1);
+          TR(0, p1 >> 1, 2 * h);
+          if (leader) mbar_arrive_expect_tx(&r1full[s], 2 * T::R1_UNIT);
+          for (int k = 0; k < 3; ++k)     // this CTA's 32 of the chunk's 64 hidden rows
+            tma_load_2d_cta2(&tmW1, lbar(&r1full[s]), r1 + s * T::R1_UNIT + k * 4096, (3 * h + k) * 64, c * 64 + cta_rank * 32, kEvictLast);
+          TR(0, p1 >> 1, 2 * h + 1);
+        }
       };
       auto tile_of = [&](int tu) { return 2 * (pair + tu * num_pairs) + cta_rank; };
       auto load_x = [&](int tile, bool first) {
@@ -194,13 +202,17 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (long long off = 0; off < rows * C * 4; off += 16384)
           bulk_prefetch_l2(p + off, uint32_t(rows * C * 4 - off < 16384 ? rows * C * 4 - off : 16384));
       };
-      // X(0), then W1(g) per chunk g.  At a tile boundary the W1 ring is primed for the next tile (W1(0), W1(1): neither
-      // waits for the epilogue) before this thread blocks on the epilogue's progress.  The W2 ring has its own producer
+      // X(0), then W1(g) per chunk g.  At a tile boundary the W1 ring is primed for the next tile (W1(0): it does not
+      // wait for the epilogue) before this thread blocks on the epilogue's progress.  The W2 ring has its own producer
       // warp: with one in-order thread for both rings a W2 unit that waited for GEMM2(g-1) held back W1(g+2), which closed a
       // three-chunk loop GEMM2 -> W2 -> W1 -> GEMM1 -> GELU -> GEMM2 (3 400 clk per chunk against 1 900 of MMA work).
       for (int g = 0; g <= total; ++g) {
         const int tu = g / NCH, c = g % NCH;
         if (g == 0) load_x(tile_of(0), true);
+        if (c == 1 && tu > 0) {           // before W1(1): the ring holds 1.5 chunks, its fourth unit would wait for GEMM1(0), i.e. for X
+          resid_round(tile_of(tu - 1), tu - 1, 1);
+          load_x(tile_of(tu), false);
+        }
         if (g < total) {
           if (c == NCH / 2) {
             prefetch_resid(tile_of(tu));
@@ -210,10 +222,6 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           load_w1(c);
         }
         if (c == 0 && g > 0) resid_round(tile_of(tu - 1), tu - 1, 0);
-        if (c == 1 && tu > 0) {
-          resid_round(tile_of(tu - 1), tu - 1, 1);
-          load_x(tile_of(tu), false);
-        }
       }
       resid_round(tile_of(my_units - 1), my_units - 1, 1);
     }
@@ -236,26 +244,32 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       constexpr uint32_t idesc1 = make_idesc_f16(256, 64, kFp16);
       const uint32_t xs_u32 = smem_u32(xs), r1_u32 = smem_u32(r1);
       for (int cgx = 0; cgx < total; ++cgx) {
-        const int c = cgx % NCH, tu = cgx / NCH, hb = cgx % NB, s = cgx % S1;
+        const int c = cgx % NCH, tu = cgx / NCH, hb = cgx % NB;
         mbar_wait(&hempty[hb], ((cgx / NB) & 1) ^ 1);        // both CTAs' GELU warps hold the buffer's previous contents
         if (lane == 0) TR(2, cgx, 0);
         if (c == 0) {
           for (int k = 0; k < KX; ++k) mbar_wait(&xfull[k], tu & 1);
         }
-        mbar_wait(&r1full[s], (cgx / S1) & 1);
-        if (lane == 0) TR(2, cgx, 1);
-        tc_fence_after();
-        if (elect_one()) {
+        for (int h = 0; h < 2; ++h) {
+          const int s = (2 * cgx + h) % S1;
+          mbar_wait(&r1full[s], ((2 * cgx + h) / S1) & 1);
+          if (lane == 0 && h == 1) TR(2, cgx, 1);
+          tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < KX; ++k) {
-            const uint64_t da = make_sdesc_sw128(xs_u32 + k * 16384);
-            const uint64_t db = make_sdesc_sw128(r1_u32 + s * T::R1_UNIT + k * 4096);
+            for (int k = 0; k < 3; ++k) {
+              const uint64_t da = make_sdesc_sw128(xs_u32 + (3 * h + k) * 16384);
+              const uint64_t db = make_sdesc_sw128(r1_u32 + s * T::R1_UNIT + k * 4096);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              if (!(dbg & 16))
-              umma_f16_ss_cta2(tmem + COL_H + 64 * hb, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc1, (k | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < 4; ++kk)
+                if (!(dbg & 16))
+                umma_f16_ss_cta2(tmem + COL_H + 64 * hb, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc1, (h | k | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit_cta2(&r1empty[s]);
           }
-          umma_commit_cta2(&r1empty[s]);
+          __syncwarp();
+        }
+        if (elect_one()) {
           if (c == NCH - 1) {
             for (int k = 0; k < KX; ++k) umma_commit_cta2(&xempty[k]);     // last reader of the X slabs
           }
@@ -362,7 +376,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {          // one arrival per warp: its 32 rows of H are written and visible to the async proxy
-            if (leader) mbar_arrive(&sfull[hb]); else mbar_arrive_remote_release(mapa_u32(smem_u32(&sfull[hb]), 0));
+            if (leader) mbar_arrive(&sfull[hb]); else mbar_arrive_remote(mapa_u32(smem_u32(&sfull[hb]), 0));
             if (quad == 3) TR(4 + hb, tu * NCH + c, 3);
           }
         }
