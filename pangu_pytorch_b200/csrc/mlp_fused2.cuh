@@ -453,6 +453,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               if (leader) mbar_arrive(yempty); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(yempty), 0));
             }
           }
+          if (lane == 0 && warp == 6) TR(7, tu * 8 + 1 + i, 0);
           const float4* b4 = reinterpret_cast<const float4*>(s_b2 + 32 * b);
           const float4* g4 = reinterpret_cast<const float4*>(s_gamma + 32 * b);
           const float4* e4 = reinterpret_cast<const float4*>(s_beta + 32 * b);
@@ -479,7 +480,9 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
                 make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          if (lane == 0 && warp == 6) TR(7, tu * 8 + 1 + i, 1);
           fence_proxy_async_smem();
+          if (lane == 0 && warp == 6) TR(7, tu * 8 + 1 + i, 2);
         } else if (i == 3 && lane == 0) {
           if (leader) mbar_arrive(yempty); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(yempty), 0));
         }
@@ -488,6 +491,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tma_store_2d(&tmR, xs + k * 16384 + quad * 4096, 32 * b, tile * 128 + quad * 32);
           bulk_commit();
         }
+        if (lane == 0 && warp == 6) TR(7, tu * 8 + 1 + i, 3);
         if (!(dbg & 4)) {
 #pragma unroll
           for (int it = 0; it < 4; ++it) {

@@ -38,8 +38,9 @@ if trace is not None:
     rel = lambda v: int(v) - t0 if int(v) else -1
     names = ["W1 load: slot free, issued", "W2 load: h0 free, h0 issued, h1 free, h1 issued", "G1: Hacc free, W1 full, committed",
              "G2: H full, W2 h0 full, W2 h1 full, committed", "GELU wg0: Hacc full, math done, H buffer free, arrived",
-             "GELU wg1: Hacc full, math done, H buffer free, arrived", "epilogue warp 6: [tile*8] Y full | block i: start, resid full, stored, drained", ""]
-    for role in range(7):
+             "GELU wg1: Hacc full, math done, H buffer free, arrived", "epilogue warp 6: [tile*8] Y full | block i: start, resid full, stored, drained",
+             "epilogue warp 6, block i: accumulator in registers, math + staging written, fence done, TMA store issued"]
+    for role in range(8):
         print("role", role, names[role])
         for g in range(56):
             if int(tr[role, g].abs().sum()) == 0:
