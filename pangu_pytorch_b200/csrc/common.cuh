@@ -400,47 +400,39 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// Exact-erf GELU on a pair (see gelu_erf below for the formula): the degree-7 Horner chain and the
-// surrounding multiplies run as packed FFMA2/FMUL2, i.e. ~9 issue slots per element instead of 13.
+// Exact-erf GELU (nn.GELU default, reference models/layers.py:261), branch free:
+//   gelu(x) = max(x, 0) - |x| * 0.5 erfc(|x| / sqrt(2)),     0.5 erfc(a / sqrt(2)) = 2^(a * P4(a) - 1),  a = |x|
+// P4 is a degree-4 minimax fit (weighted by the error it causes in gelu) of log2(erfc(a / sqrt(2))) / a on [0, 6]; its
+// leading coefficient is negative and P4 <= -1.15 everywhere, so the exponent only gets more negative for large |x| and
+// no clamp is needed.  max |gelu - exact| = 5.3e-7 in exact arithmetic, 7e-7 with fp32 Horner + ex2.approx -- far below
+// the 16-bit rounding of the stored activation.  On a pair the chain is 6 packed FFMA2 (4 Horner steps, the exponent, the
+// final multiply-add) + 2 MUFU + 2 FMNMX: 5 issue slots per element (the degree-7 fit in |x| / sqrt(2) it replaces took 9).
+constexpr float kGeluC0 = -1.151000543e+00f, kGeluC1 = -4.595958433e-01f, kGeluC2 = -5.214663275e-02f,
+                kGeluC3 = 7.198718708e-03f, kGeluC4 = -4.881021609e-04f;
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
-  const float a0 = fabsf(x0), a1 = fabsf(x1);
-  const f32x2 ax = pack2(a0, a1);
-  const f32x2 t = mul2(ax, pack2(0.70710678118654752440f, 0.70710678118654752440f));
-  f32x2 p = pack2(-5.904116739e-06f, -5.904116739e-06f);
-  p = fma2(p, t, pack2(6.987359289e-05f, 6.987359289e-05f));
-  p = fma2(p, t, pack2(-6.779016748e-05f, -6.779016748e-05f));
-  p = fma2(p, t, pack2(-3.477876114e-03f, -3.477876114e-03f));
-  p = fma2(p, t, pack2(3.092580434e-02f, 3.092580434e-02f));
-  p = fma2(p, t, pack2(-1.497507845e-01f, -1.497507845e-01f));
-  p = fma2(p, t, pack2(-9.181910519e-01f, -9.181910519e-01f));
-  p = fma2(p, t, pack2(-1.627914489e+00f, -1.627914489e+00f));
+  const f32x2 ax = pack2(fabsf(x0), fabsf(x1));
+  f32x2 p = fma2(ax, pack2(kGeluC4, kGeluC4), pack2(kGeluC3, kGeluC3));
+  p = fma2(p, ax, pack2(kGeluC2, kGeluC2));
+  p = fma2(p, ax, pack2(kGeluC1, kGeluC1));
+  p = fma2(p, ax, pack2(kGeluC0, kGeluC0));
   float e0, e1;
-  unpack2(mul2(p, t), e0, e1);       // log2(erfc(t)); strongly negative for large t, no clamp needed
-  const f32x2 u = pack2(ex2_approx(e0), ex2_approx(e1));
-  const f32x2 r = fma2(mul2(ax, pack2(-0.5f, -0.5f)), u, pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+  unpack2(fma2(p, ax, pack2(-1.0f, -1.0f)), e0, e1);
+  const f32x2 u = pack2(-ex2_approx(e0), -ex2_approx(e1));
+  const f32x2 r = fma2(ax, u, pack2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
   unpack2(r, x0, x1);
 }
 
 __device__ __forceinline__ float gelu_erf_libm(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// Exact-erf GELU (nn.GELU default, reference models/layers.py:261), branch free:
-//   gelu(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt(2)),   erfc(t) = 2^(t * P7(t)),  t in [0, 4]
-// P7 is a degree-7 fit of log2(erfc(t))/t; max |gelu - exact| = 4.9e-7 (fp32 Horner + ex2.approx),
-// i.e. far below the 16-bit rounding of the stored activation.  13 issue slots instead of ~30.
+// scalar form of gelu_erf2 (same polynomial, same result)
 __device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
-  const float t = fminf(ax * 0.70710678118654752440f, 4.0f);
-  float p = -5.904116739e-06f;
-  p = fmaf(p, t, 6.987359289e-05f);
-  p = fmaf(p, t, -6.779016748e-05f);
-  p = fmaf(p, t, -3.477876114e-03f);
-  p = fmaf(p, t, 3.092580434e-02f);
-  p = fmaf(p, t, -1.497507845e-01f);
-  p = fmaf(p, t, -9.181910519e-01f);
-  p = fmaf(p, t, -1.627914489e+00f);
-  float u;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(p * t));
-  return fmaf(-0.5f * ax, u, fmaxf(x, 0.f));
+  float p = fmaf(ax, kGeluC4, kGeluC3);
+  p = fmaf(p, ax, kGeluC2);
+  p = fmaf(p, ax, kGeluC1);
+  p = fmaf(p, ax, kGeluC0);
+  const float u = ex2_approx(fmaf(p, ax, -1.0f));
+  return fmaf(-ax, u, fmaxf(x, 0.f));
 }
 
 // streaming 16-byte global accesses

@@ -60,7 +60,7 @@ struct MlpTraits {
   static constexpr int OFF_SLAB = OFF_H + NHS * 16384;
   static constexpr int LNW = 4;                                   // LayerNorm epilogue warps (a second warpgroup alternating tiles
                                                                   // was measured slower: 543 vs 508 us at C=192)
-  static constexpr int THREADS = 32 * (3 + LNW + 8);              // TMA, GEMM1 issuer, GEMM2 issuer, LayerNorm warps, 8 GELU warps
+  static constexpr int THREADS = 32 * (3 + LNW + 8 + 1);          // TMA (X, W1), GEMM1 issuer, GEMM2 issuer, LayerNorm warps, 8 GELU warps, TMA (W2)
   static constexpr int OFF_PAR = OFF_SLAB + LNW * SLAB_BYTES;     // b1 [4C], b2 / gamma / beta [C] fp32
   static constexpr int OFF_TAB = OFF_PAR + 7 * C * 4;             // LNW warps x 64 ints
   static constexpr int OFF_BAR = OFF_TAB + LNW * 64 * 4;
@@ -143,11 +143,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* r2full = r1empty + S1;             // [S2]
   uint64_t* r2empty = r2full + S2;             // [S2]  count 2
   uint64_t* hfull = r2empty + S2;              // [NB]  Hacc ready (GEMM1 done)
-  uint64_t* hempty = hfull + NB;               // [NB]  Hacc loaded into registers by the 128 GELU threads of its warpgroup
-  uint64_t* sfull = hempty + NB;               // [NHS] H (16-bit, K-major SWIZZLE_128B) written to shared memory by 128 threads
+  uint64_t* hempty = hfull + NB;               // [NB]  Hacc loaded into registers by the 4 GELU warps of its warpgroup
+  uint64_t* sfull = hempty + NB;               // [NHS] H (16-bit, K-major SWIZZLE_128B) written to shared memory by 4 warps
   uint64_t* sempty = sfull + T::NHS;           // [NHS] GEMM2 has read the H buffer
   uint64_t* yfull = sempty + T::NHS;           // [YB]  Y complete
-  uint64_t* yempty = yfull + YB;               // [YB]  Y drained by the 128 epilogue threads
+  uint64_t* yempty = yfull + YB;               // [YB]  Y drained by the 4 epilogue warps
   uint64_t* rfull = yempty + YB;               // [LNW][2] residual tile landed (RES_TMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2 * T::LNW);
 
@@ -164,9 +164,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int k = 0; k < KX; ++k) { mbar_init(&xfull[k], 1); mbar_init(&xempty[k], 1); }
     for (int s = 0; s < S1; ++s) { mbar_init(&r1full[s], 1); mbar_init(&r1empty[s], T::MCAST ? 2 : 1); }
     for (int s = 0; s < S2; ++s) { mbar_init(&r2full[s], 1); mbar_init(&r2empty[s], T::MCAST ? 2 : 1); }
-    for (int b = 0; b < NB; ++b) { mbar_init(&hfull[b], 1); mbar_init(&hempty[b], 128); }
-    for (int b = 0; b < T::NHS; ++b) { mbar_init(&sfull[b], 128); mbar_init(&sempty[b], 1); }
-    for (int y = 0; y < YB; ++y) { mbar_init(&yfull[y], 1); mbar_init(&yempty[y], 128); }
+    for (int b = 0; b < NB; ++b) { mbar_init(&hfull[b], 1); mbar_init(&hempty[b], 4); }
+    for (int b = 0; b < T::NHS; ++b) { mbar_init(&sfull[b], 4); mbar_init(&sempty[b], 1); }
+    for (int y = 0; y < YB; ++y) { mbar_init(&yfull[y], 1); mbar_init(&yempty[y], 4); }
     for (int i = 0; i < 2 * T::LNW; ++i) mbar_init(&rfull[i], 1);
     fence_barrier_init();
   }
@@ -180,11 +180,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (*tmem_slot != 0u) __trap();      // all 512 columns: the allocation starts at TMEM address 0
   constexpr uint32_t tmem = 0u;
 
+  // one lane waits, the warp follows: 32 lanes in mbarrier.try_wait on one barrier are served one after the other (~250 clk)
+  auto warp_wait = [&](uint64_t* bar, uint32_t parity) {
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+  };
   if (warp == 0) {
     // ================================ TMA producer ================================
-    // issue order == consumption order of the MMA warp:  X(tile), W1(0), then per chunk  W1(c+1), W2(c)
+    // X(tile), then W1(c) per chunk, in the order the GEMM1 issuer consumes them
     if (lane == 0) {
-      int p1 = 0, p2 = 0;        // ring positions (running counters)
+      int p1 = 0;                // ring position (running counter)
       int xuse = 0;              // tiles loaded so far (X barrier phases)
       auto load_w1 = [&](int c) {          // chunk c (0..NCH-1): one unit of KX slabs [64 hidden x 64 k]
         const int s = p1 % S1;
@@ -199,18 +204,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         ++p1;
       };
-      auto load_w2 = [&](int c) {          // chunk c: NH units [192 out rows x 64 k]
-        for (int h = 0; h < NH; ++h, ++p2) {
-          const int s = p2 % S2;
-          mbar_wait(&r2empty[s], ((p2 / S2) & 1) ^ 1);
-          mbar_arrive_expect_tx(&r2full[s], T::R2_UNIT);
-          if constexpr (T::MCAST)
-            tma_load_2d_mcast(&tmW2, &r2full[s], r2 + s * T::R2_UNIT + cta_rank * 12288, c * 64, h * 192 + cta_rank * 96,
-                              uint16_t(3), kEvictLast);
-          else
-            tma_load_2d_hint(&tmW2, &r2full[s], r2 + s * T::R2_UNIT, c * 64, h * 192, kEvictLast);
-        }
-      };
       auto load_x = [&](int tile, int use) {   // use-th X tile of this CTA; slabs free up as the previous tile's last GEMM1 retires
         for (int k = 0; k < KX; ++k) {
           mbar_wait(&xempty[k], (use & 1) ^ 1);
@@ -221,15 +214,30 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       // flat chunk sequence over this CTA's tiles, same order as the MMA warp:  G1(cgx), G2(cgx - (NB-1))
       const int my_tiles = (num_units - pair + num_pairs - 1) / num_pairs;
       const int total = my_tiles * NCH;
-      for (int cgx = 0; cgx < total + NB - 1; ++cgx) {
-        if (cgx < total) {
-          const int tu = cgx / NCH, c = cgx % NCH;
-          if (c == 0) load_x(2 * (pair + tu * num_pairs) + cta_rank, tu);
-          load_w1(c);
-        }
-        if (cgx >= NB - 1) load_w2((cgx - (NB - 1)) % NCH);
+      for (int cgx = 0; cgx < total; ++cgx) {
+        const int tu = cgx / NCH, c = cgx % NCH;
+        if (c == 0) load_x(2 * (pair + tu * num_pairs) + cta_rank, tu);
+        load_w1(c);
       }
       (void)xuse;
+    }
+  } else if (warp == 3 + T::LNW + 8) {
+    // ================================ TMA producer of the W2 ring ================================
+    // Its own warp: with one in-order thread for both rings a W2 unit that waited for GEMM2(c - 1) held back W1(c + 2),
+    // which closed a loop GEMM2 -> W2 -> W1 -> GEMM1 -> GELU -> GEMM2 over several chunks (see mlp_fused2.cuh).
+    if (lane == 0) {
+      const int my_tiles = (num_units - pair + num_pairs - 1) / num_pairs;
+      const int total = my_tiles * NCH * NH;
+      for (int p2 = 0; p2 < total; ++p2) {          // unit p2: chunk (p2 / NH) % NCH, half p2 % NH  [192 out rows x 64 k]
+        const int s = p2 % S2, c = (p2 / NH) % NCH, h = p2 % NH;
+        mbar_wait(&r2empty[s], ((p2 / S2) & 1) ^ 1);
+        mbar_arrive_expect_tx(&r2full[s], T::R2_UNIT);
+        if constexpr (T::MCAST)
+          tma_load_2d_mcast(&tmW2, &r2full[s], r2 + s * T::R2_UNIT + cta_rank * 12288, c * 64, h * 192 + cta_rank * 96,
+                            uint16_t(3), kEvictLast);
+        else
+          tma_load_2d_hint(&tmW2, &r2full[s], r2 + s * T::R2_UNIT, c * 64, h * 192, kEvictLast);
+      }
     }
   } else if (warp == 1 || warp == 2) {
     // ================================ MMA issuers ================================
@@ -327,13 +335,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       __syncwarp();
       if (a.debug & 4) {
-        mbar_wait(&yfull[yb], (tuse / YB) & 1);
+        warp_wait(&yfull[yb], (tuse / YB) & 1);
         tc_fence_after();
         tc_fence_before();
-        mbar_arrive(&yempty[yb]);
+        if (lane == 0) mbar_arrive(&yempty[yb]);
         continue;
       }
-      if constexpr (T::RES_TMA) {
+      {
         // ---- residual stream by TMA: two [32 rows x 32 fp32 columns] SWIZZLE_128B tiles per warp; chunk c lives in
         // slot c & 1; the LayerNorm result is added in place and the tile leaves with one bulk store.
         constexpr int NCHK = C / 32;
@@ -349,7 +357,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           fetch(0);
           fetch(1);
         }
-        mbar_wait(&yfull[yb], (tuse / YB) & 1);
+        warp_wait(&yfull[yb], (tuse / YB) & 1);
         tc_fence_after();
         float mean, rstd;
         {
@@ -390,7 +398,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           uint8_t* tl = slots + (c & 1) * 4096;
           uint32_t r[32];
           tmem_ld32(tacc + c0, r);
-          mbar_wait(&rf[c & 1], (tuse * (NCHK / 2) + (c >> 1)) & 1);     // each slot is filled NCHK / 2 times per tile
+          warp_wait(&rf[c & 1], (tuse * (NCHK / 2) + (c >> 1)) & 1);     // each slot is filled NCHK / 2 times per tile
           tmem_ld_wait();
           const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
           const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
@@ -409,12 +417,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             unpack2(v23, v2, v3);
             *cell = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
           }
-          if (c == NCHK - 1) {         // accumulator fully read: hand the Y buffer back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(&yempty[yb]);
-          }
+          if (c == NCHK - 1) tc_fence_before();      // accumulator fully read (every lane: tcgen05.wait::ld above)
           fence_proxy_async_smem();
           __syncwarp();
+          if (c == NCHK - 1 && lane == 0) mbar_arrive(&yempty[yb]);      // hand the Y buffer back to the GEMM2 issuer
           if (lane == 0 && row0 < a.T) {
             tma_store_2d(&tmRes, tl, c0, row0);     // rows beyond T are clipped
             bulk_commit();
@@ -441,109 +447,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             fetch(c + 2);
           }
         }
-      } else {
-        constexpr int PPR = 8;       // 16 B fp32 pieces per 32-column row chunk
-        auto load_resid = [&](int cc, uint4 (&dst)[PPR]) {
-  #pragma unroll
-          for (int it = 0; it < PPR; ++it) {
-            const int id = it * 32 + lane;
-            const int rr = id / PPR, pc = id % PPR;
-            const int tok = s_tok[rr];
-            dst[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (tok >= 0) dst[it] = ldg16(a.x32 + size_t(tok) * C + cc + pc * 4);
-          }
-        };
-        uint4 resq[PPR];
-        load_resid(0, resq);         // latency hidden behind the wait for the accumulator
-        mbar_wait(&yfull[yb], (tuse / YB) & 1);
-        tc_fence_after();
-        // ---- LayerNorm statistics of (acc + b2) over the row: shifted sums, packed fp32x2 math
-        float mean, rstd;
-        {
-          float shift = 0.f;
-          f32x2 s1 = pack2(0.f, 0.f), s2 = pack2(0.f, 0.f);
-  #pragma unroll 1
-          for (int c0 = 0; c0 < C; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tacc + c0, r);
-            tmem_ld_wait();
-            if (c0 == 0) shift = __uint_as_float(r[0]) + s_b2[0];
-            const f32x2 nshift = pack2(-shift, -shift);
-            const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
-  #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = b4[j4];
-              const f32x2 v01 = add2(add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y)), nshift);
-              const f32x2 v23 = add2(add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w)), nshift);
-              s1 = add2(s1, add2(v01, v23));
-              s2 = fma2(v01, v01, s2);
-              s2 = fma2(v23, v23, s2);
-            }
-          }
-          float s1a, s1b, s2a, s2b;
-          unpack2(s1, s1a, s1b);
-          unpack2(s2, s2a, s2b);
-          const float inv_n = 1.0f / float(C);
-          const float m = (s1a + s1b) * inv_n;
-          const float var = fmaxf((s2a + s2b) * inv_n - m * m, 0.f);
-          mean = shift + m;
-          rstd = rsqrtf(var + a.eps);
-        }
-        const f32x2 ln_a = pack2(rstd, rstd), ln_b = pack2(-mean * rstd, -mean * rstd);
-  #pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 32) {
-          uint4 resn[PPR];
-          if (c0 + 32 < C) load_resid(c0 + 32, resn);
-          // phase A: TMEM -> registers -> (acc + b2 - mean) * rstd * gamma + beta -> slab (row per lane)
-          {
-            uint32_t r[32];
-            tmem_ld32(tacc + c0, r);
-            tmem_ld_wait();
-            const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
-            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
-            const float4* e4 = reinterpret_cast<const float4*>(s_beta + c0);
-            uint4* dstp = reinterpret_cast<uint4*>(slab + lane * T::STG_PITCH);
-  #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = b4[j4], gg = g4[j4], ee = e4[j4];
-              f32x2 v01 = add2(pack2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), pack2(bb.x, bb.y));
-              f32x2 v23 = add2(pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(bb.z, bb.w));
-              v01 = fma2(fma2(v01, ln_a, ln_b), pack2(gg.x, gg.y), pack2(ee.x, ee.y));
-              v23 = fma2(fma2(v23, ln_a, ln_b), pack2(gg.z, gg.w), pack2(ee.z, ee.w));
-              float v0, v1, v2, v3;
-              unpack2(v01, v0, v1);
-              unpack2(v23, v2, v3);
-              dstp[j4] = make_uint4(__float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
-            }
-          }
-          if (c0 + 32 >= C) {          // accumulator fully read: hand the Y buffer back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(&yempty[yb]);
-          }
-          __syncwarp();
-          // phase B: slab -> global, coalesced (8 lanes per row), + residual; fp32 stream and 16-bit shadow
-  #pragma unroll
-          for (int it = 0; it < PPR; ++it) {
-            const int id = it * 32 + lane;
-            const int rr = id / PPR, pc = id % PPR;
-            const int tok = s_tok[rr];
-            if (tok < 0) continue;
-            const int col = c0 + pc * 4;
-            const uint4 v = *reinterpret_cast<const uint4*>(slab + rr * T::STG_PITCH + pc * 16);
-            const uint4 q = resq[it];
-            const float f0 = fmaf(a.res_scale, __uint_as_float(v.x), __uint_as_float(q.x));
-            const float f1 = fmaf(a.res_scale, __uint_as_float(v.y), __uint_as_float(q.y));
-            const float f2 = fmaf(a.res_scale, __uint_as_float(v.z), __uint_as_float(q.z));
-            const float f3 = fmaf(a.res_scale, __uint_as_float(v.w), __uint_as_float(q.w));
-            stg16(a.x32 + size_t(tok) * C + col,
-                  make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)));
-            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.out16) + size_t(s_dst[rr]) * C + col) =
-                make_uint2(pack16<kFp16>(f0, f1), pack16<kFp16>(f2, f3));
-          }
-          __syncwarp();
-  #pragma unroll
-          for (int it = 0; it < PPR; ++it) resq[it] = resn[it];
-        }
       }
     }
   } else {
@@ -558,14 +461,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     int n = 0;           // chunks this warpgroup has processed
     for (int unit = pair; unit < num_units; unit += num_pairs) {
       for (int c = wgp; c < NCH; c += 2, ++n) {
-        mbar_wait(&hfull[wgp], n & 1);
+        warp_wait(&hfull[wgp], n & 1);
         tc_fence_after();
         uint32_t r[2][32];
         tmem_ld32(haddr, r[0]);
         tmem_ld32(haddr + 32, r[1]);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&hempty[wgp]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hempty[wgp]);      // one arrival per warp: all its lanes hold their Hacc values
         uint32_t pk[32];
         const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 64);
 #pragma unroll
@@ -583,12 +487,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             pk[hh * 16 + 2 * j4 + 1] = pack16<kFp16>(v2, v3);
           }
         }
-        mbar_wait(&sempty[wgp], (n & 1) ^ 1);        // GEMM2 of this warpgroup's previous chunk has read the buffer
+        warp_wait(&sempty[wgp], (n & 1) ^ 1);        // GEMM2 of this warpgroup's previous chunk has read the buffer
 #pragma unroll
         for (int q = 0; q < 8; ++q)                  // 8 x 16 B = this row's 64 hidden units, XOR-swizzled 16 B chunks
           *reinterpret_cast<uint4*>(hrow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         fence_proxy_async_smem();
-        mbar_arrive(&sfull[wgp]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sfull[wgp]);       // one arrival per warp: its 32 rows of H are visible to the async proxy
       }
     }
   }

@@ -140,7 +140,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   constexpr uint32_t tmem = 0u;
   constexpr uint32_t COL_H = 384;
 #ifdef PANGU_ATTN_TRACE       // development builds only: per-role clock64 timeline of CTA `a.debug >> 8` ([role 8][chunk 64][event 4])
-  const bool tracing = a.trace != nullptr && int(blockIdx.x) == (a.debug >> 8);
+  const bool tracing = a.trace != nullptr && int(blockIdx.x) == ((a.debug >> 8) & 255);
   auto TR = [&](int role, int g, int ev) { if (tracing && g < 64) a.trace[(role * 64 + g) * 4 + ev] = clock64(); };
 #else
   auto TR = [](int, int, int) {};
