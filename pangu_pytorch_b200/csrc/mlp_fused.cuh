@@ -180,11 +180,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (*tmem_slot != 0u) __trap();      // all 512 columns: the allocation starts at TMEM address 0
   constexpr uint32_t tmem = 0u;
 
-  // one lane waits, the warp follows: 32 lanes in mbarrier.try_wait on one barrier are served one after the other (~250 clk)
-  auto warp_wait = [&](uint64_t* bar, uint32_t parity) {
-    if (lane == 0) mbar_wait(bar, parity);
-    __syncwarp();
-  };
+#ifdef PANGU_ATTN_TRACE       // development builds only: per-role clock64 timeline of CTA `a.debug >> 8` ([role 8][chunk 64][event 4])
+  const bool tracing = a.trace != nullptr && int(blockIdx.x) == ((a.debug >> 8) & 255);
+  auto TR = [&](int role, int g, int ev) { if (tracing && g < 64) a.trace[(role * 64 + g) * 4 + ev] = clock64(); };
+#else
+  auto TR = [](int, int, int) {};
+#endif
+  // Every lane waits.  (One waiting lane + __syncwarp was measured: a wait on an already completed barrier then takes ~800 clk
+  // instead of ~300, and the issuer warps, which wait two or three times per chunk, slowed the kernels down by 60 %.)
+  auto warp_wait = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
   if (warp == 0) {
     // ================================ TMA producer ================================
     // X(tile), then W1(c) per chunk, in the order the GEMM1 issuer consumes them
@@ -194,6 +198,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       auto load_w1 = [&](int c) {          // chunk c (0..NCH-1): one unit of KX slabs [64 hidden x 64 k]
         const int s = p1 % S1;
         mbar_wait(&r1empty[s], ((p1 / S1) & 1) ^ 1);
+        TR(0, p1, 0);
         mbar_arrive_expect_tx(&r1full[s], T::R1_UNIT);
         for (int k = 0; k < KX; ++k) {
           if constexpr (T::MCAST)          // this CTA fetches 32 of the 64 hidden rows of every slab and multicasts them to the pair
@@ -202,6 +207,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           else
             tma_load_2d_hint(&tmW1, &r1full[s], r1 + s * T::R1_UNIT + k * 8192, k * 64, c * 64, kEvictLast);
         }
+        TR(0, p1, 1);
         ++p1;
       };
       auto load_x = [&](int tile, int use) {   // use-th X tile of this CTA; slabs free up as the previous tile's last GEMM1 retires
@@ -217,6 +223,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       for (int cgx = 0; cgx < total; ++cgx) {
         const int tu = cgx / NCH, c = cgx % NCH;
         if (c == 0) load_x(2 * (pair + tu * num_pairs) + cta_rank, tu);
+        if (c == NCH / 2 && tu + 1 < my_tiles)      // the X slabs are single-buffered: the next tile's load waits for this tile's last
+          for (int k = 0; k < KX; ++k)              // GEMM1 and is on the critical path, so at least let it hit L2
+            tma_prefetch_2d(&tmX, k * 64, (2 * (pair + (tu + 1) * num_pairs) + cta_rank) * 128);
         load_w1(c);
       }
       (void)xuse;
@@ -231,12 +240,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       for (int p2 = 0; p2 < total; ++p2) {          // unit p2: chunk (p2 / NH) % NCH, half p2 % NH  [192 out rows x 64 k]
         const int s = p2 % S2, c = (p2 / NH) % NCH, h = p2 % NH;
         mbar_wait(&r2empty[s], ((p2 / S2) & 1) ^ 1);
+        TR(1, p2, 0);
         mbar_arrive_expect_tx(&r2full[s], T::R2_UNIT);
         if constexpr (T::MCAST)
           tma_load_2d_mcast(&tmW2, &r2full[s], r2 + s * T::R2_UNIT + cta_rank * 12288, c * 64, h * 192 + cta_rank * 96,
                             uint16_t(3), kEvictLast);
         else
           tma_load_2d_hint(&tmW2, &r2full[s], r2 + s * T::R2_UNIT, c * 64, h * 192, kEvictLast);
+        TR(1, p2, 1);
       }
     }
   } else if (warp == 1 || warp == 2) {
@@ -253,12 +264,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     auto gemm1 = [&](int c_in_tile, int tile_use) {      // chunk -> Hacc[cgx & 1]; cgx = global index of that chunk
       const int cgx = tile_use * NCH + c_in_tile, hb = cgx % NB;
       const int s = p1 % S1;
-      mbar_wait(&hempty[hb], ((cgx / NB) & 1) ^ 1);       // the GELU warps hold the buffer's previous contents in registers
+      warp_wait(&hempty[hb], ((cgx / NB) & 1) ^ 1);       // the GELU warps hold the buffer's previous contents in registers
+      if (lane == 0) TR(2, cgx, 0);
       tc_fence_after();
       if (c_in_tile == 0) {
-        for (int k = 0; k < KX; ++k) mbar_wait(&xfull[k], tile_use & 1);
+        for (int k = 0; k < KX; ++k) warp_wait(&xfull[k], tile_use & 1);
       }
-      mbar_wait(&r1full[s], (p1 / S1) & 1);
+      warp_wait(&r1full[s], (p1 / S1) & 1);
+      if (lane == 0) TR(2, cgx, 1);
       tc_fence_after();
       const uint32_t xa = xs_u32, wb = r1_u32 + s * T::R1_UNIT;
       if (elect_one()) {
@@ -275,6 +288,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int k = 0; k < KX; ++k) umma_commit(&xempty[k]);     // last reader of the X slabs
         }
         umma_commit(&hfull[hb]);
+        TR(2, cgx, 2);
       }
       __syncwarp();
       ++p1;
@@ -282,14 +296,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t hs_u32 = smem_u32(hs);
     auto gemm2 = [&](int c_in_tile, int tile_use) {
       const int cgx = tile_use * NCH + c_in_tile, sb = cgx % T::NHS;
-      mbar_wait(&sfull[sb], (cgx / T::NHS) & 1);         // GELU(H) of this chunk is in shared memory
+      warp_wait(&sfull[sb], (cgx / T::NHS) & 1);         // GELU(H) of this chunk is in shared memory
+      if (lane == 0) TR(3, cgx, 0);
       const int yb = tile_use % YB;
-      if (c_in_tile == 0) mbar_wait(&yempty[yb], ((tile_use / YB) & 1) ^ 1);   // the epilogue has drained this Y buffer
+      if (c_in_tile == 0) warp_wait(&yempty[yb], ((tile_use / YB) & 1) ^ 1);   // the epilogue has drained this Y buffer
+      if (lane == 0) TR(3, cgx, 1);
       tc_fence_after();
       const uint64_t da = make_sdesc_sw128(hs_u32 + sb * 16384);
       for (int h = 0; h < NH; ++h, ++p2) {
         const int s = p2 % S2;
-        mbar_wait(&r2full[s], (p2 / S2) & 1);
+        warp_wait(&r2full[s], (p2 / S2) & 1);
+        if (lane == 0) TR(3, cgx, 2);
         tc_fence_after();
         const uint64_t db = make_sdesc_sw128(r2_u32 + s * T::R2_UNIT);
         if (elect_one()) {
@@ -299,6 +316,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if constexpr (T::MCAST) umma_commit_mcast(&r2empty[s], uint16_t(3)); else umma_commit(&r2empty[s]);
           if (h == NH - 1) umma_commit(&sempty[sb]);
           if (c_in_tile == NCH - 1 && h == NH - 1) umma_commit(&yfull[yb]);
+          TR(3, cgx, 3);
         }
         __syncwarp();
       }
@@ -357,7 +375,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           fetch(0);
           fetch(1);
         }
+        if (lane == 0 && warp == 3) TR(6, tuse, 0);
         warp_wait(&yfull[yb], (tuse / YB) & 1);
+        if (lane == 0 && warp == 3) TR(6, tuse, 1);
         tc_fence_after();
         float mean, rstd;
         {
@@ -390,6 +410,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mean = shift + m;
           rstd = rsqrtf(var + a.eps);
         }
+        if (lane == 0 && warp == 3) TR(6, tuse, 2);
         const f32x2 ln_a = pack2(rstd * a.res_scale, rstd * a.res_scale), ln_b = pack2(-mean * rstd * a.res_scale, -mean * rstd * a.res_scale);
         const f32x2 rs2 = pack2(a.res_scale, a.res_scale);
 #pragma unroll 1
@@ -447,6 +468,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             fetch(c + 2);
           }
         }
+        if (lane == 0 && warp == 3) TR(6, tuse, 3);
       }
     }
   } else {
@@ -462,38 +484,45 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int unit = pair; unit < num_units; unit += num_pairs) {
       for (int c = wgp; c < NCH; c += 2, ++n) {
         warp_wait(&hfull[wgp], n & 1);
+        if (lane == 0 && quad == 3) TR(4 + wgp, 2 * n + wgp, 0);
         tc_fence_after();
         uint32_t r[2][32];
         tmem_ld32(haddr, r[0]);
         tmem_ld32(haddr + 32, r[1]);
         tmem_ld_wait();
+        if (lane == 0 && quad == 3 && wgp == 0) TR(7, n, 0);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&hempty[wgp]);      // one arrival per warp: all its lanes hold their Hacc values
+        if (lane == 0 && quad == 3 && wgp == 0) TR(7, n, 1);
         uint32_t pk[32];
         const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 64);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bb = b4[hh * 8 + j4];
-            float v0 = __uint_as_float(r[hh][4 * j4]) + bb.x, v1 = __uint_as_float(r[hh][4 * j4 + 1]) + bb.y;
-            float v2 = __uint_as_float(r[hh][4 * j4 + 2]) + bb.z, v3 = __uint_as_float(r[hh][4 * j4 + 3]) + bb.w;
-            if (!(a.debug & 8)) {
-              gelu_erf2(v0, v1);
-              gelu_erf2(v2, v3);
-            }
-            pk[hh * 16 + 2 * j4] = pack16<kFp16>(v0, v1);
-            pk[hh * 16 + 2 * j4 + 1] = pack16<kFp16>(v2, v3);
+          for (int j8 = 0; j8 < 4; ++j8) {       // 8 hidden units at a time (two 16 B bias reads, four interleaved pair chains)
+            const float4 ba = b4[hh * 8 + 2 * j8], bb = b4[hh * 8 + 2 * j8 + 1];
+            float v[8] = {__uint_as_float(r[hh][8 * j8]) + ba.x, __uint_as_float(r[hh][8 * j8 + 1]) + ba.y,
+                          __uint_as_float(r[hh][8 * j8 + 2]) + ba.z, __uint_as_float(r[hh][8 * j8 + 3]) + ba.w,
+                          __uint_as_float(r[hh][8 * j8 + 4]) + bb.x, __uint_as_float(r[hh][8 * j8 + 5]) + bb.y,
+                          __uint_as_float(r[hh][8 * j8 + 6]) + bb.z, __uint_as_float(r[hh][8 * j8 + 7]) + bb.w};
+            if (!(a.debug & 8)) gelu_erf8(v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pk[hh * 16 + 4 * j8 + q] = pack16<kFp16>(v[2 * q], v[2 * q + 1]);
           }
         }
+        if (lane == 0 && quad == 3) TR(4 + wgp, 2 * n + wgp, 1);
         warp_wait(&sempty[wgp], (n & 1) ^ 1);        // GEMM2 of this warpgroup's previous chunk has read the buffer
+        if (lane == 0 && quad == 3) TR(4 + wgp, 2 * n + wgp, 2);
+        if (lane == 0 && quad == 3 && wgp == 0) TR(7, n, 2);
 #pragma unroll
         for (int q = 0; q < 8; ++q)                  // 8 x 16 B = this row's 64 hidden units, XOR-swizzled 16 B chunks
           *reinterpret_cast<uint4*>(hrow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        if (lane == 0 && quad == 3 && wgp == 0) TR(7, n, 3);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sfull[wgp]);       // one arrival per warp: its 32 rows of H are visible to the async proxy
+        if (lane == 0 && quad == 3) TR(4 + wgp, 2 * n + wgp, 3);
       }
     }
   }

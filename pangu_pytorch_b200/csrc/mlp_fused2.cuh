@@ -151,11 +151,9 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   constexpr int dbg = 0;
 #endif
 
-  // one lane waits, the warp follows: 32 lanes in mbarrier.try_wait on one barrier are served one after the other (~250 clk)
-  auto warp_wait = [&](uint64_t* bar, uint32_t parity) {
-    if (lane == 0) mbar_wait(bar, parity);
-    __syncwarp();
-  };
+  // Every lane waits.  (One waiting lane + __syncwarp was measured: a wait on an already completed barrier then takes ~800 clk
+  // instead of ~300, and the issuer warps, which wait two or three times per chunk, slowed the kernels down by 60 %.)
+  auto warp_wait = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ================================
     // issue order == consumption order of the MMA warps:  X(tile), W1(0), then per chunk  W1(c+1), W2(c)
@@ -245,14 +243,14 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t xs_u32 = smem_u32(xs), r1_u32 = smem_u32(r1);
       for (int cgx = 0; cgx < total; ++cgx) {
         const int c = cgx % NCH, tu = cgx / NCH, hb = cgx % NB;
-        mbar_wait(&hempty[hb], ((cgx / NB) & 1) ^ 1);        // both CTAs' GELU warps hold the buffer's previous contents
+        warp_wait(&hempty[hb], ((cgx / NB) & 1) ^ 1);        // both CTAs' GELU warps hold the buffer's previous contents
         if (lane == 0) TR(2, cgx, 0);
         if (c == 0) {
-          for (int k = 0; k < KX; ++k) mbar_wait(&xfull[k], tu & 1);
+          for (int k = 0; k < KX; ++k) warp_wait(&xfull[k], tu & 1);
         }
         for (int h = 0; h < 2; ++h) {
           const int s = (2 * cgx + h) % S1;
-          mbar_wait(&r1full[s], ((2 * cgx + h) / S1) & 1);
+          warp_wait(&r1full[s], ((2 * cgx + h) / S1) & 1);
           if (lane == 0 && h == 1) TR(2, cgx, 1);
           tc_fence_after();
           if (elect_one()) {
@@ -288,7 +286,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int cgx = 0; cgx < total; ++cgx) {
         const int c = cgx % NCH, tu = cgx / NCH, sb = cgx % NHS;
         if (c == 0) {                                        // both CTAs' LayerNorm warps have drained Y of the previous tile
-          mbar_wait(yempty, (tu & 1) ^ 1);
+          warp_wait(yempty, (tu & 1) ^ 1);
         }
         mbar_wait_cluster(&sfull[sb], (cgx / NHS) & 1);      // GELU(H) of this chunk is in both CTAs' shared memory
         if (lane == 0) TR(3, cgx, 0);
@@ -296,7 +294,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint64_t da = make_sdesc_sw128(hs_u32 + sb * 16384);
         for (int h = 0; h < 2; ++h, ++p2) {
           const int s = p2 % S2;
-          mbar_wait(&r2full[s], (p2 / S2) & 1);
+          warp_wait(&r2full[s], (p2 / S2) & 1);
           if (lane == 0) TR(3, cgx, 1 + h);
           tc_fence_after();
           const uint64_t db = make_sdesc_sw128(r2_u32 + s * T::R2_UNIT);
@@ -354,16 +352,15 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = b4[hh * 8 + j4];
-              float v0 = __uint_as_float(r[hh][4 * j4]) + bb.x, v1 = __uint_as_float(r[hh][4 * j4 + 1]) + bb.y;
-              float v2 = __uint_as_float(r[hh][4 * j4 + 2]) + bb.z, v3 = __uint_as_float(r[hh][4 * j4 + 3]) + bb.w;
-              if (!(dbg & 8)) {
-                gelu_erf2(v0, v1);
-                gelu_erf2(v2, v3);
-              }
-              pk[hh * 16 + 2 * j4] = pack16<kFp16>(v0, v1);
-              pk[hh * 16 + 2 * j4 + 1] = pack16<kFp16>(v2, v3);
+            for (int j8 = 0; j8 < 4; ++j8) {       // 8 hidden units at a time (two 16 B bias reads, four interleaved pair chains)
+              const float4 ba = b4[hh * 8 + 2 * j8], bb = b4[hh * 8 + 2 * j8 + 1];
+              float v[8] = {__uint_as_float(r[hh][8 * j8]) + ba.x, __uint_as_float(r[hh][8 * j8 + 1]) + ba.y,
+                            __uint_as_float(r[hh][8 * j8 + 2]) + ba.z, __uint_as_float(r[hh][8 * j8 + 3]) + ba.w,
+                            __uint_as_float(r[hh][8 * j8 + 4]) + bb.x, __uint_as_float(r[hh][8 * j8 + 5]) + bb.y,
+                            __uint_as_float(r[hh][8 * j8 + 6]) + bb.z, __uint_as_float(r[hh][8 * j8 + 7]) + bb.w};
+              if (!(dbg & 8)) gelu_erf8(v);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) pk[hh * 16 + 4 * j8 + q] = pack16<kFp16>(v[2 * q], v[2 * q + 1]);
             }
           }
           if (lane == 0 && quad == 3) TR(4 + hb, tu * NCH + c, 1);
