@@ -423,6 +423,9 @@ static EpiArgs epi_defaults() {
 #ifdef PANGU_DEV_SWITCHES     // development builds only (-DPANGU_DEV_SWITCHES): timing ablations, results invalid
   if (const char* d = getenv("PANGU_B200_GEMM_DEBUG")) e.debug = atoi(d);
 #endif
+#ifdef PANGU_ATTN_TRACE
+  if (const char* t = getenv("PANGU_B200_GEMM_TRACE")) e.trace = reinterpret_cast<long long*>(strtoull(t, nullptr, 0));
+#endif
   return e;
 }
 

@@ -57,6 +57,7 @@ struct EpiArgs {
   int lat, lon;         // RECOVER: output field extents (721, 1440)
   int plane_rows;       // HEADMAJOR: rows per 32-column plane of the 16-bit output
   int debug;            // development only: bit0 no residual loads, bit1 no stores, bit2 no epilogue math
+  long long* trace;     // development only (-DPANGU_ATTN_TRACE): clock64 timeline of CTA `debug >> 8`, [role 8][index 64][event 4]
 };
 
 // ---------------------------------------------------------------------------------------
@@ -181,15 +182,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   pdl_trigger();     // persistent grid, every CTA resident: the next kernel's CTAs may take over SMs as ours retire
   pdl_wait();        // the prologue above overlapped the previous kernel's tail; its outputs are needed from here on
 
+#ifdef PANGU_ATTN_TRACE
+  const bool tracing = ep.trace != nullptr && int(blockIdx.x) == ((ep.debug >> 8) & 255);
+  auto TR = [&](int role, int g, int ev) { if (tracing && g >= 0 && g < 64) ep.trace[(role * 64 + g) * 4 + ev] = clock64(); };
+#else
+  auto TR = [](int, int, int) {};
+#endif
+  constexpr int TR0 = 24;      // first k-block / tile traced is number TR0 / TR0 / 6 (steady state)
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int kbn = 0;
       for (int unit = unit0; unit < num_units; unit += unit_stride) {
         const int m_blk = unit_m(unit), n_blk = unit_n(unit);
-        for (int kb = 0; kb < shape.num_k_blocks; ++kb) {
+        for (int kb = 0; kb < shape.num_k_blocks; ++kb, ++kbn) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          TR(0, kbn - TR0, 0);
           uint8_t* sa = ring + stage * T::STAGE_BYTES;
           uint8_t* sb = sa + T::A_BYTES;
           if constexpr (T::CTA2) {
@@ -201,6 +211,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < T::NUM_B; ++j)     // this CTA's half (UN/2 rows) of the B tile of every MMA of the K step
               tma_load_2d_cta2(&tmB, lbar, sb + j * (UN / 2) * 128, kb * BLOCK_K, n_blk * BN + j * UN + cta_rank * (UN / 2), kEvictLast);
+            TR(0, kbn - TR0, 1);
             if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -227,26 +238,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                               uint16_t((1 << CL) - 1), kEvictLast);
           }
           }
+          TR(0, kbn - TR0, 1);
           if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0 && (!T::CTA2 || cta_rank == 0)) {
+    // The whole warp runs the loop converged (every lane waits on the barriers) and one elected lane issues: tcgen05.mma /
+    // commit take their operands from uniform registers, and in a single-lane divergent branch the issue of one k-block
+    // (4 MMAs + commit) took ~400 clk and a wait on an already completed barrier ~250 -- 770 clk per k-block against 384 clk
+    // of MMA work (QKV at C = 384: tensor pipe 52 % busy with the ring full and the epilogue idle).
+    if (!T::CTA2 || cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc_f16(T::CTA2 ? 2 * BLOCK_M : BLOCK_M, UN, kFp16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int unit = unit0; unit < num_units; unit += unit_stride) {
+      int kbn = 0, tn = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_stride, ++tn) {
+        if (lane == 0) TR(2, tn - TR0 / 6, 0);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        if (lane == 0) TR(2, tn - TR0 / 6, 1);
         tc_fence_after();
-        for (int kb = 0; kb < shape.num_k_blocks; ++kb) {
+        for (int kb = 0; kb < shape.num_k_blocks; ++kb, ++kbn) {
+          if (lane == 0) TR(1, kbn - TR0, 0);
           mbar_wait(&full_bar[stage], phase);
+          if (lane == 0) TR(1, kbn - TR0, 1);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + stage * T::STAGE_BYTES);
           const uint64_t da = make_sdesc_sw128(sa);
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
 #pragma unroll
@@ -263,10 +285,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // frees the ring slot (in every CTA of the cluster: the peer multicasts into it) once read
           if constexpr (T::CTA2) umma_commit_cta2(&empty_bar[stage]);
           else if constexpr (CL == 1) umma_commit(&empty_bar[stage]); else umma_commit_mcast(&empty_bar[stage], uint16_t((1 << CL) - 1));
+          if (kb == shape.num_k_blocks - 1) {      // accumulator complete -> epilogue (same lane: the commit tracks its MMAs)
+            if constexpr (T::CTA2) umma_commit_cta2(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+          }
+          TR(1, kbn - TR0, 2);
+          }
+          __syncwarp();
           if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
         }
-        if constexpr (T::CTA2) umma_commit_cta2(&tfull_bar[acc]); else
-        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
         if (++acc == T::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -312,7 +338,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ------- 16-bit row-major output, identity row map: registers -> private swizzled [32 x 64 B]
         // slab -> one TMA bulk store per slab (double buffered).  The TMEM load of the next chunk is in
         // flight while the current one is being converted.
+        const int tn = (unit - unit0) / unit_stride - TR0 / 6;
+        if (lane == 0 && (wslot & 3) == 0) TR(3 + (wslot >> 2), tn, 0);
         mbar_wait(&tfull_bar[acc], acc_phase);
+        if (lane == 0 && (wslot & 3) == 0) TR(3 + (wslot >> 2), tn, 1);
         tc_fence_after();
         constexpr int CSTEP = 32 * T::GROUPS;      // column distance between consecutive chunks of one warp
         constexpr int NCH = BN / CSTEP;            // chunks of 32 columns per warp
@@ -366,6 +395,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (ci + 1 < NCH) tmem_ld_wait();
         }
         tc_fence_before();
+        if (lane == 0 && (wslot & 3) == 0) TR(3 + (wslot >> 2), tn, 2);
         if constexpr (T::CTA2) {          // the issuing CTA (rank 0) waits for both halves of the M = 256 accumulator to be drained
           if (cta_rank == 0) mbar_arrive(&tempty_bar[acc]);
           else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
