@@ -101,7 +101,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nchunks > 0) {
+    if (nchunks > 0) {       // whole warp converged, one elected lane issues (a single-lane divergent issuer is ~2x slower, see gemm.cuh)
       // both operands MN-major: a_major (bit 15) and b_major (bit 16) set
       const uint32_t idesc = make_idesc_f16(128, a.KB, kFp16) | (1u << 15) | (1u << 16);
       for (int i = 0; i < nchunks; ++i) {
@@ -111,12 +111,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         const uint32_t sa = smem_u32(smem + st * WG_STAGE_BYTES);
         const uint64_t da = make_sdesc_mn_sw128(sa, WG_BOX_BYTES);
         const uint64_t db = make_sdesc_mn_sw128(sa + 2 * WG_BOX_BYTES, WG_BOX_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < WG_TOK / 16; ++k)      // 16 token rows = 2048 B per MMA K step
-          umma_f16_ss(tmem, da + uint64_t(k * 128), db + uint64_t(k * 128), idesc, (i | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[st]);
+          for (int k = 0; k < WG_TOK / 16; ++k)      // 16 token rows = 2048 B per MMA K step
+            umma_f16_ss(tmem, da + uint64_t(k * 128), db + uint64_t(k * 128), idesc, (i | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[st]);
+          if (i == nchunks - 1) umma_commit(tfull_bar);
+        }
+        __syncwarp();
       }
-      umma_commit(tfull_bar);
     }
   } else if (nchunks > 0) {
     const int quad = warp & 3;
