@@ -42,43 +42,58 @@ __global__ void __launch_bounds__(EMB_THREADS) embed_im2col_kernel(const EmbedAr
     for (int i = threadIdx.x; i < ntok * 4; i += EMB_THREADS)
       *reinterpret_cast<uint2*>(tile + (i >> 2) * EMB_PITCH + 224 + (i & 3) * 8) = make_uint2(0u, 0u);
   }
-  for (int idx = threadIdx.x; idx < ngrp * ntok; idx += EMB_THREADS) {
-    const int grp = idx / ntok, tk = idx % ntok;     // consecutive threads -> consecutive longitudes
-    const int dh = grp & 3;
-    const int la = 4 * ht + dh;
-    const int lo = 4 * (wt0 + tk);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (zp == 0) {
-      const int c = grp >> 2;                        // 0..6
-      if (c < 4) {
-        if (la < a.lat) {
-          v = *reinterpret_cast<const float4*>(a.surface + c * plane + size_t(la) * a.lon + lo);
-          if (a.s_mean) {
-            const float m = a.s_mean[c], s = a.s_std[c];
-            v.x = (v.x - m) / s; v.y = (v.y - m) / s; v.z = (v.z - m) / s; v.w = (v.w - m) / s;
+  // Four items per thread and iteration, all four loads issued before the first use: with one 16 B load in flight per thread
+  // the kernel ran at 2.9 TB/s (latency-bound: 4 KB in flight per CTA).
+  const int nitem = ngrp * ntok;
+  for (int base = threadIdx.x; base < nitem; base += 4 * EMB_THREADS) {
+    float4 v[4];
+    float mm[4], ss[4];
+    int off[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + u * EMB_THREADS;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mm[u] = 0.f; ss[u] = 1.f; off[u] = -1;
+      if (idx >= nitem) continue;
+      const int grp = idx / ntok, tk = idx - grp * ntok;     // consecutive threads -> consecutive longitudes
+      off[u] = tk * EMB_PITCH + grp * 8;
+      const int dh = grp & 3;
+      const int la = 4 * ht + dh;
+      const int lo = 4 * (wt0 + tk);
+      const float* src = nullptr;
+      if (zp == 0) {
+        const int c = grp >> 2;                        // 0..6
+        if (c < 4) {
+          if (la < a.lat) {
+            src = a.surface + c * plane + size_t(la) * a.lon + lo;
+            if (a.s_mean) { mm[u] = a.s_mean[c]; ss[u] = a.s_std[c]; }
+          }
+        } else if (a.maps) {
+          src = a.maps + (size_t(c - 4) * (4 * a.Hh) + la) * a.lon + lo;
+        }
+      } else {
+        const int dz = (grp >> 2) & 1, c = grp >> 3;   // 0..5
+        const int lev = 2 * (zp - 1) + dz;
+        if (lev < 13 && la < a.lat) {
+          if (c < 5) {
+            src = a.upper + (size_t(c) * 13 + lev) * plane + size_t(la) * a.lon + lo;
+            if (a.u_mean) { mm[u] = a.u_mean[(12 - lev) * 5 + c]; ss[u] = a.u_std[(12 - lev) * 5 + c]; }
+          } else if (a.const_h) {
+            src = a.const_h + size_t(lev) * plane + size_t(la) * a.lon + lo;
           }
         }
-      } else if (a.maps) {
-        v = *reinterpret_cast<const float4*>(a.maps + (size_t(c - 4) * (4 * a.Hh) + la) * a.lon + lo);
       }
-    } else {
-      const int dz = (grp >> 2) & 1, c = grp >> 3;   // 0..5
-      const int lev = 2 * (zp - 1) + dz;
-      if (lev < 13 && la < a.lat) {
-        if (c < 5) {
-          v = *reinterpret_cast<const float4*>(a.upper + (size_t(c) * 13 + lev) * plane + size_t(la) * a.lon + lo);
-          if (a.u_mean) {
-            const float m = a.u_mean[(12 - lev) * 5 + c], s = a.u_std[(12 - lev) * 5 + c];
-            v.x = (v.x - m) / s; v.y = (v.y - m) / s; v.z = (v.z - m) / s; v.w = (v.w - m) / s;
-          }
-        } else if (a.const_h) {
-          v = *reinterpret_cast<const float4*>(a.const_h + size_t(lev) * plane + size_t(la) * a.lon + lo);
-        }
-      }
+      if (src) v[u] = *reinterpret_cast<const float4*>(src);
     }
-    if (a.s_mean == nullptr) { v.x *= a.gscale; v.y *= a.gscale; v.z *= a.gscale; v.w *= a.gscale; }
-    *reinterpret_cast<uint2*>(tile + tk * EMB_PITCH + grp * 8) =
-        make_uint2(pack16<kFp16>(v.x, v.y), pack16<kFp16>(v.z, v.w));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (off[u] < 0) continue;
+      float4 w = v[u];
+      const float m = mm[u], sd = ss[u];
+      w.x = (w.x - m) / sd; w.y = (w.y - m) / sd; w.z = (w.z - m) / sd; w.w = (w.w - m) / sd;      // m = 0, sd = 1: exact identity
+      if (a.s_mean == nullptr) { w.x *= a.gscale; w.y *= a.gscale; w.z *= a.gscale; w.w *= a.gscale; }
+      *reinterpret_cast<uint2*>(tile + off[u]) = make_uint2(pack16<kFp16>(w.x, w.y), pack16<kFp16>(w.z, w.w));
+    }
   }
   __syncthreads();
   // the tile's token rows are contiguous in the output: flat 8-byte copy
