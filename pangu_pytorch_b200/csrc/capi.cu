@@ -373,14 +373,14 @@ static int launch_mlp_fused2_t(const void* x16_in, const void* w1_16, const void
   PG_REQUIRE((reinterpret_cast<uintptr_t>(a.x32) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out16) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(a.b2) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.gamma) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(a.beta) & 15) == 0, "mlp: residual stream / LayerNorm parameters not 16 B aligned");
-  CUtensorMap mr;       // fp32 residual stream [T, C]: 32-column x 32-row SWIZZLE_128B pieces (loaded, updated in place, stored)
+  CUtensorMap mr;       // fp32 residual stream [T, C]: 16-column x 32-row SWIZZLE_64B pieces (loaded, updated in place, stored)
   {
     cuuint64_t dims[2] = {cuuint64_t(C), cuuint64_t(a.T)};
     cuuint64_t strides[1] = {cuuint64_t(C) * 4};
-    cuuint32_t box[2] = {32, 32};
+    cuuint32_t box[2] = {16, 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.x32, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-6, "cuTensorMapEncodeTiled(mlp residual) failed (%d)", int(r));
   }

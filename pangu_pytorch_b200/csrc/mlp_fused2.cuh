@@ -50,7 +50,7 @@ struct Mlp2Traits {
   static constexpr int OFF_PAR = OFF_H + NHS * 16384;  // b1 [4C], b2 / gamma / beta [C] fp32
   static constexpr int OFF_STAT = OFF_PAR + 7 * C * 4; // LayerNorm partial sums [3 column thirds][128 rows] float2
   static constexpr int OFF_BAR = OFF_STAT + 3 * 128 * 8;
-  static constexpr int NUM_BARS = 4 * KX + 2 * S1 + 2 * S2 + (6 + NB) + (NHS + 6) + 2 + 1;
+  static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + (6 + NB) + (NHS + 6) + 2 + 1 + 2 * 12;
   static constexpr int SMEM_BYTES = OFF_BAR + ((NUM_BARS * 8 + 16 + 127) / 128) * 128;
   static constexpr int THREADS = 32 * (3 + LNW + 8 + 1);     // + the W2 producer warp
   static_assert(OFF_R1 % 1024 == 0 && OFF_R2 % 1024 == 0 && OFF_H % 1024 == 0 && R1_UNIT % 1024 == 0 && R2_UNIT % 1024 == 0,
@@ -104,9 +104,8 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* yfull = sempty + 6;                // [1]   each CTA: Y complete (commit multicast)
   uint64_t* yempty = yfull + 1;                // [1]   leader: the 2 x 12 epilogue warps of the pair have drained Y
   uint64_t* lnfree = yempty + 1;               // [1]   each CTA: its 12 epilogue warps no longer use the H buffers as staging
-  uint64_t* rfull = lnfree + 1;                // [KX]  each CTA: a [128 x 32] fp32 block of the residual rows landed in X slab k
-  uint64_t* rfree = rfull + KX;                // [KX]  each CTA: the 4 epilogue warps of the block have stored it (smem read finished)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfree + KX);
+  uint64_t* rfb = lnfree + 1;                  // [12][2] per epilogue warp: a [32 x 16] fp32 piece of its residual rows landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfb + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta_rank = int(cluster_ctarank());
@@ -121,7 +120,8 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmR);
-    for (int k = 0; k < KX; ++k) { mbar_init(&xfull[k], 1); mbar_init(&xempty[k], 1); mbar_init(&rfull[k], 1); mbar_init(&rfree[k], 4); }
+    for (int k = 0; k < KX; ++k) { mbar_init(&xfull[k], 1); mbar_init(&xempty[k], 1); }
+    for (int i = 0; i < 24; ++i) mbar_init(&rfb[i], 1);
     for (int s = 0; s < S1; ++s) { mbar_init(&r1full[s], 1); mbar_init(&r1empty[s], 1); }
     for (int s = 0; s < S2; ++s) { mbar_init(&r2full[s], 1); mbar_init(&r2empty[s], 1); }
     for (int b = 0; b < 6; ++b) { mbar_init(&hfull[b], 1); mbar_init(&sempty[b], 1); }
@@ -172,27 +172,16 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       };
       auto tile_of = [&](int tu) { return 2 * (pair + tu * num_pairs) + cta_rank; };
-      auto load_x = [&](int tile, bool first) {
+      auto load_x = [&](int tile, int use) {         // slabs free up as the previous tile's last GEMM1 retires
         for (int k = 0; k < KX; ++k) {
-          if (!first) mbar_wait(&rfree[k], 1);          // the epilogue has stored its second block out of this slab
+          mbar_wait(&xempty[k], (use & 1) ^ 1);
           if (leader) mbar_arrive_expect_tx(&xfull[k], 2 * 16384);
           tma_load_2d_cta2(&tmX, lbar(&xfull[k]), xs + k * 16384, k * 64, tile * 128, kEvictFirst);   // rows >= T read as zero
         }
       };
-      // The LayerNorm epilogue reads and rewrites this CTA's 128 x 384 fp32 residual rows (196 KB, contiguous).  They stream
-      // through the X slabs, which are idle from the tile's last GEMM1 to the next tile's first: twelve [128 x 32] fp32
-      // blocks (16 KB, SWIZZLE_128B: the geometry of an X slab) in two rounds of six.  Round 0 is issued as soon as GEMM1 has
-      // released the slabs (two chunks before Y is complete), round 1 / the next X slab as soon as the four epilogue warps of
-      // the block before have stored theirs.  All CTAs reach their epilogues at about the same time and nothing else of the
-      // kernel touches HBM then, so the rows are also pulled into L2 half a tile earlier.
-      auto resid_round = [&](int tile, int tu, int round) {
-        for (int k = 0; k < KX; ++k) {
-          if (round == 0) mbar_wait(&xempty[k], tu & 1); else mbar_wait(&rfree[k], 0);
-          mbar_arrive_expect_tx(&rfull[k], 16384);
-          for (int q = 0; q < 4; ++q)
-            tma_load_2d(&tmR, &rfull[k], xs + k * 16384 + q * 4096, 32 * (k + KX * round), tile * 128 + 32 * q);
-        }
-      };
+      // The LayerNorm epilogue reads and rewrites this CTA's 128 x 384 fp32 residual rows (196 KB, contiguous).  All CTAs reach
+      // their epilogues at about the same time and nothing else of the kernel touches HBM then, so the rows are pulled into
+      // L2 half a tile earlier; the epilogue warps fetch them from there by TMA, piece by piece (see below).
       auto prefetch_resid = [&](int tile) {
         const long long row0 = (long long)tile * 128;
         const long long rows = row0 + 128 <= a.T ? 128 : (a.T > row0 ? a.T - row0 : 0);
@@ -200,35 +189,24 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (long long off = 0; off < rows * C * 4; off += 16384)
           bulk_prefetch_l2(p + off, uint32_t(rows * C * 4 - off < 16384 ? rows * C * 4 - off : 16384));
       };
-      // X(0), then W1(g) per chunk g.  At a tile boundary the W1 ring is primed for the next tile (W1(0): it does not
-      // wait for the epilogue) before this thread blocks on the epilogue's progress.  The W2 ring has its own producer
-      // warp: with one in-order thread for both rings a W2 unit that waited for GEMM2(g-1) held back W1(g+2), which closed a
-      // three-chunk loop GEMM2 -> W2 -> W1 -> GEMM1 -> GELU -> GEMM2 (3 400 clk per chunk against 1 900 of MMA work).
-      for (int g = 0; g <= total; ++g) {
+      // X(tile), then W1(c) per chunk.  The W2 ring has its own producer warp: with one in-order thread for both rings a W2
+      // unit that waited for GEMM2(g-1) held back W1(g+2), which closed a three-chunk loop GEMM2 -> W2 -> W1 -> GEMM1 -> GELU ->
+      // GEMM2 (3 400 clk per chunk against 1 900 of MMA work).  Nothing here waits for the epilogue: the next tile's X and its
+      // first W1 units land, and its first two GEMM1 chunks run, while the epilogue of this tile is still busy.
+      for (int g = 0; g < total; ++g) {
         const int tu = g / NCH, c = g % NCH;
-        if (g == 0) load_x(tile_of(0), true);
-        if (c == 1 && tu > 0) {           // before W1(1): the ring holds 1.5 chunks, its fourth unit would wait for GEMM1(0), i.e. for X
-          resid_round(tile_of(tu - 1), tu - 1, 1);
-          load_x(tile_of(tu), false);
-        }
-        if (g < total) {
-          if (c == NCH / 2) {
-            prefetch_resid(tile_of(tu));
-            if (tu + 1 < my_units)               // the next X tile too: its load is issued after the epilogue and should hit L2
-              for (int k = 0; k < KX; ++k) tma_prefetch_2d(&tmX, k * 64, tile_of(tu + 1) * 128);
-          }
-          load_w1(c);
-        }
-        if (c == 0 && g > 0) resid_round(tile_of(tu - 1), tu - 1, 0);
+        if (c == 0) load_x(tile_of(tu), tu);
+        if (c == NCH / 2) prefetch_resid(tile_of(tu));
+        load_w1(c);
       }
-      resid_round(tile_of(my_units - 1), my_units - 1, 1);
     }
   } else if (warp == 3 + T::LNW + 8) {
     // ================================ W2 producer (both CTAs) ================================
     if (lane == 0) {
       auto lbar = [&](uint64_t* b) { return mapa_u32(smem_u32(b), 0); };
       for (int p2 = 0; p2 < 2 * total; ++p2) {
-        const int s = p2 % S2, c = (p2 >> 1) % NCH, h = p2 & 1;
+        const int s = p2 % S2, c = (p2 >> 1) % NCH, h = p2 & 1, tu = (p2 >> 1) / NCH;
+        if (c == 0 && h == 0 && tu > 0) mbar_wait(lnfree, (tu - 1) & 1);      // the epilogue stages its residual pieces in this ring
         mbar_wait(&r2empty[s], ((p2 / S2) & 1) ^ 1);
         TR(1, p2 >> 1, 2 * h);
         if (leader) mbar_arrive_expect_tx(&r2full[s], 2 * T::R2_UNIT);
@@ -325,9 +303,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int part = wgp;                                // which third of the columns this warp owns in the epilogue
     const uint32_t tacc = tmem + (uint32_t(quad * 32) << 16);
     const int row = quad * 32 + lane;
-    uint8_t* stage = hs + (part * 4 + quad) * 2048;
     const Geo geo = make_geo(a.Z, a.H, a.W);
-    const int pc = lane & 3;                             // 16 B piece of a 64 B row segment handled by this lane in phase B
     for (int tu = 0; tu < my_units; ++tu) {
       {
         for (int c = wgp; c < NCH; c += 3) {
@@ -379,21 +355,33 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       }
       // ------------------------------ LayerNorm + residual epilogue of tile tu ------------------------------
-      // Three warps per TMEM lane quadrant (thread = row).  Statistics: each warp sums its third of the 384 columns, the
-      // partial sums meet in shared memory.  Then the warp walks four of the twelve 32-column blocks: accumulator ->
-      // registers -> normalise -> add to the fp32 residual block that TMA put into X slab b % 6 (in place, row per lane,
-      // conflict-free under SWIZZLE_128B) -> TMA store of the warp's [32 x 32] piece; the 16-bit shadow goes through a
-      // swizzled [32 x 64 B] tile in the idle H buffers so that its global stores are 64 B row segments (4 lanes per row).
+      // Three warps per TMEM lane quadrant (thread = row), each owns 128 of the 384 columns.  Statistics: partial sums meet in
+      // shared memory.  Then the warp walks its columns in eight 16-column pieces: the [32 x 16] fp32 residual piece comes by
+      // TMA (SWIZZLE_64B, two buffers per warp, fetched by the warp's own lane 0), accumulator -> registers -> normalise -> add
+      // in place (row per lane, conflict-free) -> TMA store; the 16-bit shadow goes through a swizzled [32 x 32 B] tile so
+      // that its global stores are 32 B row segments (2 lanes per row, window scatter).  All of this is staged in the W2 ring
+      // and the H buffers, which are idle exactly from "Y complete" to "Y drained" -- NOT in the X slabs: the next tile's X
+      // load and its first two GEMM1 chunks run under this epilogue (staging in the X slabs cost 5 600 clk per tile for the X
+      // tile alone).
       const int tile = 2 * (pair + tu * num_pairs) + cta_rank;
-      const int g = tile * 128 + quad * 32 + lane;
+      const int row0 = tile * 128 + quad * 32;
+      const int g = row0 + lane;
       const int my_tok = g < a.T ? g : -1;
       const int my_dst = (my_tok >= 0 && a.roll_out >= 0) ? token_to_win_row(geo, my_tok, a.roll_out) : my_tok;
-      int dsts[4];         // shadow rows of this lane's phase-B items: row rr = it * 8 + (lane >> 2)
+      int dsts[2];         // shadow rows of this lane's phase-B items: row rr = it * 16 + (lane >> 1)
 #pragma unroll
-      for (int it = 0; it < 4; ++it) dsts[it] = __shfl_sync(0xffffffffu, my_dst, it * 8 + (lane >> 2));
+      for (int it = 0; it < 2; ++it) dsts[it] = __shfl_sync(0xffffffffu, my_dst, it * 16 + (lane >> 1));
+      const int wslot = warp - 3;
+      uint8_t* stg = r2 + wslot * 6144;            // 2 x 2 KB residual pieces + 2 KB shadow tile
+      uint64_t* rf = rfb + 2 * wslot;
+      auto fetch = [&](int j) {                     // lane 0
+        mbar_arrive_expect_tx(&rf[j & 1], 2048);
+        tma_load_2d(&tmR, &rf[j & 1], stg + (j & 1) * 2048, 128 * part + 16 * j, row0);      // rows >= T read as zero
+      };
       warp_wait(yfull, tu & 1);
       if (lane == 0 && warp == 6) TR(6, tu * 8, 0);
       tc_fence_after();
+      if (lane == 0 && !(dbg & 4)) { fetch(0); fetch(1); }
       float mean = 0.f, rstd = 0.f;
       if (!(dbg & 4)) {
         uint32_t r0;
@@ -430,83 +418,78 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mean = shift + m;
         rstd = rsqrtf(var + a.eps);
       }
+      if (lane == 0 && warp == 6) TR(6, tu * 8 + 1, 0);
       const f32x2 ln_a = pack2(rstd, rstd), ln_b = pack2(-mean * rstd, -mean * rstd);
       const f32x2 rs2 = pack2(a.res_scale, a.res_scale);
+      uint8_t* shd = stg + 4096;
 #pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        const int b = part + 3 * i, k = part + 3 * (i & 1);      // column block, X slab that holds its residual rows
-        uint8_t* srow = xs + k * 16384 + row * 128;
-        if (lane == 0 && warp == 6) TR(6, tu * 8 + 1 + i, 0);
-        warp_wait(&rfull[k], i >> 1);
-        if (lane == 0 && warp == 6) TR(6, tu * 8 + 1 + i, 1);
-        if (!(dbg & 4)) {
-          uint32_t r[32];
-          tmem_ld32(tacc + 32 * b, r);
-          tmem_ld_wait();
-          if (i == 3) {          // this warp has read the accumulator for the last time: hand Y back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (leader) mbar_arrive(yempty); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(yempty), 0));
-            }
+      for (int j = 0; j < 8; ++j) {
+        const int c0 = 128 * part + 16 * j;
+        uint8_t* buf = stg + (j & 1) * 2048;
+        if (dbg & 4) {
+          if (j == 7 && lane == 0) {
+            if (leader) mbar_arrive(yempty); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(yempty), 0));
           }
-          if (lane == 0 && warp == 6) TR(7, tu * 8 + 1 + i, 0);
-          const float4* b4 = reinterpret_cast<const float4*>(s_b2 + 32 * b);
-          const float4* g4 = reinterpret_cast<const float4*>(s_gamma + 32 * b);
-          const float4* e4 = reinterpret_cast<const float4*>(s_beta + 32 * b);
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = b4[j], gg = g4[j], ee = e4[j];
-            uint4* cell = reinterpret_cast<uint4*>(srow + ((j ^ (row & 7)) << 4));
-            const uint4 q = *cell;
-            f32x2 v01 = add2(pack2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), pack2(bb.x, bb.y));
-            f32x2 v23 = add2(pack2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), pack2(bb.z, bb.w));
-            v01 = fma2(fma2(v01, ln_a, ln_b), pack2(gg.x, gg.y), pack2(ee.x, ee.y));
-            v23 = fma2(fma2(v23, ln_a, ln_b), pack2(gg.z, gg.w), pack2(ee.z, ee.w));
-            v01 = fma2(rs2, v01, pack2(__uint_as_float(q.x), __uint_as_float(q.y)));
-            v23 = fma2(rs2, v23, pack2(__uint_as_float(q.z), __uint_as_float(q.w)));
-            float f0, f1, f2, f3;
-            unpack2(v01, f0, f1);
-            unpack2(v23, f2, f3);
-            *cell = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3));
-            pk[2 * j] = pack16<kFp16>(f0, f1);
-            pk[2 * j + 1] = pack16<kFp16>(f2, f3);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          if (lane == 0 && warp == 6) TR(7, tu * 8 + 1 + i, 1);
-          fence_proxy_async_smem();
-          if (lane == 0 && warp == 6) TR(7, tu * 8 + 1 + i, 2);
-        } else if (i == 3 && lane == 0) {
-          if (leader) mbar_arrive(yempty); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(yempty), 0));
+          continue;
         }
+        warp_wait(&rf[j & 1], (tu * 4 + (j >> 1)) & 1);        // each buffer is filled four times per tile
+        uint32_t r[16];
+        tmem_ld16(tacc + c0, r);
+        tmem_ld_wait();
+        if (j == 7) {          // this warp has read the accumulator for the last time: hand Y back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(yempty); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(yempty), 0));
+          }
+        }
+        const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
+        const float4* g4 = reinterpret_cast<const float4*>(s_gamma + c0);
+        const float4* e4 = reinterpret_cast<const float4*>(s_beta + c0);
+        uint32_t pk[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 bb = b4[q], gg = g4[q], ee = e4[q];
+          uint4* cell = reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
+          const uint4 x = *cell;
+          f32x2 v01 = add2(pack2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), pack2(bb.x, bb.y));
+          f32x2 v23 = add2(pack2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), pack2(bb.z, bb.w));
+          v01 = fma2(fma2(v01, ln_a, ln_b), pack2(gg.x, gg.y), pack2(ee.x, ee.y));
+          v23 = fma2(fma2(v23, ln_a, ln_b), pack2(gg.z, gg.w), pack2(ee.z, ee.w));
+          v01 = fma2(rs2, v01, pack2(__uint_as_float(x.x), __uint_as_float(x.y)));
+          v23 = fma2(rs2, v23, pack2(__uint_as_float(x.z), __uint_as_float(x.w)));
+          float f0, f1, f2, f3;
+          unpack2(v01, f0, f1);
+          unpack2(v23, f2, f3);
+          *cell = make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3));
+          pk[2 * q] = pack16<kFp16>(f0, f1);
+          pk[2 * q + 1] = pack16<kFp16>(f2, f3);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          *reinterpret_cast<uint4*>(shd + lane * 32 + ((h ^ ((lane >> 2) & 1)) << 4)) =
+              make_uint4(pk[4 * h], pk[4 * h + 1], pk[4 * h + 2], pk[4 * h + 3]);
+        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && !(dbg & 4)) {       // rows >= T are clipped by the tensor map
-          tma_store_2d(&tmR, xs + k * 16384 + quad * 4096, 32 * b, tile * 128 + quad * 32);
+        if (lane == 0) {       // rows >= T are clipped by the tensor map
+          tma_store_2d(&tmR, buf, c0, row0);
           bulk_commit();
         }
-        if (lane == 0 && warp == 6) TR(7, tu * 8 + 1 + i, 3);
-        if (!(dbg & 4)) {
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            if (dsts[it] < 0) continue;
-            const int rr = it * 8 + (lane >> 2);
-            const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4));
-            stg16(reinterpret_cast<uint16_t*>(a.out16) + size_t(dsts[it]) * C + 32 * b + pc * 8, v);
-          }
+        for (int it = 0; it < 2; ++it) {
+          if (dsts[it] < 0) continue;
+          const int rr = it * 16 + (lane >> 1), pcc = lane & 1;
+          const uint4 v = *reinterpret_cast<const uint4*>(shd + rr * 32 + ((pcc ^ ((rr >> 2) & 1)) << 4));
+          stg16(reinterpret_cast<uint16_t*>(a.out16) + size_t(dsts[it]) * C + c0 + pcc * 8, v);
         }
-        if (lane == 0 && warp == 6) TR(6, tu * 8 + 1 + i, 2);
         if (lane == 0) {
-          bulk_wait_read<0>();               // the store has read the slab piece: it may be overwritten
-          mbar_arrive(&rfree[k]);
+          bulk_wait_read<0>();               // the store has read the piece: its buffer may be refilled
+          if (j + 2 < 8) fetch(j + 2);
         }
-        if (lane == 0 && warp == 6) TR(6, tu * 8 + 1 + i, 3);
-        __syncwarp();                        // the shadow tile is rewritten by the next block
+        __syncwarp();                        // the shadow tile is rewritten by the next piece
       }
-      if (lane == 0) mbar_arrive(lnfree);           // this warp no longer touches the H buffers (the block loop ends in a __syncwarp)
+      if (lane == 0 && warp == 6) TR(6, tu * 8 + 1, 1);
+      if (lane == 0) mbar_arrive(lnfree);           // this warp no longer touches the W2 ring / H buffers (the piece loop ends in a __syncwarp)
     }
   }
 
