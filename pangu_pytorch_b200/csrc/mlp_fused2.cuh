@@ -432,7 +432,9 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           }
           continue;
         }
+        if (lane == 0 && warp == 6 && tu == 0) TR(7, j, 0);
         warp_wait(&rf[j & 1], (tu * 4 + (j >> 1)) & 1);        // each buffer is filled four times per tile
+        if (lane == 0 && warp == 6 && tu == 0) TR(7, j, 1);
         uint32_t r[16];
         tmem_ld16(tacc + c0, r);
         tmem_ld_wait();
@@ -469,12 +471,14 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int h = 0; h < 2; ++h)
           *reinterpret_cast<uint4*>(shd + lane * 32 + ((h ^ ((lane >> 2) & 1)) << 4)) =
               make_uint4(pk[4 * h], pk[4 * h + 1], pk[4 * h + 2], pk[4 * h + 3]);
+        if (lane == 0 && warp == 6 && tu == 0) TR(7, j, 2);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {       // rows >= T are clipped by the tensor map
           tma_store_2d(&tmR, buf, c0, row0);
           bulk_commit();
         }
+        if (lane == 0 && warp == 6 && tu == 0) TR(7, j, 3);
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
           if (dsts[it] < 0) continue;
@@ -482,10 +486,12 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const uint4 v = *reinterpret_cast<const uint4*>(shd + rr * 32 + ((pcc ^ ((rr >> 2) & 1)) << 4));
           stg16(reinterpret_cast<uint16_t*>(a.out16) + size_t(dsts[it]) * C + c0 + pcc * 8, v);
         }
+        if (lane == 0 && warp == 6 && tu == 0) TR(7, 8 + j, 0);
         if (lane == 0) {
           bulk_wait_read<0>();               // the store has read the piece: its buffer may be refilled
           if (j + 2 < 8) fetch(j + 2);
         }
+        if (lane == 0 && warp == 6 && tu == 0) TR(7, 8 + j, 1);
         __syncwarp();                        // the shadow tile is rewritten by the next piece
       }
       if (lane == 0 && warp == 6) TR(6, tu * 8 + 1, 1);
