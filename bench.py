@@ -654,5 +654,15 @@ def main():
         run_gpu_arm(args)
 
 
+def _only_the_json_line_on_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on rank 0 when the
+    box sets NCCL_DEBUG=VERSION): point fd 1 at stderr for the whole run and give ``print`` the real stdout back."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _only_the_json_line_on_stdout()
     main()
