@@ -17,8 +17,8 @@
 // GEMM1 work queued while the GELU warps are busy; the tensor pipe executes in issue order, which is what
 // makes the in-place reuse of the Hacc buffers safe (G2(c) has read H(c) before G1(c+NB) overwrites it).
 // TMEM: Y [0,C) then NB Hacc buffers of 64 columns (C=192: 4 buffers, C=384: 2).
-// Warps (640 threads): 0 TMA producer (X, W1), 1 GEMM1 issuer, 2 GEMM2 issuer, 3-6 LayerNorm epilogue (one per TMEM lane
-// quadrant), 7-18 GELU (three warpgroups take the chunks in turn), 19 TMA producer (W2).
+// Warps (448 threads): 0 TMA producer, 1 MMA issuer, 2-5 LayerNorm epilogue (one per TMEM lane quadrant),
+// 6-13 GELU (two warpgroups alternate chunks).
 #pragma once
 #include "common.cuh"
 #include "geometry.cuh"
@@ -60,14 +60,11 @@ struct MlpTraits {
   static constexpr int OFF_SLAB = OFF_H + NHS * 16384;
   static constexpr int LNW = 4;                                   // LayerNorm epilogue warps (a second warpgroup alternating tiles
                                                                   // was measured slower: 543 vs 508 us at C=192)
-  static constexpr int GELU_WARPS = 12;                           // three warpgroups take the chunks in turn (two were the pace-setter:
-                                                                  // ~2 800 clk per chunk and warpgroup against 960 clk of MMA work)
-  static constexpr int THREADS = 32 * (3 + LNW + GELU_WARPS + 1); // TMA (X, W1), GEMM1 issuer, GEMM2 issuer, LayerNorm warps, GELU warps, TMA (W2)
+  static constexpr int THREADS = 32 * (3 + LNW + 8 + 1);          // TMA (X, W1), GEMM1 issuer, GEMM2 issuer, LayerNorm warps, 8 GELU warps, TMA (W2)
   static constexpr int OFF_PAR = OFF_SLAB + LNW * SLAB_BYTES;     // b1 [4C], b2 / gamma / beta [C] fp32
   static constexpr int OFF_TAB = OFF_PAR + 7 * C * 4;             // LNW warps x 64 ints
   static constexpr int OFF_BAR = OFF_TAB + LNW * 64 * 4;
-  static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + (6 + NB) + (NHS + 6) + 2 * YB + 2 * LNW;
-  static_assert(NCH % 6 == 0, "three GELU warpgroups x two buffers");
+  static constexpr int NUM_BARS = 2 * KX + 2 * S1 + 2 * S2 + 2 * NB + 2 * NHS + 2 * YB + 2 * LNW;
   static constexpr int SMEM_BYTES = 1024 + OFF_BAR + ((NUM_BARS * 8 + 16 + 127) / 128) * 128;
   static_assert(C == 192, "the single-kernel Mlp is built for C = 192 (at C = 384 neither TMEM nor shared memory has room)");
   static_assert(OFF_R1 % 1024 == 0 && OFF_R2 % 1024 == 0 && OFF_SLAB % (RES_TMA ? 1024 : 512) == 0, "operand alignment");
@@ -145,14 +142,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* r1empty = r1full + S1;             // [S1]  count 2: tcgen05.commit of both CTAs of the pair
   uint64_t* r2full = r1empty + S1;             // [S2]
   uint64_t* r2empty = r2full + S2;             // [S2]  count 2
-  // hfull / sempty are waited for by the GELU warpgroups, which rotate over the chunks (chunk c -> warpgroup c % 3) while the
-  // buffers alternate (c % 2): one barrier per c % 6, so that a barrier always has the same waiting warpgroup and a parity
-  // wait can never be more than one phase behind.
-  uint64_t* hfull = r2empty + S2;              // [6]   Hacc[c % 2] holds chunk c (GEMM1 done)
-  uint64_t* hempty = hfull + 6;                // [NB]  Hacc loaded into registers by the 4 GELU warps of the chunk's warpgroup
+  uint64_t* hfull = r2empty + S2;              // [NB]  Hacc ready (GEMM1 done)
+  uint64_t* hempty = hfull + NB;               // [NB]  Hacc loaded into registers by the 4 GELU warps of its warpgroup
   uint64_t* sfull = hempty + NB;               // [NHS] H (16-bit, K-major SWIZZLE_128B) written to shared memory by 4 warps
-  uint64_t* sempty = sfull + T::NHS;           // [6]   GEMM2 of chunk c has read H[c % 2]
-  uint64_t* yfull = sempty + 6;                // [YB]  Y complete
+  uint64_t* sempty = sfull + T::NHS;           // [NHS] GEMM2 has read the H buffer
+  uint64_t* yfull = sempty + T::NHS;           // [YB]  Y complete
   uint64_t* yempty = yfull + YB;               // [YB]  Y drained by the 4 epilogue warps
   uint64_t* rfull = yempty + YB;               // [LNW][2] residual tile landed (RES_TMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2 * T::LNW);
@@ -170,9 +164,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int k = 0; k < KX; ++k) { mbar_init(&xfull[k], 1); mbar_init(&xempty[k], 1); }
     for (int s = 0; s < S1; ++s) { mbar_init(&r1full[s], 1); mbar_init(&r1empty[s], T::MCAST ? 2 : 1); }
     for (int s = 0; s < S2; ++s) { mbar_init(&r2full[s], 1); mbar_init(&r2empty[s], T::MCAST ? 2 : 1); }
-    for (int b = 0; b < 6; ++b) { mbar_init(&hfull[b], 1); mbar_init(&sempty[b], 1); }
-    for (int b = 0; b < NB; ++b) mbar_init(&hempty[b], 4);
-    for (int b = 0; b < T::NHS; ++b) mbar_init(&sfull[b], 4);
+    for (int b = 0; b < NB; ++b) { mbar_init(&hfull[b], 1); mbar_init(&hempty[b], 4); }
+    for (int b = 0; b < T::NHS; ++b) { mbar_init(&sfull[b], 4); mbar_init(&sempty[b], 1); }
     for (int y = 0; y < YB; ++y) { mbar_init(&yfull[y], 1); mbar_init(&yempty[y], 4); }
     for (int i = 0; i < 2 * T::LNW; ++i) mbar_init(&rfull[i], 1);
     fence_barrier_init();
@@ -237,7 +230,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       (void)xuse;
     }
-  } else if (warp == 3 + T::LNW + T::GELU_WARPS) {
+  } else if (warp == 3 + T::LNW + 8) {
     // ================================ TMA producer of the W2 ring ================================
     // Its own warp: with one in-order thread for both rings a W2 unit that waited for GEMM2(c - 1) held back W1(c + 2),
     // which closed a loop GEMM2 -> W2 -> W1 -> GEMM1 -> GELU -> GEMM2 over several chunks (see mlp_fused2.cuh).
@@ -294,7 +287,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (c_in_tile == NCH - 1) {
           for (int k = 0; k < KX; ++k) umma_commit(&xempty[k]);     // last reader of the X slabs
         }
-        umma_commit(&hfull[cgx % 6]);
+        umma_commit(&hfull[hb]);
         TR(2, cgx, 2);
       }
       __syncwarp();
@@ -321,7 +314,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int kk = 0; kk < 4; ++kk)     // K = 64 hidden units
             umma_f16_ss(tmem + yb * C + h * 192, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc2, (c_in_tile | kk) != 0 ? 1u : 0u);
           if constexpr (T::MCAST) umma_commit_mcast(&r2empty[s], uint16_t(3)); else umma_commit(&r2empty[s]);
-          if (h == NH - 1) umma_commit(&sempty[cgx % 6]);
+          if (h == NH - 1) umma_commit(&sempty[sb]);
           if (c_in_tile == NCH - 1 && h == NH - 1) umma_commit(&yfull[yb]);
           TR(3, cgx, 3);
         }
@@ -480,31 +473,28 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   } else {
     // ================================ GELU warps ================================
-    // Three warpgroups take the chunks in turn (chunk c -> warpgroup c % 3, Hacc / H buffer c % 2).  A warp pulls the fp32
+    // Warpgroup w owns the chunks with (global chunk index & 1) == w, Hacc buffer w and H buffer w.  It pulls the fp32
     // accumulator into registers and hands the TMEM buffer straight back (GEMM1 of chunk c + 2 may start), applies
     // bias + GELU and writes the 16-bit H tile to shared memory as the K-major SWIZZLE_128B A operand of GEMM2.
-    const int quad = warp & 3, wgp = (warp - (3 + T::LNW)) >> 2;     // warpgroup 0..2
+    const int quad = warp & 3, wgp = (warp - (3 + T::LNW)) >> 2;
+    const uint32_t haddr = tmem + (uint32_t(quad * 32) << 16) + T::COL_H + 64 * wgp;
     const int row = quad * 32 + lane;
-    int tuse = 0;
-    for (int unit = pair; unit < num_units; unit += num_pairs, ++tuse) {
-      for (int c = wgp; c < NCH; c += 3) {
-        const int hb = c & 1;                        // NCH is even: buffer index and use count follow from the chunk number
-        const int cgx = tuse * NCH + c;
-        const uint32_t haddr = tmem + (uint32_t(quad * 32) << 16) + T::COL_H + 64 * hb;
-        uint8_t* hrow = hs + hb * 16384 + row * 128;
-        const int n = cgx >> 1;
-        warp_wait(&hfull[c % 6], (cgx / 6) & 1);
-        if (lane == 0 && quad == 3) TR(4 + hb, cgx, 0);
+    uint8_t* hrow = hs + wgp * 16384 + row * 128;
+    int n = 0;           // chunks this warpgroup has processed
+    for (int unit = pair; unit < num_units; unit += num_pairs) {
+      for (int c = wgp; c < NCH; c += 2, ++n) {
+        warp_wait(&hfull[wgp], n & 1);
+        if (lane == 0 && quad == 3) TR(4 + wgp, 2 * n + wgp, 0);
         tc_fence_after();
         uint32_t r[2][32];
         tmem_ld32(haddr, r[0]);
         tmem_ld32(haddr + 32, r[1]);
         tmem_ld_wait();
-        if (lane == 0 && quad == 3 && hb == 0) TR(7, n, 0);
+        if (lane == 0 && quad == 3 && wgp == 0) TR(7, n, 0);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&hempty[hb]);       // one arrival per warp: all its lanes hold their Hacc values
-        if (lane == 0 && quad == 3 && hb == 0) TR(7, n, 1);
+        if (lane == 0) mbar_arrive(&hempty[wgp]);      // one arrival per warp: all its lanes hold their Hacc values
+        if (lane == 0 && quad == 3 && wgp == 0) TR(7, n, 1);
         uint32_t pk[32];
         const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 64);
 #pragma unroll
@@ -521,18 +511,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int q = 0; q < 4; ++q) pk[hh * 16 + 4 * j8 + q] = pack16<kFp16>(v[2 * q], v[2 * q + 1]);
           }
         }
-        if (lane == 0 && quad == 3) TR(4 + hb, cgx, 1);
-        if (cgx >= 2) warp_wait(&sempty[(cgx - 2) % 6], ((cgx - 2) / 6) & 1);      // GEMM2 of chunk c - 2 has read the buffer
-        if (lane == 0 && quad == 3) TR(4 + hb, cgx, 2);
-        if (lane == 0 && quad == 3 && hb == 0) TR(7, n, 2);
+        if (lane == 0 && quad == 3) TR(4 + wgp, 2 * n + wgp, 1);
+        warp_wait(&sempty[wgp], (n & 1) ^ 1);        // GEMM2 of this warpgroup's previous chunk has read the buffer
+        if (lane == 0 && quad == 3) TR(4 + wgp, 2 * n + wgp, 2);
+        if (lane == 0 && quad == 3 && wgp == 0) TR(7, n, 2);
 #pragma unroll
         for (int q = 0; q < 8; ++q)                  // 8 x 16 B = this row's 64 hidden units, XOR-swizzled 16 B chunks
           *reinterpret_cast<uint4*>(hrow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        if (lane == 0 && quad == 3 && hb == 0) TR(7, n, 3);
+        if (lane == 0 && quad == 3 && wgp == 0) TR(7, n, 3);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sfull[hb]);        // one arrival per warp: its 32 rows of H are visible to the async proxy
-        if (lane == 0 && quad == 3) TR(4 + hb, cgx, 3);
+        if (lane == 0) mbar_arrive(&sfull[wgp]);       // one arrival per warp: its 32 rows of H are visible to the async proxy
+        if (lane == 0 && quad == 3) TR(4 + wgp, 2 * n + wgp, 3);
       }
     }
   }
