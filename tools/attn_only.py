@@ -8,7 +8,7 @@ import torch
 import pangu_pytorch_b200 as pb
 from pangu_pytorch_b200 import engine, ops, _lib
 
-if os.environ.get('ATTN_TRACE') or os.environ.get('PANGU_B200_ATTN_DEBUG'):     # development build with the trace hooks compiled in (tools/bin, see README of tools)
+if os.environ.get('ATTN_TRACE') or os.environ.get('PANGU_B200_ATTN_DEBUG'):     # development build with the trace hooks compiled in (tools/bin, see tools/README.md)
     _lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin", "libpangu_b200_dev.so")
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "hi"
