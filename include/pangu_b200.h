@@ -89,8 +89,9 @@ int pangu_proj_ln_residual(const void* att16, const void* w16 /*[C,C]*/, const f
 
 /* Mlp.forward + norm2 + residual (models/layers.py:264-270, 251):
  *   x32 += res_scale * LN2(GELU(x W1^T + b1) W2^T + b2)      (exact erf GELU)
- * x16_in natural order.  ws_hidden [T, 4C]: receives the 16-bit GELU activations (the training tape keeps them); NULL at
- * C = 192: the activation is not materialised -- one kernel keeps it in tensor memory (C = 384 needs the workspace).
+ * x16_in natural order.  ws_hidden [T, 4C]: receives the 16-bit GELU activations (the training tape keeps them); NULL:
+ * the activation is not materialised -- one kernel keeps it on the SM (C = 192: mlp_fused_kernel, C = 384: the CTA-pair
+ * mlp_fused2_kernel).  All device pointers 16 B aligned.
  * x16_out: 16-bit copy of the new
  * residual stream, in natural order when roll_out < 0, else in window order for a following
  * block with roll state roll_out (pad rows never written). */
