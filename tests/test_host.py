@@ -241,3 +241,17 @@ def test_add_lora_wraps_67_linears_and_round_trips():
         _ = w.weight
     w.eval()
     assert w.weight.shape == (8, 8)
+
+
+def test_bench_stdout_carries_only_the_json_line():
+    """bench.py's contract is ONE JSON line on stdout; library chatter written to fd 1 (NCCL's version banner on rank 0)
+    must end up on stderr."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench._only_the_json_line_on_stdout(); "
+            "os.write(1, b'NCCL version banner\\n'); print('{\"ok\": 1}')" % root)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout.strip() == '{"ok": 1}'
+    assert "NCCL version banner" in res.stderr
